@@ -1,0 +1,517 @@
+// mppi_api.cu — C ABI of the MPPI controller (mpcb_mppi_*), replacing mpc::mppi::Mppi (src/mppi.rs:7-92).
+#include <dlfcn.h>
+#include <math.h>
+
+#include <new>
+
+#include "mppi_kernel.cuh"
+#include "nccl_shim.h"
+
+using namespace mpcb;
+
+struct mpcb_mppi {
+    mpcb_mppi_cfg cfg;
+    cudaStream_t stream = nullptr;
+    int num_sms = 0;
+    long long K_local = 0, k_offset = 0;
+    int H = 0, C = 0, PL = 0;
+    int block = 0, chunks = 0, group_size = 0, groups = 0;
+    long long batches_per_chunk = 0;
+    size_t smem = 0;
+    ModelConsts mc;
+    MppiKernelFn k_noise[3] = {nullptr, nullptr, nullptr};  // indexed by MppiNoise
+    // device
+    double* d_x = nullptr;
+    double* d_u = nullptr;
+    double* d_u_out = nullptr;
+    double* d_partial = nullptr;
+    double* d_rank_partial = nullptr;
+    double* d_gather = nullptr;
+    unsigned int* d_counters = nullptr;
+    mpcb_mppi_info* d_info = nullptr;
+    double* d_costs = nullptr;
+    void* d_eps = nullptr;
+    size_t d_eps_bytes = 0;
+    void* d_dump = nullptr;
+    // pinned / mapped host
+    double* h_in = nullptr;              // [C][4] then [C][H]
+    double* h_out = nullptr;             // mapped: [C][H]
+    double* h_out_dev = nullptr;         // device alias of h_out
+    mpcb_mppi_info* h_info = nullptr;    // mapped: [C]
+    mpcb_mppi_info* h_info_dev = nullptr;
+    bool costs_valid = false;
+    uint32_t call_idx = 0;
+    int64_t launches = 0;
+    // NCCL
+    void* comm = nullptr;
+};
+
+namespace {
+
+size_t elt_size(const mpcb_mppi* h) { return h->cfg.precision == MPCB_F64 ? sizeof(double) : sizeof(float); }
+
+mpcb_status pick_kernels(mpcb_mppi* h) {
+    const bool f64 = h->cfg.precision == MPCB_F64;
+    cudaDeviceProp prop;
+    MPCB_CUDA_TRY(cudaGetDeviceProperties(&prop, h->cfg.device));
+    h->num_sms = prop.multiProcessorCount;
+    const size_t smem_max = prop.sharedMemPerBlockOptin;
+    const int blocks[3] = {128, 64, 32};
+    for (int b : blocks) {
+        const size_t need = f64 ? mppi_smem_bytes<double>(h->H, b) : mppi_smem_bytes<float>(h->H, b);
+        if (need + 1024 <= smem_max) {  // 1 KB reserved per block by the driver
+            h->block = b;
+            h->smem = need;
+            break;
+        }
+    }
+    if (h->block == 0) {
+        set_error("horizon %d needs more shared memory than one SM has", h->H);
+        return MPCB_BAD_ARG;
+    }
+    for (int noise = 0; noise < 3; ++noise) {
+        h->k_noise[noise] = f64 ? mppi_kernel_f64(h->cfg.model_id, h->block, noise) : mppi_kernel_f32(h->cfg.model_id, h->block, noise);
+        if (!h->k_noise[noise]) {
+            set_error("no MPPI kernel for model %d", h->cfg.model_id);
+            return MPCB_BAD_ARG;
+        }
+        MPCB_CUDA_TRY(cudaFuncSetAttribute((const void*)h->k_noise[noise], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)h->smem));
+    }
+    int occ = 0;
+    MPCB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)h->k_noise[NOISE_GENERATE], h->block, h->smem));
+    if (occ < 1) occ = 1;
+    const long long resident = (long long)occ * h->num_sms;
+    const long long nbatches = (h->K_local + h->block - 1) / h->block;
+    long long per_ctrl = resident / h->C;
+    if (per_ctrl < 1) per_ctrl = 1;
+    if (per_ctrl > nbatches) per_ctrl = nbatches;
+    h->batches_per_chunk = (nbatches + per_ctrl - 1) / per_ctrl;
+    if (per_ctrl > kMergeFan * kMergeFan) per_ctrl = kMergeFan * kMergeFan;
+    h->batches_per_chunk = (nbatches + per_ctrl - 1) / per_ctrl;
+    h->chunks = (int)((nbatches + h->batches_per_chunk - 1) / h->batches_per_chunk);
+    // two-level merge tree with fan-in <= kMergeFan
+    if (h->chunks <= kMergeFan) {
+        h->group_size = h->chunks;
+        h->groups = 1;
+    } else {
+        int gs = (int)ceil(sqrt((double)h->chunks));
+        if (gs > kMergeFan) gs = kMergeFan;
+        h->group_size = gs;
+        h->groups = (h->chunks + gs - 1) / gs;
+    }
+    return MPCB_OK;
+}
+
+void fill_params(const mpcb_mppi* h, MppiParams* p) {
+    memset(p, 0, sizeof(*p));
+    p->H = h->H;
+    p->C = h->C;
+    p->chunks = h->chunks;
+    p->group_size = h->group_size;
+    p->groups = h->groups;
+    p->K_local = h->K_local;
+    p->K_global = h->cfg.samples;
+    p->k_offset = h->k_offset;
+    p->batches_per_chunk = h->batches_per_chunk;
+    p->seed_lo = (unsigned int)(h->cfg.seed & 0xffffffffull);
+    p->seed_hi = (unsigned int)(h->cfg.seed >> 32);
+    p->call_idx = h->call_idx;
+    p->lambda = h->cfg.lambda;
+    p->inv_var = 1.0 / (h->cfg.std_dev * h->cfg.std_dev);  // std_dev.powi(-2), src/mppi.rs:48
+    p->lo = h->cfg.limit_lo;
+    p->hi = h->cfg.limit_hi;
+    p->std_dev = h->cfg.std_dev;
+    p->partial = h->d_partial;
+    p->counters = h->d_counters;
+    p->u_out = h->d_u_out;
+    p->info = h->d_info;
+    p->rank_partial = h->d_rank_partial;
+    p->mc = h->mc;
+    p->costs = h->cfg.keep_costs ? h->d_costs : nullptr;
+}
+
+// Enqueue one fused control step.
+mpcb_status launch(mpcb_mppi* h, MppiParams& p) {
+    const int noise = p.eps != nullptr ? NOISE_REPLAY : (p.eps_dump != nullptr ? NOISE_GENERATE_DUMP : NOISE_GENERATE);
+    MppiKernelFn fn = h->k_noise[noise];
+    const dim3 grid((unsigned)(h->C * h->chunks)), block((unsigned)h->block);
+    fn<<<grid, block, h->smem, h->stream>>>(p);
+    MPCB_CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    h->call_idx += 1;
+    h->costs_valid = h->cfg.keep_costs != 0;
+    return MPCB_OK;
+}
+
+mpcb_status ensure_eps(mpcb_mppi* h, size_t bytes) {
+    if (h->d_eps_bytes >= bytes) return MPCB_OK;
+    if (h->d_eps) MPCB_CUDA_TRY(cudaFree(h->d_eps));
+    h->d_eps = nullptr;
+    h->d_eps_bytes = 0;
+    MPCB_CUDA_TRY(cudaMalloc(&h->d_eps, bytes));
+    h->d_eps_bytes = bytes;
+    return MPCB_OK;
+}
+
+// Stages host x/u_in: inline in the kernel parameters for the single-controller case, else one pinned H2D copy.
+mpcb_status stage_inputs(mpcb_mppi* h, MppiParams& p, const double* x, const double* u_in) {
+    const size_t nx = (size_t)h->C * 4, nu = (size_t)h->C * h->H;
+    if (h->C == 1 && h->H <= kInlineHorizon) {
+        p.use_inline = 1;
+        memcpy(p.xu_inline, x, 4 * sizeof(double));
+        memcpy(p.xu_inline + 4, u_in, (size_t)h->H * sizeof(double));
+        return MPCB_OK;
+    }
+    memcpy(h->h_in, x, nx * sizeof(double));
+    memcpy(h->h_in + nx, u_in, nu * sizeof(double));
+    MPCB_CUDA_TRY(cudaMemcpyAsync(h->d_x, h->h_in, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    MPCB_CUDA_TRY(cudaMemcpyAsync(h->d_u, h->h_in + nx, nu * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    p.x = h->d_x;
+    p.u = h->d_u;
+    return MPCB_OK;
+}
+
+// Waits for the step and hands u_out/info to the caller (results were written straight into mapped host memory).
+mpcb_status finish_host(mpcb_mppi* h, double* u_out, mpcb_mppi_info* info) {
+    MPCB_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    memcpy(u_out, h->h_out, (size_t)h->C * h->H * sizeof(double));
+    if (info) memcpy(info, h->h_info, (size_t)h->C * sizeof(mpcb_mppi_info));
+    if (h->C == 1) return (mpcb_status)h->h_info[0].status;
+    return MPCB_OK;
+}
+
+mpcb_status exchange_and_combine(mpcb_mppi* h);
+
+mpcb_status compute_host(mpcb_mppi* h, const double* x, const double* u_in, const void* d_eps, int eps_dtype,
+                         void* d_dump, double* u_out, mpcb_mppi_info* info) {
+    MPCB_REQUIRE(h && x && u_in && u_out, "null pointer");
+    MPCB_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    MppiParams p;
+    fill_params(h, &p);
+    mpcb_status st = stage_inputs(h, p, x, u_in);
+    if (st != MPCB_OK) return st;
+    p.eps = d_eps;
+    p.eps_f64 = (eps_dtype == MPCB_DT_F64);
+    p.eps_dump = d_dump;
+    const bool sharded = h->cfg.world_size > 1;
+    if (sharded) {
+        MPCB_REQUIRE(h->comm != nullptr, "world_size > 1 needs mpcb_mppi_attach_comm (or use compute_partial + combine)");
+        p.final_mode = 1;
+    } else {
+        p.u_out_host = h->h_out_dev;
+        p.info_host = h->h_info_dev;
+    }
+    st = launch(h, p);
+    if (st != MPCB_OK) return st;
+    if (sharded) {
+        st = exchange_and_combine(h);
+        if (st != MPCB_OK) return st;
+    }
+    return finish_host(h, u_out, info);
+}
+
+mpcb_status run_combine(mpcb_mppi* h, const double* rows, int G) {
+    MppiCombineParams cp;
+    cp.rows = rows;
+    cp.G = G;
+    cp.C = h->C;
+    cp.H = h->H;
+    cp.lambda = h->cfg.lambda;
+    cp.u_out = h->d_u_out;
+    cp.u_out_host = h->h_out_dev;
+    cp.info = h->d_info;
+    cp.info_host = h->h_info_dev;
+    mppi_combine_kernel<128><<<h->C, 128, 0, h->stream>>>(cp);
+    MPCB_CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    return MPCB_OK;
+}
+
+mpcb_status exchange_and_combine(mpcb_mppi* h) {
+    const size_t count = (size_t)h->C * h->PL;
+    mpcb_status st = nccl_all_gather(h->comm, h->d_rank_partial, h->d_gather, count, h->stream);
+    if (st != MPCB_OK) return st;
+    return run_combine(h, h->d_gather, h->cfg.world_size);
+}
+
+}  // namespace
+
+extern "C" {
+
+mpcb_status mpcb_mppi_default_cfg(int32_t model_id, mpcb_mppi_cfg* c) {
+    if (!c) return MPCB_BAD_ARG;
+    memset(c, 0, sizeof(*c));
+    mpcb_status st = mpcb_model_defaults(model_id, &c->model);
+    if (st != MPCB_OK) return st;
+    c->model_id = model_id;
+    c->precision = MPCB_F32;
+    c->horizon = 8;
+    c->state_dim = 4;
+    c->controllers = 1;
+    c->world_size = 1;
+    c->seed = 0x6d70632d72730001ull;
+    switch (model_id) {
+        case MPCB_MODEL_L:   // examples/mppi4.rs:8-18
+        case MPCB_MODEL_NL:  // examples/mppi4-non-liner.rs:8-18
+            c->samples = 800000;
+            c->lambda = 0.5;
+            c->std_dev = 3.0;
+            c->limit_lo = -20.0;
+            c->limit_hi = 20.0;
+            return MPCB_OK;
+        case MPCB_MODEL_NL6:  // examples/mppi4-non-liner-ukf.rs:13-24
+            c->samples = 500000;
+            c->lambda = 1.4;
+            c->std_dev = 4.0;
+            c->limit_lo = -10.0;
+            c->limit_hi = 10.0;
+            return MPCB_OK;
+        default:
+            set_error("model %d is not an MPPI model", model_id);
+            return MPCB_BAD_ARG;
+    }
+}
+
+mpcb_status mpcb_mppi_create(mpcb_mppi** out, const mpcb_mppi_cfg* cfg) {
+    MPCB_REQUIRE(out && cfg, "null pointer");
+    *out = nullptr;
+    MPCB_REQUIRE(cfg->state_dim == 4, "the built-in models have S = 4");
+    MPCB_REQUIRE(cfg->horizon >= 1 && cfg->horizon <= kMaxHorizon, "horizon out of range");
+    MPCB_REQUIRE(cfg->samples >= 1, "samples must be >= 1");
+    MPCB_REQUIRE(cfg->controllers >= 1, "controllers must be >= 1");
+    MPCB_REQUIRE(cfg->world_size >= 1 && cfg->world_size <= kMergeFan && cfg->rank >= 0 && cfg->rank < cfg->world_size,
+                 "bad rank/world_size (1..64 ranks)");
+    MPCB_REQUIRE(cfg->precision == MPCB_F32 || cfg->precision == MPCB_F64, "bad precision");
+    MPCB_REQUIRE(cfg->std_dev > 0.0 && cfg->lambda > 0.0, "std_dev and lambda must be positive");
+    MPCB_REQUIRE(cfg->limit_lo <= cfg->limit_hi, "limit.0 > limit.1");
+    int ndev = 0;
+    MPCB_CUDA_TRY(cudaGetDeviceCount(&ndev));
+    MPCB_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "no such CUDA device (this library has no CPU path)");
+    MPCB_CUDA_TRY(cudaSetDevice(cfg->device));
+
+    mpcb_mppi* h = new (std::nothrow) mpcb_mppi();
+    MPCB_REQUIRE(h != nullptr, "out of memory");
+    h->cfg = *cfg;
+    h->H = cfg->horizon;
+    h->C = cfg->controllers;
+    h->PL = kPartialHdr + h->H;
+    // contiguous shard of the global sample index
+    const long long K = cfg->samples, G = cfg->world_size, r = cfg->rank;
+    h->k_offset = K * r / G;
+    h->K_local = K * (r + 1) / G - h->k_offset;
+    mpcb_status st = MPCB_OK;
+    auto fail = [&](mpcb_status s) {
+        mpcb_mppi_destroy(h);
+        return s;
+    };
+    if (h->K_local < 1) {
+        set_error("rank %d of %d has no samples (K = %lld)", (int)r, (int)G, K);
+        return fail(MPCB_BAD_ARG);
+    }
+    st = build_model_consts(cfg->model_id, cfg->model, cfg->model.dt, &h->mc);
+    if (st != MPCB_OK) return fail(st);
+    if (cfg->model_id != MPCB_MODEL_L && cfg->model_id != MPCB_MODEL_NL && cfg->model_id != MPCB_MODEL_NL6) {
+        set_error("model %d is not an MPPI model", cfg->model_id);
+        return fail(MPCB_BAD_ARG);
+    }
+    st = pick_kernels(h);
+    if (st != MPCB_OK) return fail(st);
+
+#define TRY_OR_FAIL(expr)                                                                             \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            set_error("%s failed: %s", #expr, cudaGetErrorString(_e));                                \
+            return fail(MPCB_CUDA_ERROR);                                                             \
+        }                                                                                             \
+    } while (0)
+    TRY_OR_FAIL(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    const size_t C = h->C, H = h->H;
+    TRY_OR_FAIL(cudaMalloc(&h->d_x, C * 4 * sizeof(double)));
+    TRY_OR_FAIL(cudaMalloc(&h->d_u, C * H * sizeof(double)));
+    TRY_OR_FAIL(cudaMalloc(&h->d_u_out, C * H * sizeof(double)));
+    TRY_OR_FAIL(cudaMalloc(&h->d_partial, C * (size_t)(h->chunks + h->groups) * h->PL * sizeof(double)));
+    TRY_OR_FAIL(cudaMalloc(&h->d_rank_partial, C * h->PL * sizeof(double)));
+    TRY_OR_FAIL(cudaMalloc(&h->d_gather, (size_t)cfg->world_size * C * h->PL * sizeof(double)));
+    TRY_OR_FAIL(cudaMalloc(&h->d_counters, C * (size_t)(h->groups + 1) * sizeof(unsigned int)));
+    TRY_OR_FAIL(cudaMemset(h->d_counters, 0, C * (size_t)(h->groups + 1) * sizeof(unsigned int)));
+    TRY_OR_FAIL(cudaMalloc(&h->d_info, C * sizeof(mpcb_mppi_info)));
+    TRY_OR_FAIL(cudaMemset(h->d_info, 0, C * sizeof(mpcb_mppi_info)));
+    if (cfg->keep_costs) TRY_OR_FAIL(cudaMalloc(&h->d_costs, C * (size_t)h->K_local * sizeof(double)));
+    TRY_OR_FAIL(cudaHostAlloc(&h->h_in, C * (4 + H) * sizeof(double), cudaHostAllocDefault));
+    TRY_OR_FAIL(cudaHostAlloc(&h->h_out, C * H * sizeof(double), cudaHostAllocMapped));
+    TRY_OR_FAIL(cudaHostAlloc(&h->h_info, C * sizeof(mpcb_mppi_info), cudaHostAllocMapped));
+    memset(h->h_out, 0, C * H * sizeof(double));
+    memset(h->h_info, 0, C * sizeof(mpcb_mppi_info));
+    TRY_OR_FAIL(cudaHostGetDevicePointer((void**)&h->h_out_dev, h->h_out, 0));
+    TRY_OR_FAIL(cudaHostGetDevicePointer((void**)&h->h_info_dev, h->h_info, 0));
+#undef TRY_OR_FAIL
+    *out = h;
+    return MPCB_OK;
+}
+
+void mpcb_mppi_destroy(mpcb_mppi* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm) nccl_destroy(h->comm);
+    cudaFree(h->d_x);
+    cudaFree(h->d_u);
+    cudaFree(h->d_u_out);
+    cudaFree(h->d_partial);
+    cudaFree(h->d_rank_partial);
+    cudaFree(h->d_gather);
+    cudaFree(h->d_counters);
+    cudaFree(h->d_info);
+    cudaFree(h->d_costs);
+    cudaFree(h->d_eps);
+    cudaFree(h->d_dump);
+    if (h->h_in) cudaFreeHost(h->h_in);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->h_info) cudaFreeHost(h->h_info);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+    delete h;
+}
+
+mpcb_status mpcb_mppi_compute(mpcb_mppi* h, const double* x, const double* u_in, double* u_out, mpcb_mppi_info* info) {
+    return compute_host(h, x, u_in, nullptr, MPCB_DT_F32, nullptr, u_out, info);
+}
+
+mpcb_status mpcb_mppi_compute_replay(mpcb_mppi* h, const double* x, const double* u_in, const void* eps,
+                                     int32_t eps_dtype, int32_t eps_on_device, double* u_out, mpcb_mppi_info* info) {
+    MPCB_REQUIRE(h && eps, "null pointer");
+    MPCB_REQUIRE(eps_dtype == MPCB_DT_F32 || eps_dtype == MPCB_DT_F64, "bad eps dtype");
+    MPCB_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const void* d_eps = eps;
+    if (!eps_on_device) {
+        const size_t es = eps_dtype == MPCB_DT_F64 ? sizeof(double) : sizeof(float);
+        const size_t bytes = (size_t)h->C * (size_t)h->cfg.samples * h->H * es;
+        mpcb_status st = ensure_eps(h, bytes);
+        if (st != MPCB_OK) return st;
+        MPCB_CUDA_TRY(cudaMemcpyAsync(h->d_eps, eps, bytes, cudaMemcpyHostToDevice, h->stream));
+        d_eps = h->d_eps;
+    }
+    return compute_host(h, x, u_in, d_eps, eps_dtype, nullptr, u_out, info);
+}
+
+mpcb_status mpcb_mppi_compute_dump(mpcb_mppi* h, const double* x, const double* u_in, void* eps_out, double* u_out,
+                                   mpcb_mppi_info* info) {
+    MPCB_REQUIRE(h && eps_out, "null pointer");
+    MPCB_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const size_t bytes = (size_t)h->C * (size_t)h->K_local * h->H * elt_size(h);
+    if (!h->d_dump) MPCB_CUDA_TRY(cudaMalloc(&h->d_dump, bytes));
+    mpcb_status st = compute_host(h, x, u_in, nullptr, MPCB_DT_F32, h->d_dump, u_out, info);
+    // the noise is returned even when the controller reports a numeric failure
+    if (st == MPCB_BAD_ARG || st == MPCB_CUDA_ERROR || st == MPCB_NCCL_ERROR) return st;
+    MPCB_CUDA_TRY(cudaMemcpy(eps_out, h->d_dump, bytes, cudaMemcpyDeviceToHost));
+    return st;
+}
+
+mpcb_status mpcb_mppi_get_costs(mpcb_mppi* h, double* c_out) {
+    MPCB_REQUIRE(h && c_out, "null pointer");
+    MPCB_REQUIRE(h->cfg.keep_costs && h->costs_valid, "cfg.keep_costs was not set or nothing computed yet");
+    MPCB_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    MPCB_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    MPCB_CUDA_TRY(cudaMemcpy(c_out, h->d_costs, (size_t)h->C * h->K_local * sizeof(double), cudaMemcpyDeviceToHost));
+    return MPCB_OK;
+}
+
+mpcb_status mpcb_mppi_compute_device(mpcb_mppi* h, const double* d_x, const double* d_u_in, const void* d_eps,
+                                     int32_t eps_dtype, double* d_u_out) {
+    MPCB_REQUIRE(h && d_x && d_u_in && d_u_out, "null pointer");
+    MPCB_REQUIRE(h->cfg.world_size == 1 || h->comm != nullptr, "sharded handle needs mpcb_mppi_attach_comm");
+    MPCB_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    MppiParams p;
+    fill_params(h, &p);
+    p.x = d_x;
+    p.u = d_u_in;
+    p.eps = d_eps;
+    p.eps_f64 = (eps_dtype == MPCB_DT_F64);
+    p.u_out = d_u_out;
+    const bool sharded = h->cfg.world_size > 1;
+    p.final_mode = sharded ? 1 : 0;
+    mpcb_status st = launch(h, p);
+    if (st != MPCB_OK) return st;
+    if (sharded) {
+        st = nccl_all_gather(h->comm, h->d_rank_partial, h->d_gather, (size_t)h->C * h->PL, h->stream);
+        if (st != MPCB_OK) return st;
+        MppiCombineParams cp;
+        cp.rows = h->d_gather;
+        cp.G = h->cfg.world_size;
+        cp.C = h->C;
+        cp.H = h->H;
+        cp.lambda = h->cfg.lambda;
+        cp.u_out = d_u_out;
+        cp.u_out_host = nullptr;
+        cp.info = h->d_info;
+        cp.info_host = nullptr;
+        mppi_combine_kernel<128><<<h->C, 128, 0, h->stream>>>(cp);
+        MPCB_CUDA_TRY(cudaGetLastError());
+        h->launches += 1;
+    }
+    return MPCB_OK;
+}
+
+mpcb_status mpcb_mppi_sync(mpcb_mppi* h) {
+    MPCB_REQUIRE(h, "null handle");
+    MPCB_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    MPCB_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return MPCB_OK;
+}
+
+mpcb_status mpcb_mppi_last_info(mpcb_mppi* h, mpcb_mppi_info* info) {
+    MPCB_REQUIRE(h && info, "null pointer");
+    MPCB_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    MPCB_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    MPCB_CUDA_TRY(cudaMemcpy(info, h->d_info, (size_t)h->C * sizeof(mpcb_mppi_info), cudaMemcpyDeviceToHost));
+    return MPCB_OK;
+}
+
+void* mpcb_mppi_stream(mpcb_mppi* h) { return h ? (void*)h->stream : nullptr; }
+int64_t mpcb_mppi_launches(mpcb_mppi* h) { return h ? h->launches : 0; }
+int64_t mpcb_mppi_local_samples(mpcb_mppi* h) { return h ? h->K_local : 0; }
+int32_t mpcb_mppi_partial_len(mpcb_mppi* h) { return h ? h->PL : 0; }
+
+mpcb_status mpcb_mppi_compute_partial(mpcb_mppi* h, const double* x, const double* u_in, const void* d_eps,
+                                      int32_t eps_dtype, double* d_partial) {
+    MPCB_REQUIRE(h && x && u_in && d_partial, "null pointer");
+    MPCB_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    MppiParams p;
+    fill_params(h, &p);
+    mpcb_status st = stage_inputs(h, p, x, u_in);
+    if (st != MPCB_OK) return st;
+    p.eps = d_eps;
+    p.eps_f64 = (eps_dtype == MPCB_DT_F64);
+    p.final_mode = 1;
+    p.rank_partial = d_partial;
+    st = launch(h, p);
+    if (st != MPCB_OK) return st;
+    MPCB_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return MPCB_OK;
+}
+
+mpcb_status mpcb_mppi_combine(mpcb_mppi* h, const double* d_partials, int32_t n_ranks, double* u_out,
+                              mpcb_mppi_info* info) {
+    MPCB_REQUIRE(h && d_partials && u_out, "null pointer");
+    MPCB_REQUIRE(n_ranks >= 1 && n_ranks <= h->cfg.world_size, "n_ranks exceeds cfg.world_size");
+    MPCB_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    mpcb_status st = run_combine(h, d_partials, n_ranks);
+    if (st != MPCB_OK) return st;
+    return finish_host(h, u_out, info);
+}
+
+mpcb_status mpcb_comm_unique_id(char id[128]) { return nccl_unique_id(id); }
+
+mpcb_status mpcb_mppi_attach_comm(mpcb_mppi* h, const char id[128]) {
+    MPCB_REQUIRE(h && id, "null pointer");
+    MPCB_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (h->comm) {
+        nccl_destroy(h->comm);
+        h->comm = nullptr;
+    }
+    return nccl_init_rank(&h->comm, id, h->cfg.rank, h->cfg.world_size);
+}
+
+}  // extern "C"

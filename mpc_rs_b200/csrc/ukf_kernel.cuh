@@ -1,0 +1,541 @@
+// ukf_kernel.cuh — batched unscented Kalman filter, one thread per filter, everything in registers, FP64.
+//
+// Replaces UnscentedKalmanFilter::{predict,update} of src/ukf.rs:44-74 (n=4,o=3), src/ukf2.rs:44-74
+// (n=6,o=5) and the free functions of examples/ukf-pen.rs:44-141 (n=4,o=2, Cholesky).  The unscented
+// weights are +-1e6 (alpha = 1e-3, src/ukf.rs:24-28), which amplifies rounding by ~1.7e5 per step: FP32 is
+// unusable here (SURVEY.md finding 4), so state, covariance, sigma points and the model functions are FP64
+// and the arithmetic follows the reference's association order (this TU is compiled with -fmad=false).
+//
+// HBM layout is structure-of-arrays [component][B]: every load/store of a warp is one 256-byte coalesced
+// transaction per component.  A fused step reads x, P, z and writes x, P: 8*(2n + 2n^2 + o) bytes per
+// filter-update (336 B at n=4,o=2); with steps > 1 the state stays in registers between steps and only z
+// streams in.
+#pragma once
+
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "models.cuh"
+
+namespace mpcb {
+
+namespace uslot {  // hx constants, disjoint from the dynamics slots of models.cuh
+constexpr int G = 12, L = 13, RPM = 14, NRPM = 15, DEG = 17, M2G = 18, M2 = 19, M2L = 20;
+}
+
+struct UkfParams {
+    long long B;
+    int steps;
+    int has_u;
+    double* x;        // [n][B]
+    double* P;        // [n*n][B]
+    double* sigma_f;  // [n*M][B] (split predict/update only)
+    const double* u;  // [steps][B] or nullptr
+    const double* z;  // [steps][o][B]
+    int* status;      // [B], sticky
+    double u_scalar;
+    double dt;
+    double wm0, wc0, wi, cC;  // sigma_weight (src/ukf.rs:112-118), C = alpha^2 (n + kappa)
+    double Q[36];
+    double R[25];
+    ModelConsts mc;
+};
+
+enum UkfMode { UKF_PREDICT = 0, UKF_UPDATE = 1, UKF_FUSED = 2 };
+
+// ------------------------------------------------------------------------------------------------
+// process / measurement models (f64, reference association order)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void nl6_ddot(const ModelConsts& mc, double th, double thd, double u, double* ddx,
+                                         double* ddth) {
+    // examples/mppi4-non-liner-ukf.rs:126-139 with f = 0 (the UKF process model passes f = 0, :278)
+    const double s2 = sin(th), c2 = cos(th);
+    const double mlc = mc.k[slot::N6_ML] * c2;
+    const double d = mc.k[slot::N6_D1] - mlc * mlc;
+    const double w2 = thd * thd;
+    const double term1 = mc.k[slot::N6_BML] / d * w2 * s2;
+    const double term2 = mc.k[slot::N6_NML2G] / d * s2 * c2;
+    const double term3 = mc.k[slot::N6_TWOB] / (d * mc.k[slot::N6_RW]) * mc.k[slot::N6_KT] * u;
+    *ddx = term1 + term2 + term3 + 0.0;
+    const double t1 = mc.k[slot::N6_NML2] / d * w2 * s2 * c2;
+    const double t2 = (mc.k[slot::N6_M2G] * s2 - 2.0 * 0.0) * mc.k[slot::N6_L] * mc.k[slot::N6_A2] / d;
+    const double t3 = mc.k[slot::N6_NEG2ML] / (d * mc.k[slot::N6_RW]) * mc.k[slot::N6_KT] * u * c2;
+    *ddth = t1 + t2 + t3 + 0.0;
+}
+
+template <int MODEL, int N>
+__device__ __forceinline__ void ukf_fx(const ModelConsts& mc, double (&x)[N], double u, double dt) {
+    if constexpr (MODEL == MPCB_MODEL_PEN_LIN) {
+        // examples/ukf-pen.rs:76-83
+        x[3] += (mc.k[slot::L_A1] * x[2] - mc.k[slot::L_B1] * u) * dt;
+        x[2] += x[3] * dt;
+        x[1] += (mc.k[slot::L_A2] * x[2] + mc.k[slot::L_B2] * u) * dt;
+        x[0] += x[1] * dt;
+    } else if constexpr (MODEL == MPCB_MODEL_PEN_NL) {
+        // examples/ukf-pen2.rs:31-44
+        const double s = sin(x[2]), c = cos(x[2]);
+        const double d = mc.k[slot::NL_D] - mc.k[slot::NL_E2] * c * c;
+        const double term1 = mc.k[slot::NL_T1] * s;
+        const double q = mc.k[slot::NL_KT] * u / mc.k[slot::NL_RW] + mc.k[slot::NL_ML] * (x[3] * x[3]) * s;
+        const double term2 = q * mc.k[slot::NL_M2] * mc.k[slot::NL_L] * c;
+        const double r3 = x[3] + (term1 - term2) / d * dt;
+        const double r2 = x[2] + x[3] * dt;
+        const double term3 = mc.k[slot::NL_JML] * q;
+        const double term4 = mc.k[slot::NL_T4] * s * c;
+        const double r1 = x[1] + (term3 + term4) / d * dt;
+        const double r0 = x[0] + x[1] * dt;
+        x[0] = r0; x[1] = r1; x[2] = r2; x[3] = r3;
+    } else if constexpr (MODEL == MPCB_MODEL_PEN6) {
+        // examples/ukf-pen3.rs:35-50 — d from x[2].cos() as written (theta is x[3] in this layout)
+        const double mlc = mc.k[slot::NL_ML] * cos(x[2]);
+        const double d = mc.k[slot::NL_D] - mlc * mlc;
+        const double s3 = sin(x[3]), c3 = cos(x[3]);
+        const double q = mc.k[slot::NL_KT] * u / mc.k[slot::NL_RW] + mc.k[slot::NL_ML] * (x[4] * x[4]) * s3;
+        const double r0 = x[0] + x[1] * dt;
+        const double r1 = x[1] + x[2] * dt;
+        const double term3 = mc.k[slot::NL_JML] * q;
+        const double term4 = mc.k[slot::NL_T4] * s3 * c3;
+        const double r2 = (term3 + term4) / d;
+        const double r3 = x[3] + x[4] * dt;
+        const double r4 = x[4] + x[5] * dt;
+        const double term1 = mc.k[slot::NL_T1] * s3;
+        const double term2 = q * mc.k[slot::NL_M2] * mc.k[slot::NL_L] * c3;
+        const double r5 = (term1 - term2) / d;
+        x[0] = r0; x[1] = r1; x[2] = r2; x[3] = r3; x[4] = r4; x[5] = r5;
+    } else {
+        // MPCB_MODEL_NL6_UKF: dynamics_short(x, u, dt, 0) — examples/mppi4-non-liner-ukf.rs:149-159
+        double ddx, ddth;
+        nl6_ddot(mc, x[3], x[4], u, &ddx, &ddth);
+        x[5] = ddth;
+        x[4] += x[5] * dt;
+        x[3] += x[4] * dt;
+        x[2] = ddx;
+        x[1] += x[2] * dt;
+        x[0] += x[1] * dt;
+    }
+}
+
+template <int MODEL, int N, int O>
+__device__ __forceinline__ void ukf_hx(const ModelConsts& mc, const double (&x)[N], double (&z)[O]) {
+    if constexpr (MODEL == MPCB_MODEL_PEN_LIN) {
+        z[0] = x[1];  // examples/ukf-pen.rs:86-91
+        z[1] = x[3];
+    } else if constexpr (MODEL == MPCB_MODEL_PEN_NL) {
+        z[0] = mc.k[uslot::RPM] * x[1];  // examples/ukf-pen2.rs:47-53
+        z[1] = mc.k[uslot::RPM] * x[1];
+        z[2] = x[3] * mc.k[uslot::DEG];
+    } else if constexpr (MODEL == MPCB_MODEL_PEN6) {
+        // examples/ukf-pen3.rs:53-63
+        const double s3 = sin(x[3]), c3 = cos(x[3]);
+        const double v = mc.k[uslot::M2G] * c3 + mc.k[uslot::M2] * x[2] * s3 - mc.k[uslot::M2L] * (x[4] * x[4]);
+        const double h = -mc.k[uslot::M2G] * s3 + mc.k[uslot::M2] * x[2] * c3 + mc.k[uslot::M2L] * x[5];
+        z[0] = mc.k[uslot::RPM] * x[1];
+        z[1] = mc.k[uslot::RPM] * x[1];
+        z[2] = x[3] * mc.k[uslot::DEG];
+        z[3] = v / mc.k[uslot::G];
+        z[4] = h / mc.k[uslot::G];
+    } else {
+        // examples/mppi4-non-liner-ukf.rs:169-179
+        const double s3 = sin(x[3]), c3 = cos(x[3]);
+        const double ax = mc.k[uslot::G] * s3 + x[2] * c3 + mc.k[uslot::L] * x[5];
+        const double az = mc.k[uslot::G] * c3 - x[2] * s3 + mc.k[uslot::L] * (x[4] * x[4]);
+        z[0] = mc.k[uslot::RPM] * x[1];
+        z[1] = mc.k[uslot::NRPM] * x[1];
+        z[2] = x[4] * mc.k[uslot::DEG];
+        z[3] = az / mc.k[uslot::G];
+        z[4] = ax / mc.k[uslot::G];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small dense kernels, fully unrolled
+// ------------------------------------------------------------------------------------------------
+// nalgebra-style lower Cholesky (reads the lower triangle); false if a pivot is not > 0
+template <int N>
+__device__ __forceinline__ bool chol_lower(double (&m)[N][N]) {
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+#pragma unroll
+        for (int k = 0; k < j; ++k) {
+            const double ljk = m[j][k];
+#pragma unroll
+            for (int i = j; i < N; ++i) m[i][j] -= m[i][k] * ljk;
+        }
+        const double diag = m[j][j];
+        if (!(diag > 0.0)) ok = false;
+        const double denom = sqrt(diag);
+        m[j][j] = denom;
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) m[i][j] /= denom;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = i + 1; j < N; ++j) m[i][j] = 0.0;
+    return ok;
+}
+
+// U*sqrt(S) of the SVD of a symmetric PSD matrix by cyclic Jacobi (src/ukf.rs:121-124); at most 10
+// row-cyclic sweeps, stops when every off-diagonal element is exactly zero.
+template <int N>
+__device__ __forceinline__ void sym_eig_sqrt(double (&A)[N][N], double (&Lo)[N][N]) {
+    double V[N][N];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            V[i][j] = (i == j) ? 1.0 : 0.0;
+            if (j > i) A[i][j] = A[j][i];  // lower triangle is the input
+        }
+    for (int sweep = 0; sweep < 10; ++sweep) {
+        double off = 0.0;
+#pragma unroll
+        for (int p = 0; p < N - 1; ++p)
+#pragma unroll
+            for (int q = p + 1; q < N; ++q) off += A[p][q] * A[p][q];
+        if (off == 0.0) break;
+#pragma unroll
+        for (int p = 0; p < N - 1; ++p) {
+#pragma unroll
+            for (int q = p + 1; q < N; ++q) {
+                const double apq = A[p][q];
+                if (apq != 0.0) {
+                    const double tau = (A[q][q] - A[p][p]) / (2.0 * apq);
+                    const double rt = sqrt(1.0 + tau * tau);
+                    const double t = (tau >= 0.0) ? 1.0 / (tau + rt) : -1.0 / (-tau + rt);
+                    const double c = 1.0 / sqrt(1.0 + t * t);
+                    const double s = t * c;
+#pragma unroll
+                    for (int k = 0; k < N; ++k) {
+                        const double akp = A[k][p], akq = A[k][q];
+                        A[k][p] = c * akp - s * akq;
+                        A[k][q] = s * akp + c * akq;
+                    }
+#pragma unroll
+                    for (int k = 0; k < N; ++k) {
+                        const double apk = A[p][k], aqk = A[q][k];
+                        A[p][k] = c * apk - s * aqk;
+                        A[q][k] = s * apk + c * aqk;
+                    }
+                    A[p][q] = 0.0;
+                    A[q][p] = 0.0;
+#pragma unroll
+                    for (int k = 0; k < N; ++k) {
+                        const double vkp = V[k][p], vkq = V[k][q];
+                        V[k][p] = c * vkp - s * vkq;
+                        V[k][q] = s * vkp + c * vkq;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const double sq = sqrt(fabs(A[j][j]));
+#pragma unroll
+        for (int i = 0; i < N; ++i) Lo[i][j] = V[i][j] * sq;
+    }
+}
+
+// try_inverse: closed forms for 2x2 / 3x3, LU with partial pivoting otherwise; false = singular
+template <int O>
+__device__ __forceinline__ bool inverse_small(const double (&A)[O][O], double (&Ai)[O][O]) {
+    if constexpr (O == 2) {
+        const double det = A[0][0] * A[1][1] - A[1][0] * A[0][1];
+        if (det == 0.0) return false;
+        Ai[0][0] = A[1][1] / det; Ai[0][1] = -A[0][1] / det; Ai[1][0] = -A[1][0] / det; Ai[1][1] = A[0][0] / det;
+        return true;
+    } else if constexpr (O == 3) {
+        const double m11 = A[0][0], m12 = A[0][1], m13 = A[0][2], m21 = A[1][0], m22 = A[1][1], m23 = A[1][2],
+                     m31 = A[2][0], m32 = A[2][1], m33 = A[2][2];
+        const double minor_m12_m23 = m22 * m33 - m32 * m23;
+        const double minor_m11_m23 = m21 * m33 - m31 * m23;
+        const double minor_m11_m22 = m21 * m32 - m31 * m22;
+        const double det = m11 * minor_m12_m23 - m12 * minor_m11_m23 + m13 * minor_m11_m22;
+        if (det == 0.0) return false;
+        Ai[0][0] = minor_m12_m23 / det;
+        Ai[0][1] = (m13 * m32 - m33 * m12) / det;
+        Ai[0][2] = (m12 * m23 - m22 * m13) / det;
+        Ai[1][0] = -minor_m11_m23 / det;
+        Ai[1][1] = (m11 * m33 - m31 * m13) / det;
+        Ai[1][2] = (m13 * m21 - m23 * m11) / det;
+        Ai[2][0] = minor_m11_m22 / det;
+        Ai[2][1] = (m12 * m31 - m32 * m11) / det;
+        Ai[2][2] = (m11 * m22 - m21 * m12) / det;
+        return true;
+    } else {
+        double lu[O][O], rhs[O][O];  // rhs = row-permuted identity
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < O; ++i)
+#pragma unroll
+            for (int j = 0; j < O; ++j) {
+                lu[i][j] = A[i][j];
+                rhs[i][j] = (i == j) ? 1.0 : 0.0;
+            }
+#pragma unroll
+        for (int k = 0; k < O; ++k) {
+            int piv = k;
+            double best = fabs(lu[k][k]);
+#pragma unroll
+            for (int i = k + 1; i < O; ++i) {
+                const double v = fabs(lu[i][k]);
+                if (v > best) { best = v; piv = i; }
+            }
+            if (best == 0.0) ok = false;
+#pragma unroll
+            for (int i = k + 1; i < O; ++i) {
+                const bool sw = (piv == i);
+#pragma unroll
+                for (int j = 0; j < O; ++j) {
+                    const double a = lu[k][j], b = lu[i][j];
+                    lu[k][j] = sw ? b : a;
+                    lu[i][j] = sw ? a : b;
+                    const double ra = rhs[k][j], rb = rhs[i][j];
+                    rhs[k][j] = sw ? rb : ra;
+                    rhs[i][j] = sw ? ra : rb;
+                }
+            }
+            const double d = lu[k][k];
+#pragma unroll
+            for (int i = k + 1; i < O; ++i) {
+                lu[i][k] /= d;
+                const double l = lu[i][k];
+#pragma unroll
+                for (int j = k + 1; j < O; ++j) lu[i][j] -= l * lu[k][j];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < O; ++c) {
+            double y[O];
+#pragma unroll
+            for (int i = 0; i < O; ++i) {
+                double s = rhs[i][c];
+#pragma unroll
+                for (int j = 0; j < i; ++j) s -= lu[i][j] * y[j];
+                y[i] = s;
+            }
+#pragma unroll
+            for (int i = O - 1; i >= 0; --i) {
+                double s = y[i];
+#pragma unroll
+                for (int j = i + 1; j < O; ++j) s -= lu[i][j] * Ai[j][c];
+                Ai[i][c] = s / lu[i][i];
+            }
+        }
+        return ok;
+    }
+}
+
+// sigma-point column index of +L_i / -L_i
+template <int N, int ORDER>
+__device__ __forceinline__ constexpr int col_plus(int i) { return ORDER == MPCB_ORDER_INTERLEAVED ? 1 + 2 * i : 1 + i; }
+template <int N, int ORDER>
+__device__ __forceinline__ constexpr int col_minus(int i) { return ORDER == MPCB_ORDER_INTERLEAVED ? 2 + 2 * i : 1 + N + i; }
+
+// unscented_transform (src/ukf.rs:96-110): mean = sigmas*wm, P = sum_i wc_i y_i y_i^T + cov
+template <int S, int M>
+__device__ __forceinline__ void unscented_transform(const double (&sig)[S][M], double wm0, double wc0, double wi,
+                                                    const double* cov, double (&mean)[S], double (&P)[S][S]) {
+#pragma unroll
+    for (int r = 0; r < S; ++r) {
+        double acc = sig[r][0] * wm0;
+#pragma unroll
+        for (int i = 1; i < M; ++i) acc += sig[r][i] * wi;
+        mean[r] = acc;
+    }
+#pragma unroll
+    for (int r = 0; r < S; ++r)
+#pragma unroll
+        for (int c = 0; c < S; ++c) P[r][c] = 0.0;
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        double y[S];
+#pragma unroll
+        for (int r = 0; r < S; ++r) y[r] = sig[r][i] - mean[r];
+        const double w = (i == 0) ? wc0 : wi;
+#pragma unroll
+        for (int r = 0; r < S; ++r) {
+            const double wy = w * y[r];
+#pragma unroll
+            for (int c = 0; c < S; ++c) P[r][c] += wy * y[c];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < S; ++r)
+#pragma unroll
+        for (int c = 0; c < S; ++c) P[r][c] = P[r][c] + cov[r * S + c];
+}
+
+template <int N, int O, int MODEL, int SQRT, int ORDER, int MODE>
+__global__ void __launch_bounds__(128) ukf_kernel(const __grid_constant__ UkfParams p) {
+    constexpr int M = 2 * N + 1;
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    const long long B = p.B;
+
+    double x[N], P[N][N], sig[N][M];
+    int st = p.status[b];
+#pragma unroll
+    for (int r = 0; r < N; ++r) x[r] = p.x[(long long)r * B + b];
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+        for (int c = 0; c < N; ++c) P[r][c] = p.P[(long long)(r * N + c) * B + b];
+    if constexpr (MODE == UKF_UPDATE) {
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+#pragma unroll
+            for (int i = 0; i < M; ++i) sig[r][i] = p.sigma_f[(long long)(r * M + i) * B + b];
+    }
+
+    const int steps = (MODE == UKF_FUSED) ? p.steps : 1;
+    for (int s = 0; s < steps && st == MPCB_OK; ++s) {
+        if constexpr (MODE != UKF_UPDATE) {
+            // ---- predict (src/ukf.rs:44-52) ----
+            const double u = p.has_u ? p.u[(long long)s * B + b] : p.u_scalar;
+            double Lm[N][N];
+            bool ok = true;
+            if constexpr (SQRT == MPCB_SQRT_CHOLESKY) {
+#pragma unroll
+                for (int r = 0; r < N; ++r)
+#pragma unroll
+                    for (int c = 0; c < N; ++c) Lm[r][c] = p.cC * P[r][c];
+                ok = chol_lower<N>(Lm);
+            } else {
+                double cp[N][N];
+#pragma unroll
+                for (int r = 0; r < N; ++r)
+#pragma unroll
+                    for (int c = 0; c < N; ++c) cp[r][c] = p.cC * P[r][c];
+                sym_eig_sqrt<N>(cp, Lm);
+            }
+            if (!ok) { st = MPCB_CHOLESKY_FAIL; break; }
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+                sig[r][0] = x[r];
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    sig[r][col_plus<N, ORDER>(i)] = x[r] + Lm[r][i];
+                    sig[r][col_minus<N, ORDER>(i)] = x[r] - Lm[r][i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+                double col[N];
+#pragma unroll
+                for (int r = 0; r < N; ++r) col[r] = sig[r][i];
+                ukf_fx<MODEL, N>(p.mc, col, u, p.dt);
+#pragma unroll
+                for (int r = 0; r < N; ++r) sig[r][i] = col[r];
+            }
+            unscented_transform<N, M>(sig, p.wm0, p.wc0, p.wi, p.Q, x, P);
+        }
+        if constexpr (MODE != UKF_PREDICT) {
+            // ---- update (src/ukf.rs:54-74) ----
+            double zs[O][M];
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+                double col[N], zz[O];
+#pragma unroll
+                for (int r = 0; r < N; ++r) col[r] = sig[r][i];
+                ukf_hx<MODEL, N, O>(p.mc, col, zz);
+#pragma unroll
+                for (int r = 0; r < O; ++r) zs[r][i] = zz[r];
+            }
+            double zp[O], pz[O][O];
+            unscented_transform<O, M>(zs, p.wm0, p.wc0, p.wi, p.R, zp, pz);
+            double pxz[N][O];
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int c = 0; c < O; ++c) pxz[r][c] = 0.0;
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+                const double w = (i == 0) ? p.wc0 : p.wi;
+#pragma unroll
+                for (int r = 0; r < N; ++r) {
+                    const double wdx = w * (sig[r][i] - x[r]);
+#pragma unroll
+                    for (int c = 0; c < O; ++c) pxz[r][c] += wdx * (zs[c][i] - zp[c]);
+                }
+            }
+            double pzi[O][O];
+            if (!inverse_small<O>(pz, pzi)) { st = MPCB_INVERSE_FAIL; break; }
+            double k[N][O];
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int c = 0; c < O; ++c) {
+                    double acc = pxz[r][0] * pzi[0][c];
+#pragma unroll
+                    for (int j = 1; j < O; ++j) acc += pxz[r][j] * pzi[j][c];
+                    k[r][c] = acc;
+                }
+            double innov[O];
+#pragma unroll
+            for (int c = 0; c < O; ++c) innov[c] = p.z[((long long)s * O + c) * B + b] - zp[c];
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+                double acc = k[r][0] * innov[0];
+#pragma unroll
+                for (int j = 1; j < O; ++j) acc += k[r][j] * innov[j];
+                x[r] += acc;
+            }
+            double kp[N][O];
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int c = 0; c < O; ++c) {
+                    double acc = k[r][0] * pz[0][c];
+#pragma unroll
+                    for (int j = 1; j < O; ++j) acc += k[r][j] * pz[j][c];
+                    kp[r][c] = acc;
+                }
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    double acc = kp[r][0] * k[c][0];
+#pragma unroll
+                    for (int j = 1; j < O; ++j) acc += kp[r][j] * k[c][j];
+                    P[r][c] -= acc;
+                }
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int c = r; c < N; ++c) {
+                    const double a = (P[r][c] + P[c][r]) / 2.0;
+                    P[r][c] = a;
+                    P[c][r] = a;
+                }
+        }
+    }
+
+#pragma unroll
+    for (int r = 0; r < N; ++r) p.x[(long long)r * B + b] = x[r];
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+        for (int c = 0; c < N; ++c) p.P[(long long)(r * N + c) * B + b] = P[r][c];
+    if constexpr (MODE == UKF_PREDICT) {
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+#pragma unroll
+            for (int i = 0; i < M; ++i) p.sigma_f[(long long)(r * M + i) * B + b] = sig[r][i];
+    }
+    p.status[b] = st;
+}
+
+// AoS <-> SoA transposes for the host-facing calls: in[B][W] <-> out[W][B]
+__global__ void ukf_aos_to_soa(const double* __restrict__ in, double* __restrict__ out, long long B, int W);
+__global__ void ukf_soa_to_aos(const double* __restrict__ in, double* __restrict__ out, long long B, int W,
+                               long long first, long long count);
+__global__ void ukf_broadcast(const double* __restrict__ row, double* __restrict__ out, long long B, int W);
+
+using UkfKernelFn = void (*)(const UkfParams);
+UkfKernelFn ukf_kernel_n4(int model_id, int sqrt_mode, int order, int mode);
+UkfKernelFn ukf_kernel_n6(int model_id, int sqrt_mode, int order, int mode);
+
+}  // namespace mpcb

@@ -578,8 +578,8 @@ int orc_cholesky_lower(int n, const double* A, double* L) {
 
 /* U*sqrt(S) of svd_unordered(C*P) (src/ukf.rs:121-124).  For a symmetric PSD matrix the SVD is the
  * eigendecomposition; nalgebra's SVD routine is not available here, so this is the published cyclic
- * Jacobi method (Golub & Van Loan, Alg. 8.5.x: symmetric Schur rotations, row-cyclic sweeps, fixed
- * sweep count) on the lower triangle.  Column sign/order of U are immaterial (±L_i carry equal weights). */
+ * Jacobi method (Golub & Van Loan, Alg. 8.5.x: symmetric Schur rotations, row-cyclic sweeps, at most
+ * ORC_JACOBI_SWEEPS sweeps) on the lower triangle.  Column sign/order of U are immaterial (±L_i carry equal weights). */
 #define ORC_JACOBI_SWEEPS 10
 void orc_sym_eig_sqrt(int n, const double* Ain, double* Lout) {
     double A[ORC_MAX_N][ORC_MAX_N], V[ORC_MAX_N][ORC_MAX_N];
@@ -589,12 +589,17 @@ void orc_sym_eig_sqrt(int n, const double* Ain, double* Lout) {
             V[i][j] = (i == j) ? 1.0 : 0.0;
         }
     for (int sweep = 0; sweep < ORC_JACOBI_SWEEPS; ++sweep) {
+        double off = 0.0; /* stop once every off-diagonal element is exactly zero */
+        for (int p = 0; p < n - 1; ++p)
+            for (int q = p + 1; q < n; ++q) off += A[p][q] * A[p][q];
+        if (off == 0.0) break;
         for (int p = 0; p < n - 1; ++p) {
             for (int q = p + 1; q < n; ++q) {
                 const double apq = A[p][q];
                 if (apq == 0.0) continue;
                 const double tau = (A[q][q] - A[p][p]) / (2.0 * apq);
-                const double t = (tau >= 0.0) ? 1.0 / (tau + sqrt(1.0 + tau * tau)) : -1.0 / (-tau + sqrt(1.0 + tau * tau));
+                const double rt = sqrt(1.0 + tau * tau);
+                const double t = (tau >= 0.0) ? 1.0 / (tau + rt) : -1.0 / (-tau + rt);
                 const double c = 1.0 / sqrt(1.0 + t * t);
                 const double s = t * c;
                 for (int k = 0; k < n; ++k) { /* A <- A*J */

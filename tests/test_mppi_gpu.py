@@ -1,0 +1,149 @@
+"""MPPI parity: the CUDA path (through the C ABI) against the CPU oracle on identical noise (replay mode).
+
+Tolerances (BASELINE.json north_star): controls within 1e-5 relative, sample argmin (= argmax of c_k)
+bit-exact.  The FP64 path reproduces the f64 oracle to libm rounding (1e-9 here); the FP32 path is held to
+1e-5 against the f64 oracle on the named shapes.
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from mpc_rs_b200 import Mppi, MppiError, models
+from mpc_rs_b200 import _abi as A
+
+pytestmark = pytest.mark.gpu
+
+X0 = np.array([0.5, 0.0, 0.1, 0.0])  # examples/mppi4.rs:30
+CASES = {
+    # name: (device model, oracle id, H, dt, lambda, sigma, limit)
+    "L_shipped": (models.L, O.MODEL_L, 8, 0.1, 0.5, 3.0, (-20.0, 20.0)),
+    "NL_shipped": (models.NL, O.MODEL_NL, 8, 0.1, 0.5, 3.0, (-20.0, 20.0)),
+    "NL_h100": (models.NL, O.MODEL_NL, 100, 0.008, 0.5, 3.0, (-20.0, 20.0)),
+    "NL6_shipped": (models.NL6, O.MODEL_NL6, 8, 0.15, 1.4, 4.0, (-10.0, 10.0)),
+}
+
+
+def rel_err(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def closed_loop(case, K, precision, steps=3, seed=20240001, eps_dtype=np.float64):
+    """Runs `steps` closed-loop control steps on the GPU and the oracle with the same noise; yields both."""
+    model, oid, H, dt, lam, sig, lim = CASES[case]
+    p = O.model_defaults(oid, dt=dt)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    x, u_g, u_o = X0.copy(), np.zeros(H), np.zeros(H)
+    out = []
+    with Mppi(H, K, model=model, lam=lam, std_dev=sig, limit=lim, precision=precision, dt=dt, keep_costs=True) as m:
+        for _ in range(steps):
+            eps = (sig * rng.standard_normal((K, H))).astype(eps_dtype)
+            # the oracle is driven with its own previous output, the GPU with the GPU's: closed loop on each side
+            st, u_o, info_o, c_o = O.mppi_compute(oid, p, K, H, lam, sig, lim[0], lim[1], x, u_o, eps.astype(np.float64),
+                                                  want_costs=True)
+            assert st == 0
+            u_g = m.compute_replay(x, u_g, eps)
+            out.append((u_g.copy(), u_o.copy(), m.info[0], info_o, m.costs(), c_o))
+            x = O.dynamics(oid, p, x, u_o[0])
+            u_g = u_o.copy()  # keep both sides on the same input so the per-step comparison stays meaningful
+    return out
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_replay_parity_f64(gpu_required, case):
+    for u_g, u_o, ig, io, c_g, c_o in closed_loop(case, 16384, "f64"):
+        assert ig["argmax"] == io["argmax"]
+        assert ig["n_finite"] == io["n_finite"]
+        # trajectories that blow up (|c| huge, weight exactly 0) amplify 1-ulp libm differences chaotically:
+        # compare costs where they matter (within 1e4 of the best) and the softmax weights everywhere
+        near = c_o > io["max"] - 1e4
+        np.testing.assert_allclose(c_g[near], c_o[near], rtol=1e-7, atol=1e-9)
+        lam = CASES[case][4]
+        np.testing.assert_allclose(np.exp((c_g - ig["max"]) / lam), np.exp((c_o - io["max"]) / lam), rtol=1e-7, atol=1e-13)
+        assert abs(ig["max"] - io["max"]) <= 1e-9 * abs(io["max"]) + 1e-12
+        assert abs(ig["sum"] - io["sum"]) <= 1e-9 * io["sum"]
+        assert rel_err(u_g, u_o) < 1e-9
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_replay_parity_f32(gpu_required, case):
+    for u_g, u_o, ig, io, c_g, c_o in closed_loop(case, 16384, "f32", eps_dtype=np.float32):
+        assert ig["argmax"] == io["argmax"]  # sample argmin bit-exact
+        assert rel_err(u_g, u_o) < 1e-5
+
+
+def test_config2_shape_f32(gpu_required):
+    """BASELINE config #2: model NL, K = 65536, H = 100 (DT = 0.008), 3 closed-loop steps."""
+    for u_g, u_o, ig, io, c_g, c_o in closed_loop("NL_h100", 65536, "f32", eps_dtype=np.float32):
+        assert ig["argmax"] == io["argmax"]
+        assert rel_err(u_g, u_o) < 1e-5
+        assert np.max(np.abs(c_g - c_o)) < 5e-2  # FP32 rollout cost error stays far below the top-2 gap
+
+
+def test_ragged_sizes(gpu_required):
+    """K not a multiple of the block, H not a multiple of 4, K = 1 (u_out == v_0 exactly, src/mppi.rs:80-84)."""
+    model, oid, _, dt, lam, sig, lim = CASES["NL_shipped"]
+    p = O.model_defaults(oid, dt=dt)
+    rng = np.random.default_rng(5)
+    for K, H in ((1, 8), (77, 7), (1000, 13), (129, 1), (4097, 33)):
+        eps = sig * rng.standard_normal((K, H))
+        u_n = rng.uniform(-2, 2, H)
+        st, u_o, io, _ = O.mppi_compute(oid, p, K, H, lam, sig, lim[0], lim[1], X0, u_n, eps)
+        with Mppi(H, K, model=model, lam=lam, std_dev=sig, limit=lim, precision="f64", dt=dt) as m:
+            u_g = m.compute_replay(X0, u_n, eps)
+            assert m.info[0]["argmax"] == io["argmax"]
+            assert rel_err(u_g, u_o) < 1e-9
+            if K == 1:
+                np.testing.assert_array_equal(u_g, np.clip(u_n + eps[0], lim[0], lim[1]))
+
+
+def test_error_paths(gpu_required):
+    """Err strings of src/mppi.rs:69,88."""
+    model, oid, H, dt, lam, sig, lim = CASES["L_shipped"]
+    K = 512
+    eps = np.zeros((K, H))
+    with Mppi(H, K, model=model, lam=lam, std_dev=sig, limit=lim, precision="f64", dt=dt) as m:
+        with pytest.raises(MppiError, match="Cannot calculate max"):
+            m.compute_replay(np.full(4, np.nan), np.zeros(H), eps)
+        eps2 = eps.copy()
+        eps2[7, 0] = np.nan  # one NaN sample poisons the sum in the reference -> "u is invalid"
+        with pytest.raises(MppiError, match="u is invalid"):
+            m.compute_replay(X0, np.zeros(H), eps2)
+        # and the handle keeps working afterwards
+        u = m.compute_replay(X0, np.zeros(H), eps)
+        assert np.all(np.isfinite(u))
+
+
+def test_generate_mode_replays_its_own_dump(gpu_required):
+    """Philox generate mode: dumping the drawn noise and replaying it through the oracle gives the same control."""
+    model, oid, H, dt, lam, sig, lim = CASES["NL_h100"]
+    K = 8192
+    p = O.model_defaults(oid, dt=dt)
+    for prec, tol in (("f64", 1e-9), ("f32", 1e-5)):
+        with Mppi(H, K, model=model, lam=lam, std_dev=sig, limit=lim, precision=prec, dt=dt, seed=20240001) as m:
+            u_g, eps = m.compute_dump(X0, np.zeros(H))
+            assert eps.shape == (K, H)
+            z = eps.astype(np.float64).ravel() / sig
+            assert abs(z.mean()) < 5e-3 and abs(z.std() - 1.0) < 5e-3
+            st, u_o, io, _ = O.mppi_compute(oid, p, K, H, lam, sig, lim[0], lim[1], X0, np.zeros(H), eps.astype(np.float64))
+            assert m.info[0]["argmax"] == io["argmax"]
+            assert rel_err(u_g, u_o) < tol
+            # a second call draws different noise (call counter is part of the Philox counter)
+            u2, eps2 = m.compute_dump(X0, np.zeros(H))
+            assert not np.array_equal(eps, eps2)
+
+
+def test_batched_controllers(gpu_required):
+    """C independent controllers in one call equal C single-controller calls (segmented reduction)."""
+    model, oid, H, dt, lam, sig, lim = CASES["NL6_shipped"]
+    C, K = 5, 3000
+    p = O.model_defaults(oid, dt=dt)
+    rng = np.random.default_rng(11)
+    xs = rng.normal(0, 0.1, (C, 4))
+    us = rng.uniform(-1, 1, (C, H))
+    eps = sig * rng.standard_normal((C, K, H))
+    with Mppi(H, K, model=model, lam=lam, std_dev=sig, limit=lim, precision="f64", dt=dt, controllers=C) as m:
+        u_g = m.compute_replay(xs, us, eps)
+        for c in range(C):
+            st, u_o, io, _ = O.mppi_compute(oid, p, K, H, lam, sig, lim[0], lim[1], xs[c], us[c], eps[c])
+            assert m.info[c]["argmax"] == io["argmax"]
+            assert rel_err(u_g[c], u_o) < 1e-9

@@ -1,0 +1,263 @@
+"""CPU tests (-m "not gpu"): pin the oracle.
+
+The reference has no tests or golden vectors ("parity unpinned"), so the oracle is pinned by
+(1) closed-form known answers, (2) an independent numpy re-derivation from the same Rust lines (ref_numpy.py),
+(3) algebraic identities of src/mppi.rs, (4) the committed golden fixtures in tests/golden/ (made by
+tests/make_golden.py from the oracle, so that later changes to the oracle are caught).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import ref_numpy as RN
+
+X0 = np.array([0.5, 0.0, 0.1, 0.0])
+
+
+def nrel(a, b):
+    """norm-wise relative difference"""
+    return np.linalg.norm(np.ravel(a) - np.ravel(b)) / max(np.linalg.norm(np.ravel(b)), 1e-300)
+
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+# ---------------------------------------------------------------- known answers: UKF weights, Gaussian, KF
+def test_sigma_weights_known_answers():
+    # src/ukf.rs:23-28,112-118 with alpha=1e-3, beta=2, kappa=3-n  =>  C = 3e-6 for every n
+    wm, wc = O.ukf_weights(4)
+    assert wm[0] == pytest.approx(-1333332.3333333333, rel=1e-12)
+    assert wm[1] == pytest.approx(166666.66666666666, rel=1e-12)
+    assert wc[0] == pytest.approx(-1333332.3333333333 + 1.0 - 1e-6 + 2.0, rel=1e-12)
+    assert abs(wm.sum() - 1.0) < 1e-9
+    wm6, _ = O.ukf_weights(6)
+    assert wm6[0] == pytest.approx(-1999999.0, rel=1e-12)
+    assert abs(wm6.sum() - 1.0) < 1e-9
+    assert len(wm6) == 13
+
+
+def test_gaussian_product_is_scalar_kalman_update():
+    # examples/one-liner-kf.rs:26-40: Gaussian*Gaussian == (mean + K (z - mean), (1 - K) var), K = var/(var+R)
+    L = O.lib()
+    prior, meas = O.Gaussian(1.5, 4.0), O.Gaussian(2.5, 0.25)
+    post = L.orc_gaussian_mul(prior, meas)
+    K = prior.var / (prior.var + meas.var)
+    assert post.mean == pytest.approx(prior.mean + K * (meas.mean - prior.mean), rel=1e-14)
+    assert post.var == pytest.approx((1 - K) * prior.var, rel=1e-14)
+    s = L.orc_gaussian_add(prior, meas)
+    d = L.orc_gaussian_sub(prior, meas)
+    k = L.orc_gaussian_scale(prior, 3.0)
+    assert (s.mean, s.var, d.mean, d.var, k.mean, k.var) == (4.0, 4.25, -1.0, 3.75, 4.5, 12.0)
+    # the package's host-side Gaussian is the same algebra (src/gaussian.rs)
+    from mpc_rs_b200 import Gaussian
+    g = Gaussian.new(1.5, 4.0) * Gaussian.new(2.5, 0.25)
+    assert (g.mean, g.var) == (post.mean, post.var)
+    assert Gaussian() == Gaussian(0.0, 0.0)
+    assert (Gaussian.new(1.5, 4.0) * 3.0) == Gaussian(4.5, 12.0)
+
+
+def test_linear_ukf_equals_kalman_filter():
+    """For a linear model the unscented transform is exact, so the filter has a closed form
+    (examples/two-liner-kf.rs:17-52 is the textbook KF it reduces to when Q = 0).  The reference re-uses the
+    PROPAGATED sigma points in update() (src/ukf.rs:58-68) instead of redrawing them from the predicted P, so
+    the innovation statistics see F P F^T without Q:  Pz = H (P' - Q) H^T + R,  Pxz = (P' - Q) H^T."""
+    oid = O.MODEL_PEN_LIN
+    p = O.model_defaults(oid)
+    Q, R, P0 = O.ukf_default_noise(oid)
+    n = 4
+    F = np.stack([O.fx(oid, p, np.eye(n)[i], 0.0) for i in range(n)], 1)  # linear: columns = images of basis vectors
+    Bu = O.fx(oid, p, np.zeros(n), 1.0)
+    H = np.stack([O.hx(oid, p, np.eye(n)[i]) for i in range(n)], 1)
+    for Qm in (np.zeros((n, n)), Q):
+        rng = np.random.default_rng(0)
+        x, P = rng.normal(size=n), P0.copy()
+        xk, Pk = x.copy(), P.copy()
+        for _ in range(5):
+            z = rng.normal(size=2)
+            st, x, P, sf = O.ukf_predict(oid, p, x, P, Qm, 0.3, 0.0, O.SQRT_CHOLESKY, O.ORDER_INTERLEAVED)
+            st, x, P = O.ukf_update(oid, p, x, P, R, z, sf)
+            xk = F @ xk + Bu * 0.3
+            Pf = F @ Pk @ F.T  # spread of the propagated sigma points
+            Pk = Pf + Qm
+            S = H @ Pf @ H.T + R
+            K = Pf @ H.T @ np.linalg.inv(S)
+            xk = xk + K @ (z - H @ xk)
+            Pk = Pk - K @ S @ K.T
+            # the +-1e6 weights amplify rounding by ~1.7e5 * eps per step (SURVEY.md finding 4)
+            np.testing.assert_allclose(x, xk, rtol=1e-7, atol=1e-8)
+            np.testing.assert_allclose(P, Pk, rtol=1e-7, atol=1e-8)
+
+
+def test_small_matrix_kernels():
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 3, 4, 5, 6):
+        A = rng.normal(size=(n, n))
+        Pm = A @ A.T + 0.5 * np.eye(n)
+        st, Ai = O.inverse(Pm)
+        assert st == 0
+        np.testing.assert_allclose(Ai, np.linalg.inv(Pm), rtol=1e-11, atol=1e-13)
+        if n >= 2:
+            st, Lc = O.cholesky_lower(Pm)
+            assert st == 0
+            np.testing.assert_allclose(Lc, np.linalg.cholesky(Pm), rtol=1e-13, atol=1e-15)
+            Le = O.sym_eig_sqrt(Pm)
+            np.testing.assert_allclose(Le @ Le.T, Pm, rtol=1e-12, atol=1e-13)
+    assert O.inverse(np.zeros((2, 2)))[0] == 4  # "Inverse fail"
+    assert O.inverse(np.zeros((5, 5)))[0] == 4
+    assert O.cholesky_lower(-np.eye(4))[0] == 5  # "Cholesky fail"
+    # repeated eigenvalues (P0 = 10 I, examples/ukf-pen2.rs:71-76): U = I, no arbitrary rotation
+    np.testing.assert_array_equal(O.sym_eig_sqrt(10.0 * np.eye(4)), np.sqrt(10.0) * np.eye(4))
+
+
+# ---------------------------------------------------------------- cross-check against the numpy re-derivation
+@pytest.mark.parametrize("oid,dt", [(O.MODEL_L, 0.1), (O.MODEL_NL, 0.1), (O.MODEL_NL, 0.008), (O.MODEL_NL6, 0.15)])
+def test_models_match_numpy_rederivation(oid, dt):
+    p = O.model_defaults(oid, dt=dt)
+    dyn, cost = RN.MPPI_MODELS[oid]
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        x = rng.normal(0, 1.0, 4)
+        u = rng.uniform(-20, 20)
+        np.testing.assert_allclose(O.dynamics(oid, p, x, u), dyn(x, u, dt), rtol=1e-13, atol=1e-13)
+        assert O.cost(oid, p, x) == pytest.approx(float(cost(x)), rel=1e-13)
+
+
+@pytest.mark.parametrize("oid,H,dt,lam,sig,lim", [
+    (O.MODEL_L, 8, 0.1, 0.5, 3.0, (-20.0, 20.0)),
+    (O.MODEL_NL, 8, 0.1, 0.5, 3.0, (-20.0, 20.0)),
+    (O.MODEL_NL, 40, 0.02, 0.5, 3.0, (-20.0, 20.0)),
+    (O.MODEL_NL6, 8, 0.15, 1.4, 4.0, (-10.0, 10.0)),
+])
+def test_mppi_matches_numpy_rederivation(oid, H, dt, lam, sig, lim):
+    p = O.model_defaults(oid, dt=dt)
+    K = 4000
+    rng = np.random.default_rng(2)
+    u_n = rng.uniform(-3, 3, H)
+    eps = sig * rng.standard_normal((K, H))
+    st, u, info, c = O.mppi_compute(oid, p, K, H, lam, sig, lim[0], lim[1], X0, u_n, eps, want_costs=True)
+    u_ref, c_ref = RN.mppi_compute(oid, dt, lam, sig, lim, X0, u_n, eps)
+    assert st == 0
+    near = c_ref > c_ref.max() - 1e4  # blown-up rollouts amplify rounding chaotically and carry weight 0
+    np.testing.assert_allclose(c[near], c_ref[near], rtol=1e-10, atol=1e-9)
+    assert info["argmax"] == int(np.argmax(c_ref))
+    np.testing.assert_allclose(u, u_ref, rtol=1e-10, atol=1e-12)
+
+
+def test_ukf_matches_numpy_rederivation():
+    """Cholesky square root is unique, so three chained steps must agree tightly.  The SVD square root
+    (src/ukf.rs:121-124) is unique only up to a rotation inside repeated singular values — after one update the
+    unobserved directions of P still share the eigenvalue 10, and for a nonlinear fx two valid square roots differ
+    at O(weights * spread^4) ~ 1e-4 (SURVEY.md finding 5) — so the eig mode is cross-checked on the first step from
+    the diagonal P0 (U = I on both sides) and on the linear model (where the rotation cannot matter)."""
+    cases = [
+        (O.MODEL_PEN_LIN, RN.fx_pen_lin, RN.hx_pen_lin, 0.0015),
+        (O.MODEL_PEN_NL, RN.fx_pen_nl, RN.hx_pen_nl, 0.1),
+        (O.MODEL_PEN6, RN.fx_pen6, RN.hx_pen6, 0.1),
+        (O.MODEL_NL6_UKF, lambda x, u: RN.dynamics_short(x, u, 0.01, 0.0), RN.hx_nl6, 0.3),
+    ]
+    rng = np.random.default_rng(5)
+    for oid, fx, hx, u in cases:
+        p = O.model_defaults(oid)
+        n, o = O.dims(oid)
+        dt = 0.01 if oid == O.MODEL_NL6_UKF else 0.0
+        Q, R, P0 = O.ukf_default_noise(oid, dt)
+        for sq, order, steps in (("cholesky", "interleaved", 3), ("cholesky", "library", 3),
+                                 ("svd", "library", 3 if oid == O.MODEL_PEN_LIN else 1)):
+            x, P = rng.normal(0, 0.05, n), P0.copy()
+            for step in range(steps):
+                z = np.array(O.hx(oid, p, x)) + rng.normal(size=o)
+                st, x1, P1, sf = O.ukf_predict(oid, p, x, P, Q, u, dt, O.SQRT_CHOLESKY if sq == "cholesky" else O.SQRT_EIG,
+                                               O.ORDER_INTERLEAVED if order == "interleaved" else O.ORDER_LIBRARY)
+                assert st == 0
+                xr, Pr, sigr = RN.ukf_predict(lambda s: fx(s, u), x, P, Q, sq, order)
+                # +-1e6 weights amplify rounding by ~1.7e5 per transform: two f64 evaluations of the SAME sigma points
+                # sit ~1e-6 (absolute, entries up to 3e4) from the float128 value, so compare norm-wise
+                assert nrel(x1, xr) < 1e-7, f"{oid} {sq} predict x {nrel(x1, xr)}"
+                assert nrel(P1, Pr) < 1e-7, f"{oid} {sq} predict P {nrel(P1, Pr)}"
+                st, x2, P2 = O.ukf_update(oid, p, x1, P1, R, z, sf)
+                assert st == 0
+                xr2, Pr2 = RN.ukf_update(hx, x1, P1, R, z, sf)
+                # the n=6 filters are ill-conditioned (P entries 3e4 -> 1e2 through a 5x5 inverse): two correct f64
+                # evaluations differ by up to ~1e-6 norm-wise after one update; the bar is the 1e-5 of the north star
+                assert nrel(x2, xr2) < 1e-5, f"{oid} {sq} update x {nrel(x2, xr2)}"
+                assert nrel(P2, Pr2) < 1e-5, f"{oid} {sq} update P {nrel(P2, Pr2)}"
+                x, P = x2, P2
+
+
+def test_gen_q_and_dynamics_short():
+    # examples/mppi4-non-liner-ukf.rs:149-159,192-221
+    q = O.gen_q(0.01)
+    assert q[5, 5] == pytest.approx(100.0 * 0.01)
+    assert q[4, 4] == pytest.approx(100.0 * 0.01 ** 3 / 3.0 + 70.0 * 0.01)
+    assert q[1, 1] == pytest.approx(20.0 * 0.01 ** 3 / 3.0)
+    np.testing.assert_array_equal(q, q.T)
+    p = O.model_defaults(O.MODEL_NL6_UKF)
+    rng = np.random.default_rng(8)
+    for _ in range(20):
+        x6 = rng.normal(0, 0.5, 6)
+        np.testing.assert_allclose(O.dynamics_short(p, x6, 1.3, 0.012, 2.0), RN.dynamics_short(x6, 1.3, 0.012, 2.0),
+                                   rtol=1e-13, atol=1e-13)
+
+
+# ---------------------------------------------------------------- algebraic identities of src/mppi.rs
+def test_mppi_identities():
+    oid, H, dt, lam, sig, lo, hi = O.MODEL_NL, 8, 0.1, 0.5, 3.0, -20.0, 20.0
+    p = O.model_defaults(oid, dt=dt)
+    rng = np.random.default_rng(4)
+    u_n = rng.uniform(-2, 2, H)
+    # K = 1: the weight is exp(0) = 1, so u_out is exactly v_0 (src/mppi.rs:80-84)
+    eps = sig * rng.standard_normal((1, H))
+    st, u, info, _ = O.mppi_compute(oid, p, 1, H, lam, sig, lo, hi, X0, u_n, eps)
+    np.testing.assert_array_equal(u, np.clip(u_n + eps[0], lo, hi))
+    assert (st, info["sum"], info["argmax"]) == (0, 1.0, 0)
+    # the three error paths (src/mppi.rs:69,77,88)
+    st, *_ = O.mppi_compute(oid, p, 4, H, lam, sig, lo, hi, np.full(4, np.nan), u_n, np.zeros((4, H)))
+    assert st == 1
+    e = np.zeros((4, H)); e[2, 0] = np.nan
+    st, *_ = O.mppi_compute(oid, p, 4, H, lam, sig, lo, hi, X0, u_n, e)
+    assert st == 3
+    # permutation invariance up to reduction order
+    K = 2000
+    eps = sig * rng.standard_normal((K, H))
+    st, u1, i1, _ = O.mppi_compute(oid, p, K, H, lam, sig, lo, hi, X0, u_n, eps)
+    perm = rng.permutation(K)
+    st, u2, i2, _ = O.mppi_compute(oid, p, K, H, lam, sig, lo, hi, X0, u_n, eps[perm])
+    np.testing.assert_allclose(u1, u2, rtol=1e-12)
+    assert perm[i2["argmax"]] == i1["argmax"]
+    # f32 twin tracks the f64 oracle (bounds what the FP32 kernel can reach, SURVEY.md hard part 4)
+    st, u3, i3, _ = O.mppi_compute(oid, p, K, H, lam, sig, lo, hi, X0, u_n, eps.astype(np.float32), f32=True)
+    assert i3["argmax"] == i1["argmax"]
+    assert np.linalg.norm(u3 - u1) / np.linalg.norm(u1) < 1e-4
+
+
+def test_cpu_baseline_sampler_and_structure():
+    z = O.normal_fill(7, 400000)
+    from scipy import stats
+    assert stats.kstest(z, "norm").pvalue > 1e-3
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01 and np.abs(z).max() > 4.0
+    p = O.model_defaults(O.MODEL_L)
+    st, u, info = O.mppi_compute_cpu(O.MODEL_L, p, 20000, 8, 0.5, 3.0, -20.0, 20.0, X0, np.zeros(8), seed=3, threads=2)
+    assert st == 0 and info["n_finite"] == 20000 and np.all(np.abs(u) <= 20.0)
+    st2, u2, _ = O.mppi_compute_cpu(O.MODEL_L, p, 20000, 8, 0.5, 3.0, -20.0, 20.0, X0, np.zeros(8), seed=3, threads=2)
+    np.testing.assert_allclose(u, u2, rtol=1e-12)  # same seed and worker count -> same draw
+    # and the closed loop it drives keeps the pendulum up (examples/mppi4.rs:41-68, stop condition |theta| > 60 deg)
+    x, un = X0.copy(), np.zeros(8)
+    for i in range(25):
+        st, un, _ = O.mppi_compute_cpu(O.MODEL_L, p, 20000, 8, 0.5, 3.0, -20.0, 20.0, x, un, seed=100 + i, threads=2)
+        x = O.dynamics(O.MODEL_L, p, x, un[0])
+        assert abs(x[2]) < np.radians(60.0)
+    assert abs(x[2]) < 0.1 and abs(x[0]) < 0.5
+
+
+# ---------------------------------------------------------------- golden fixtures
+@pytest.mark.parametrize("name", ["mppi_L", "mppi_NL", "mppi_NL6", "ukf_PEN_LIN", "ukf_PEN_NL", "ukf_PEN6", "ukf_NL6_UKF"])
+def test_golden_fixtures(name):
+    import make_golden
+    path = os.path.join(GOLD, name + ".npz")
+    assert os.path.exists(path), "run python tests/make_golden.py"
+    g = np.load(path)
+    fresh = make_golden.CASES[name]()
+    for k in g.files:
+        np.testing.assert_allclose(fresh[k], g[k], rtol=1e-12, atol=1e-13, err_msg=f"{name}:{k}")

@@ -1,0 +1,195 @@
+"""Batched UKF parity: the CUDA path (through the C ABI) against the CPU oracle, per step and per trajectory.
+
+Tolerance: 1e-5 relative on state and covariance (BASELINE.json north_star); per-step differences are held
+to 1e-9 (same algorithm, different libm / no other source of difference: both sides run without FMA).
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from mpc_rs_b200 import BatchedUkf, UnscentedKalmanFilter, UkfError, MpcB200Error, models, ukf
+from mpc_rs_b200 import _abi as A
+
+pytestmark = pytest.mark.gpu
+
+MODELS = {
+    "PEN_LIN": (models.PEN_LIN, O.MODEL_PEN_LIN, 0.0015),  # examples/ukf-pen.rs:155
+    "PEN_NL": (models.PEN_NL, O.MODEL_PEN_NL, 0.1),        # examples/ukf-pen2.rs:79
+    "PEN6": (models.PEN6, O.MODEL_PEN6, 0.1),              # examples/ukf-pen3.rs
+    "NL6_UKF": (models.NL6_UKF, O.MODEL_NL6_UKF, 0.3),
+}
+SQRT = {"cholesky": O.SQRT_CHOLESKY, "eig": O.SQRT_EIG}
+ORDER = {"library": O.ORDER_LIBRARY, "interleaved": O.ORDER_INTERLEAVED}
+
+
+def relerr(a, b):
+    return np.linalg.norm(np.ravel(a) - np.ravel(b)) / max(np.linalg.norm(np.ravel(b)), 1e-300)
+
+
+def make_problem(name, B, T, seed, dt=0.0):
+    model, oid, u = MODELS[name]
+    p = O.model_defaults(oid)
+    n, o = O.dims(oid)
+    Q, R, P0 = O.ukf_default_noise(oid, dt)
+    rng = np.random.default_rng(seed)
+    x_act = rng.normal(0, 0.1, (B, n))
+    zs = np.empty((T, B, o))
+    sd = np.sqrt(np.diag(R))
+    for t in range(T):
+        for b in range(B):
+            x_act[b] = O.fx(oid, p, x_act[b], u, dt)
+            zs[t, b] = O.hx(oid, p, x_act[b]) + sd * rng.standard_normal(o)
+    return model, oid, p, n, o, Q, R, P0, u, zs
+
+
+@pytest.mark.parametrize("name,sqrt_mode,order", [
+    ("PEN_LIN", "cholesky", "interleaved"),  # examples/ukf-pen.rs as shipped (BASELINE config #3)
+    ("PEN_LIN", "cholesky", "library"),
+    ("PEN_LIN", "eig", "library"),
+    ("PEN_NL", "eig", "library"),            # mpc::ukf as shipped (SVD square root)
+    ("PEN_NL", "cholesky", "interleaved"),
+    ("PEN6", "eig", "library"),              # mpc::ukf2
+    ("PEN6", "cholesky", "library"),
+    ("NL6_UKF", "eig", "library"),           # config #4 filter
+    ("NL6_UKF", "cholesky", "library"),
+])
+def test_fused_step_parity_per_step(gpu_required, name, sqrt_mode, order):
+    """Every step starts from the oracle's state on both sides: isolates one predict+update."""
+    B, T = 257, 6
+    dt = 0.01 if name == "NL6_UKF" else 0.0
+    model, oid, p, n, o, Q, R, P0, u, zs = make_problem(name, B, T, 7, dt)
+    x = np.zeros((B, n))
+    P = np.tile(P0, (B, 1, 1))
+    with BatchedUkf(model, B, sqrt_mode=sqrt_mode, sigma_order=order) as f:
+        f.init(np.zeros(n), P0, Q, R)
+        for t in range(T):
+            f.set_state(x, P)
+            f.step(u, zs[t], dt)
+            xg, Pg = f.get_state()
+            x, P, st = O.ukf_step_batch(oid, p, x, P, Q, R, u, zs[t], dt, SQRT[sqrt_mode], ORDER[order])
+            assert not st.any()
+            assert relerr(xg, x) < 1e-9, (t, relerr(xg, x))
+            assert relerr(Pg, P) < 1e-9, (t, relerr(Pg, P))
+
+
+def test_trajectory_config3(gpu_required):
+    """examples/ukf-pen.rs:143-179: 100 steps, P0 = 10 I, u = 0.0015; GPU runs free for the whole trajectory."""
+    B, T = 1024, 100
+    model, oid, p, n, o, Q, R, P0, u, zs = make_problem("PEN_LIN", B, T, 20240003)
+    x, P = np.zeros((B, n)), np.tile(P0, (B, 1, 1))
+    with BatchedUkf(model, B) as f:  # defaults: Cholesky + interleaved, like the example
+        f.init(np.zeros(n), P0, Q, R)
+        for t in range(T):
+            f.step(u, zs[t])
+            x, P, st = O.ukf_step_batch(oid, p, x, P, Q, R, u, zs[t], 0.0, O.SQRT_CHOLESKY, O.ORDER_INTERLEAVED)
+        xg, Pg = f.get_state()
+        assert relerr(xg, x) < 1e-5 and relerr(Pg, P) < 1e-5
+        assert np.max(np.abs(xg - x) / (np.abs(x) + 1e-3)) < 1e-5  # per component
+
+
+def test_split_predict_update_equals_fused(gpu_required):
+    """predict() then update() (sigma points through HBM) == step() (sigma points in registers), bit for bit."""
+    B, T = 300, 4
+    for name in ("PEN_NL", "PEN6"):
+        model, oid, p, n, o, Q, R, P0, u, zs = make_problem(name, B, T, 3)
+        with BatchedUkf(model, B) as a, BatchedUkf(model, B) as b:
+            a.init(np.zeros(n), P0, Q, R)
+            b.init(np.zeros(n), P0, Q, R)
+            for t in range(T):
+                a.predict(u)
+                a.update(zs[t])
+                b.step(u, zs[t])
+            xa, Pa = a.get_state()
+            xb, Pb = b.get_state()
+            np.testing.assert_array_equal(xa, xb)
+            np.testing.assert_array_equal(Pa, Pb)
+
+
+def test_reference_style_single_filter(gpu_required):
+    """The call sequence of examples/ukf-pen2.rs:77-85 with the reference's method names, vs the oracle."""
+    oid = O.MODEL_PEN_NL
+    p = O.model_defaults(oid)
+    Q, R, P0 = ukf.default_noise(models.PEN_NL)
+    Qo, Ro, P0o = O.ukf_default_noise(oid)
+    np.testing.assert_array_equal(Q, Qo)
+    np.testing.assert_array_equal(R, Ro)
+    rng = np.random.default_rng(2)
+    x_est, P = np.zeros(4), P0.copy()
+    x_act = np.zeros(4)
+    f = UnscentedKalmanFilter.new(x_est, P0, Q, R, fx=models.PEN_NL)
+    for i in range(5):  # per-step (the filter is chaotic beyond ~10 steps, SURVEY.md finding 5)
+        x_act = O.fx(oid, p, x_act, 0.1)
+        z = O.hx(oid, p, x_act) + np.array([100.0, 100.0, 0.5]) * rng.standard_normal(3)
+        f.set_state(x_est[None], P[None])
+        f.predict(0.1, models.PEN_NL)
+        st, x_est, P, sf = O.ukf_predict(oid, p, x_est, P, Q, 0.1, 0.0, O.SQRT_EIG, O.ORDER_LIBRARY)
+        assert relerr(f.state(), x_est) < 1e-9 and relerr(f.covariance(), P) < 1e-9
+        f.update(z, models.PEN_NL)
+        st, x_est, P = O.ukf_update(oid, p, x_est, P, R, z, sf)
+        assert relerr(f.state(), x_est) < 1e-9 and relerr(f.covariance(), P) < 1e-9
+    f.close()
+
+
+def test_per_filter_u_set_q_set_r(gpu_required):
+    """Per-filter controls, set_q(gen_q(dt)) per tick (examples/mppi4-non-liner-ukf.rs:279-281) and set_r."""
+    B = 64
+    model, oid, p, n, o, Q, R, P0, u, zs = make_problem("NL6_UKF", B, 2, 9, 0.012)
+    rng = np.random.default_rng(4)
+    us = rng.uniform(-1, 1, B)
+    Q2 = O.gen_q(0.012)
+    R2 = R * 2.0
+    with BatchedUkf(model, B) as f:
+        f.init(np.zeros(n), P0, Q, R)
+        f.set_q(Q2)
+        f.set_r(R2)
+        f.step(us, zs[0], 0.012)
+        xg, Pg = f.get_state()
+    x, P, st = O.ukf_step_batch(oid, p, np.zeros((B, n)), np.tile(P0, (B, 1, 1)), Q2, R2, us, zs[0], 0.012, O.SQRT_EIG,
+                                O.ORDER_LIBRARY)
+    assert relerr(xg, x) < 1e-9 and relerr(Pg, P) < 1e-9
+
+
+def test_failure_statuses(gpu_required):
+    """Cholesky of a non-PD covariance and a singular Pz: per-filter status, reference panic strings."""
+    model, oid, p, n, o, Q, R, P0, u, zs = make_problem("PEN_LIN", 4, 1, 1)
+    with BatchedUkf(model, 4) as f:
+        f.init(np.zeros(n), P0, Q, R)
+        P = np.tile(P0, (4, 1, 1))
+        P[2] = -P0  # not positive definite
+        f.set_state(np.zeros((4, n)), P)
+        with pytest.raises(UkfError, match="Cholesky fail"):
+            f.step(u, zs[0])
+        assert list(f.status()) == [0, 0, A.CHOLESKY_FAIL, 0]
+        xg, Pg = f.get_state()
+        np.testing.assert_array_equal(Pg[2], -P0)  # the failed filter keeps its state
+        # update before predict: the reference yields NaN (sigma_f starts as NaN, src/ukf.rs:32)
+        f.init(np.zeros(n), P0, Q, R)
+        with pytest.raises(MpcB200Error, match="update before predict"):
+            f.update(zs[0])
+    with BatchedUkf(model, 2) as f:
+        f.init(np.zeros(n), np.zeros((n, n)), np.zeros((n, n)), np.zeros((o, o)))  # P = Q = R = 0 -> Pz = 0
+        with pytest.raises(UkfError):
+            f.step(u, np.zeros((2, o)))
+
+
+def test_multi_step_device_run(gpu_required):
+    """run_device: T fused steps on device-resident z[T][o][B] equal T host-driven steps."""
+    import ctypes as C
+    B, T = 1000, 10
+    model, oid, p, n, o, Q, R, P0, u, zs = make_problem("PEN_LIN", B, T, 12)
+    z_soa = np.ascontiguousarray(np.transpose(zs, (0, 2, 1)))  # [T][o][B]
+    d_z = C.c_void_p()
+    A.check(A.lib().mpcb_device_alloc(0, z_soa.nbytes, C.byref(d_z)))
+    A.check(A.lib().mpcb_device_upload(0, d_z, z_soa.ctypes.data_as(C.c_void_p), z_soa.nbytes))
+    with BatchedUkf(model, B) as a, BatchedUkf(model, B) as b:
+        a.init(np.zeros(n), P0, Q, R)
+        b.init(np.zeros(n), P0, Q, R)
+        a.run_device(T, d_z.value, u=u)
+        a.sync()
+        for t in range(T):
+            b.step(u, zs[t])
+        xa, Pa = a.get_state()
+        xb, Pb = b.get_state()
+        np.testing.assert_array_equal(xa, xb)
+        np.testing.assert_array_equal(Pa, Pb)
+    A.lib().mpcb_device_free(0, d_z)
