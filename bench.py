@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py — MPPI rollout-steps/s (and batched-UKF filter-updates/s) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" is one MPPI control step (src/mppi.rs:33-92: noise -> K x H rollout -> softmax-weighted update) on
+BASELINE.json configs[1]: examples/mppi4-non-liner.rs model NL, K = 65536 samples, H = 100 (DT = 0.8/100), FP32
+fast path, Philox noise generated in-register.  With N > 1 (torchrun, one rank per GPU) every rank rolls out its
+own 65536-sample shard of a K = 65536*N controller (weak scaling) and the partial rows meet in ONE ncclAllGather
+per control step inside the library.
+
+    value     device-resident closed loop (u_out of step i is u_in of step i+1), CUDA events per step on the
+              handle's stream, L2 flushed between timed steps, max over ranks
+    e2e       the same step through mpcb_mppi_compute with HOST buffers (inputs in the kernel parameters,
+              u_out/info written to mapped pinned memory, one stream sync per call), host wall clock
+    roofline  algorithmic FP32 flops (60 per rollout-step) / kernel time vs the FFMA peak measured
+              live by tools/peak_bench (MEASURED_PEAKS.json has no FP32 vector number)
+    ukf       BASELINE configs[2] on the side: 2^20 independent examples/ukf-pen.rs filters per GPU, FP64,
+              336 algorithmic bytes per filter-update vs the measured HBM copy bandwidth
+    cpu_baseline / --impl reference
+              the C restatement of the reference's nalgebra/rayon CPU path (oracle/, kind "port": no Rust
+              toolchain exists here or on the GPU box) on all host cores
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# ---- workload: BASELINE.json configs[1] ------------------------------------------------------------------
+K_PER_GPU = 65536
+H = 100
+DT = 0.8 / H  # T = 0.8 s as shipped (examples/mppi4-non-liner.rs:8), N raised to 100
+LAMBDA, SIGMA, LIMIT = 0.5, 3.0, (-20.0, 20.0)
+X0 = np.array([0.5, 0.0, 0.1, 0.0])  # examples/mppi4-non-liner.rs:30
+FLOPS_PER_STEP = 60.0  # model NL 58 + 2 epilogue flops per rollout-step
+UKF_B = 1 << 20
+UKF_T = 50
+UKF_BYTES = 336.0  # 8*(2n + 2n^2 + o), n=4, o=2
+FP32_FALLBACK_TFLOPS = 69.5  # tools/peak_bench on this pool's B200 (profiles/peaks_r1.json)
+FP64_FALLBACK_TFLOPS = 33.9
+METRIC = "mppi_rollout_steps_per_sec"
+UNIT = "rollout-steps/s"
+
+
+def workload(n_gpus: int) -> dict:
+    return {
+        "workload": "BASELINE configs[1]: examples/mppi4-non-liner.rs MPPI, model NL, "
+                    f"K={K_PER_GPU} samples/GPU x H={H}, DT={DT}, lambda={LAMBDA}, sigma={SIGMA}, limit=+-20",
+        "samples_per_gpu": K_PER_GPU, "samples_total": K_PER_GPU * n_gpus, "horizon": H, "controllers": 1,
+        "noise": "philox4x32-10 in-register (generate mode)", "precision": "f32 rollout, f64 accumulation/softmax",
+        "sharding": f"samples x{n_gpus}, one ncclAllGather of {H + 4} doubles per rank per step" if n_gpus > 1 else "none",
+        "l2": "flushed between timed steps (256 MiB write); inputs are O(H) bytes",
+    }
+
+
+# ---- reference arm / cpu baseline ---------------------------------------------------------------------------
+def cpu_baseline(steps: int, warmup: int, budget_s: float = 20.0):
+    """Times the CPU restatement (oracle/) of src/mppi.rs:38-91 on all host cores.  Returns (steps/s, info)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    threads = O.max_threads()
+    p = O.model_defaults(O.MODEL_NL, dt=DT)
+    K = K_PER_GPU
+    u = np.zeros(H)
+    t0 = time.perf_counter()
+    O.mppi_compute_cpu(O.MODEL_NL, p, K, H, LAMBDA, SIGMA, LIMIT[0], LIMIT[1], X0, u, seed=1, threads=threads)
+    one = time.perf_counter() - t0
+    if steps * one > budget_s:  # keep the run bounded: fewer samples per step, same H
+        K = max(4096, int(K * budget_s / (steps * one)) // 1024 * 1024)
+    for i in range(warmup):
+        O.mppi_compute_cpu(O.MODEL_NL, p, K, H, LAMBDA, SIGMA, LIMIT[0], LIMIT[1], X0, u, seed=2 + i, threads=threads)
+    x, t0 = X0.copy(), time.perf_counter()
+    for i in range(steps):
+        st, u, _ = O.mppi_compute_cpu(O.MODEL_NL, p, K, H, LAMBDA, SIGMA, LIMIT[0], LIMIT[1], x, u, seed=100 + i,
+                                      threads=threads)
+    el = time.perf_counter() - t0
+    return K * H * steps / el, {
+        "kind": "port", "cores": threads,
+        "sample": f"{steps} control steps of K={K} x H={H} (model NL) through oracle/ orc_mppi_compute_cpu: "
+                  "materialised v[K][H], six passes, xoshiro256+/ziggurat per worker, f64, -O3 -march=native "
+                  "-ffp-contract=off; C restatement of the nalgebra/rayon path, not the Rust binary",
+        "ms_per_step": el / steps * 1e3,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps = min(args.steps, 50)
+    val, info = cpu_baseline(steps, min(args.warmup, 3), budget_s=90.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 3), "ms_per_step": info["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload(args.gpus),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---- helpers ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, f"/tmp/mpcb_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            parts = [s.strip() for s in ln.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+def measured_peaks():
+    """FP32 / FP64 vector peaks from tools/peak_bench (run live), HBM from MEASURED_PEAKS.json."""
+    peaks = {"fp32_tflops": FP32_FALLBACK_TFLOPS, "fp64_tflops": FP64_FALLBACK_TFLOPS, "fp32_source": "fallback (profiles/peaks_r1.json)",
+             "hbm_gbs": 6650.0, "hbm_source": "fallback (B200_PROFILING.md)"}
+    exe = os.path.join(ROOT, "tools", "peak_bench")
+    if os.path.exists(exe):
+        try:
+            r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+            j = json.loads(r.stdout.strip().splitlines()[-1])
+            if j.get("err") == "no error" and j["fp32_tflops"] > 1:
+                peaks.update(fp32_tflops=j["fp32_tflops"], fp64_tflops=j["fp64_tflops"],
+                             fp32_source="measured live by tools/peak_bench (FFMA/DFMA chains, ILP 8)")
+        except Exception:
+            pass
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peaks.update(hbm_gbs=float(mp["hbm_gbs"]), hbm_source="measured (MEASURED_PEAKS.json)")
+    except Exception:
+        pass
+    return peaks
+
+
+def dev_alloc(A, dev, nbytes):
+    p = C.c_void_p()
+    A.check(A.lib().mpcb_device_alloc(dev, nbytes, C.byref(p)))
+    return p.value
+
+
+def upload(A, dev, dptr, arr):
+    arr = np.ascontiguousarray(arr)
+    A.check(A.lib().mpcb_device_upload(dev, dptr, arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+
+
+# ---- GPU arm --------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from mpc_rs_b200 import BatchedUkf, Mppi, comm_unique_id, models
+    from mpc_rs_b200 import _abi as A
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N > 1 with torchrun (one rank per GPU); see the module docstring")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libmpc_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = local
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- controller: global K = K_PER_GPU * world, this rank's shard = K_PER_GPU samples ----
+    mppi = Mppi(H, K_PER_GPU * world, model=models.NL, lam=LAMBDA, std_dev=SIGMA, limit=LIMIT, precision="f32", dt=DT,
+                device=dev, rank=rank, world_size=world, seed=20240001)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        mppi.attach_comm(bytes(uid.cpu().numpy().tobytes()))
+
+    stream = torch.cuda.ExternalStream(mppi.stream, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    d_x = dev_alloc(A, dev, 32)
+    d_u = [dev_alloc(A, dev, 8 * H), dev_alloc(A, dev, 8 * H)]
+    upload(A, dev, d_x, X0)
+    upload(A, dev, d_u[0], np.zeros(H))
+
+    def device_step(i):
+        mppi.compute_device(d_x, d_u[i & 1], d_u[(i + 1) & 1])
+
+    for i in range(args.warmup):
+        device_step(i)
+    mppi.sync()
+
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = mppi.launches
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    with torch.cuda.stream(stream):
+        for i in range(args.steps):
+            flush.zero_()  # L2 flush (256 MiB write) on the handle's stream, outside the event pair
+            evs[i][0].record(stream)
+            device_step(args.warmup + i)
+            evs[i][1].record(stream)
+    mppi.sync()
+    barrier()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = max_over_ranks(float(np.sum(step_ms)))
+    launches = mppi.launches - launches0
+    steps_total = K_PER_GPU * world * H * args.steps
+    value = steps_total / (total_ms * 1e-3)
+    info = mppi.last_info()[0]
+    if info["status"] != 0:
+        raise SystemExit(f"MPPI reported status {info['status']} in the timed region")
+
+    # back-to-back variant (no flush, launches queued): kernel duration proper for the roofline
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        device_step(i)
+    e1.record(stream)
+    mppi.sync()
+    kern_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+
+    # ---- e2e: host buffers through mpcb_mppi_compute ----
+    x_h, u_h = X0.copy(), np.zeros(H)
+    for _ in range(args.warmup):
+        u_h = mppi.compute(x_h, u_h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        u_h = mppi.compute(x_h, u_h)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = steps_total / e2e_s
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- UKF, BASELINE configs[2]: 2^20 examples/ukf-pen.rs filters per GPU ----
+    ukf_out = None
+    try:
+        f = BatchedUkf(models.PEN_LIN, UKF_B, device=dev)
+        Q, R, P0 = __import__("mpc_rs_b200").ukf.default_noise(models.PEN_LIN)
+        f.init(np.zeros(4), P0, Q, R)
+        g = torch.Generator(device="cuda").manual_seed(20240003 + rank)
+        z = 0.7 * torch.randn((UKF_T, 2, UKF_B), dtype=torch.float64, device="cuda", generator=g)
+        ustream = torch.cuda.ExternalStream(f.stream, device=dev)
+        torch.cuda.synchronize()
+        zs = z.element_size() * 2 * UKF_B
+        for t in range(3):
+            f.run_device(1, z.data_ptr() + t * zs, u=0.0015)
+        f.sync()
+        barrier()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ul0 = f.launches
+        u0.record(ustream)
+        for t in range(UKF_T):  # one launch per filter step: x, P, z in; x, P out (336 B per update)
+            f.run_device(1, z.data_ptr() + t * zs, u=0.0015)
+        u1.record(ustream)
+        f.sync()
+        step_ms_ukf = max_over_ranks(u0.elapsed_time(u1))
+        f.init(np.zeros(4), P0, Q, R)
+        barrier()
+        u0.record(ustream)
+        f.run_device(UKF_T, z.data_ptr(), u=0.0015)  # T steps fused: state stays in registers
+        u1.record(ustream)
+        f.sync()
+        fused_ms_ukf = max_over_ranks(u0.elapsed_time(u1))
+        st = f.status()
+        ukf_launches = f.launches - ul0
+        upd = UKF_B * UKF_T * world
+        ukf_out = {
+            "metric": "ukf_filter_updates_per_sec", "unit": "filter-updates/s",
+            "value": upd / (step_ms_ukf * 1e-3), "fused_value": upd / (fused_ms_ukf * 1e-3),
+            "config": {"workload": f"BASELINE configs[2]: examples/ukf-pen.rs UKF (n=4,o=2, Cholesky), B={UKF_B} filters/GPU, "
+                                   f"{UKF_T} steps, FP64, SoA", "filters_per_gpu": UKF_B, "steps": UKF_T},
+            "ms_per_step": step_ms_ukf / UKF_T, "fused_ms_per_step": fused_ms_ukf / UKF_T, "dtype": "f64",
+            "failed_filters": int((st != 0).sum()), "gpu_launches": int(ukf_launches),
+        }
+        f.close()
+        del z
+    except Exception as e:  # the MPPI line is still valid; say what happened
+        ukf_out = {"error": repr(e)}
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = measured_peaks()
+    ach_tflops = K_PER_GPU * H * FLOPS_PER_STEP / (kern_ms * 1e-3) / 1e12
+    roof = {
+        "bound": "fp32", "kernel": "mppi_rollout_kernel<ModelNL,float,128,generate>",
+        "achieved": ach_tflops, "peak": peaks["fp32_tflops"], "unit": "TFLOP/s", "frac": ach_tflops / peaks["fp32_tflops"],
+        "traffic": None, "kernel_ms": kern_ms,
+        "note": f"{FLOPS_PER_STEP:.0f} algorithmic FP32 flops per rollout-step (SURVEY.md 8d) x {K_PER_GPU * H} steps per launch; "
+                f"peak = {peaks['fp32_source']}; HBM traffic is O(blocks*H) partial rows, not a bound",
+    }
+    if ukf_out and "value" in ukf_out:
+        gbs = ukf_out["value"] / world * UKF_BYTES / 1e9
+        ukf_out["roofline"] = {"bound": "hbm", "kernel": "ukf_kernel<4,2,PEN_LIN,cholesky,interleaved,fused>", "achieved": gbs,
+                               "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+                               "note": f"{UKF_BYTES:.0f} algorithmic bytes per filter-update; peak = {peaks['hbm_source']}; "
+                                       f"FP64 pipe peak {peaks['fp64_tflops']:.1f} TFLOP/s ({peaks['fp32_source']})"}
+    cpu_val, cpu_info = cpu_baseline(3, 1, budget_s=15.0) if world == 1 else (None, None)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload(world),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * (4 + H) * world,
+                "d2h_bytes_per_step": (8 * H + 40) * world, "ms_per_step": e2e_s / args.steps * 1e3},
+        "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
+        "state_updates_per_sec": value * 4, "ukf": ukf_out,
+    }
+    if cpu_val is not None:
+        line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": cpu_info["cores"], "kind": cpu_info["kind"],
+                                "sample": cpu_info["sample"]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -41,13 +41,15 @@ class Mppi:
     """MPPI controller: N = horizon, K = samples, S = state dimension (src/mppi.rs:7)."""
 
     def __init__(self, N: int, K: int, S: int = 4, *, model: DeviceModel, lam: float, std_dev: float,
-                 limit=(-float("inf"), float("inf")), precision: str = "f32", controllers: int = 1, seed: int = None,
+                 limit=(-float("inf"), float("inf")), precision: str = None, controllers: int = 1, seed: int = None,
                  device: int = 0, rank: int = 0, world_size: int = 1, keep_costs: bool = False, dt: float = None,
                  params: dict = None):
         L = A.lib()
         cfg = A.MppiCfg()
         A.check(L.mpcb_mppi_default_cfg(model.model_id, C.byref(cfg)))
-        cfg.precision = {"f32": A.F32, "f64": A.F64}[precision]
+        if precision is not None:  # default: f32 for L/NL, f64 for NL6 (mpcb_mppi_default_cfg)
+            cfg.precision = {"f32": A.F32, "f64": A.F64}[precision]
+        precision = "f64" if cfg.precision == A.F64 else "f32"
         cfg.horizon, cfg.samples, cfg.state_dim = int(N), int(K), int(S)
         cfg.controllers, cfg.device, cfg.rank, cfg.world_size = int(controllers), int(device), int(rank), int(world_size)
         cfg.lambda_, cfg.std_dev = float(lam), float(std_dev)
