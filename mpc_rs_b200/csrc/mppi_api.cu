@@ -1,6 +1,7 @@
 // mppi_api.cu — C ABI of the MPPI controller (mpcb_mppi_*), replacing mpc::mppi::Mppi (src/mppi.rs:7-92).
 #include <dlfcn.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <new>
 
@@ -33,6 +34,7 @@ struct mpcb_mppi {
     void* d_eps = nullptr;
     size_t d_eps_bytes = 0;
     void* d_dump = nullptr;
+    unsigned long long* d_ts = nullptr;  // diagnostics: per-block timeline stamps (MPCB_DEBUG_TS=1)
     // pinned / mapped host
     double* h_in = nullptr;              // [C][4] then [C][H]
     double* h_out = nullptr;             // mapped: [C][H]
@@ -129,6 +131,7 @@ void fill_params(const mpcb_mppi* h, MppiParams* p) {
     p->rank_partial = h->d_rank_partial;
     p->mc = h->mc;
     p->costs = h->cfg.keep_costs ? h->d_costs : nullptr;
+    p->debug_ts = h->d_ts;
 }
 
 // Enqueue one fused control step.
@@ -339,6 +342,10 @@ mpcb_status mpcb_mppi_create(mpcb_mppi** out, const mpcb_mppi_cfg* cfg) {
     TRY_OR_FAIL(cudaMemset(h->d_counters, 0, C * (size_t)(h->groups + 1) * sizeof(unsigned int)));
     TRY_OR_FAIL(cudaMalloc(&h->d_info, C * sizeof(mpcb_mppi_info)));
     TRY_OR_FAIL(cudaMemset(h->d_info, 0, C * sizeof(mpcb_mppi_info)));
+    if (getenv("MPCB_DEBUG_TS")) {
+        TRY_OR_FAIL(cudaMalloc(&h->d_ts, C * (size_t)h->chunks * 8 * sizeof(unsigned long long)));
+        TRY_OR_FAIL(cudaMemset(h->d_ts, 0, C * (size_t)h->chunks * 8 * sizeof(unsigned long long)));
+    }
     if (cfg->keep_costs) TRY_OR_FAIL(cudaMalloc(&h->d_costs, C * (size_t)h->K_local * sizeof(double)));
     TRY_OR_FAIL(cudaHostAlloc(&h->h_in, C * (4 + H) * sizeof(double), cudaHostAllocDefault));
     TRY_OR_FAIL(cudaHostAlloc(&h->h_out, C * H * sizeof(double), cudaHostAllocMapped));
@@ -368,6 +375,7 @@ void mpcb_mppi_destroy(mpcb_mppi* h) {
     cudaFree(h->d_costs);
     cudaFree(h->d_eps);
     cudaFree(h->d_dump);
+    cudaFree(h->d_ts);
     if (h->h_in) cudaFreeHost(h->h_in);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_info) cudaFreeHost(h->h_info);
@@ -468,6 +476,18 @@ mpcb_status mpcb_mppi_last_info(mpcb_mppi* h, mpcb_mppi_info* info) {
     MPCB_CUDA_TRY(cudaStreamSynchronize(h->stream));
     MPCB_CUDA_TRY(cudaMemcpy(info, h->d_info, (size_t)h->C * sizeof(mpcb_mppi_info), cudaMemcpyDeviceToHost));
     return MPCB_OK;
+}
+
+// Diagnostics (MPCB_DEBUG_TS=1 at create): %globaltimer stamps [blocks][8] of the last launch:
+// 0 block start, 1 rollouts done, 2 ticket taken, 3 group merged, 4 second ticket, 5 final merge done.
+int64_t mpcb_mppi_debug_timeline(mpcb_mppi* h, unsigned long long* out, int64_t max_blocks) {
+    if (!h || !h->d_ts || !out) return 0;
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->stream);
+    int64_t n = (int64_t)h->C * h->chunks;
+    if (n > max_blocks) n = max_blocks;
+    cudaMemcpy(out, h->d_ts, (size_t)n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    return n;
 }
 
 void* mpcb_mppi_stream(mpcb_mppi* h) { return h ? (void*)h->stream : nullptr; }

@@ -56,6 +56,7 @@ struct MppiParams {
     mpcb_mppi_info* info;    // [C]
     mpcb_mppi_info* info_host;
     double* rank_partial;    // [C][kPartialHdr + H]
+    unsigned long long* debug_ts;  // optional [blocks][8] %globaltimer stamps (diagnostics)
     ModelConsts mc;
     double xu_inline[4 + kInlineHorizon];
 };
@@ -65,15 +66,34 @@ __device__ __forceinline__ long long double_as_ll(double v) { return __double_as
 
 constexpr long long kNoArg = 0x7fffffffffffffffll;
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define MPCB_TS(slot)                                                                       \
+    do {                                                                                    \
+        if (p.debug_ts != nullptr && threadIdx.x == 0) p.debug_ts[(size_t)blockIdx.x * 8 + (slot)] = globaltimer_ns(); \
+    } while (0)
+
+// gpu-scope release/acquire fence around the ticket atomics (cheaper than the sequentially consistent
+// __threadfence(); the ticket pattern only needs release on the producer and acquire on the consumer side)
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
 // Merges n_rows (<= kMergeFan) partial rows (row r at rows + r*row_stride) of one controller; the whole
 // block participates.  scratch: kScratchDoubles doubles of shared memory.
 //   final_mode 1: the merged, un-normalised row is written to out_row
 //   final_mode 0: u_out = sum_w*v / sum_w, info, status                      (src/mppi.rs:76-91)
+// All global loads of a merge are issued up front (headers and up to kMergeBatch values per thread), so a
+// level costs about one L2 round trip instead of one per pass.
+constexpr int kMergeBatch = 16;
+
 template <int BLOCK>
 __device__ void mppi_merge_rows(const double* rows, long long row_stride, int n_rows, int H, double lambda,
                                 int final_mode, double* u_out, double* u_out_host, mpcb_mppi_info* info,
                                 mpcb_mppi_info* info_host, double* out_row, double* scratch) {
     constexpr int NW = BLOCK / 32;
+    constexpr int RPT = (kMergeFan + BLOCK - 1) / BLOCK;  // header rows per thread
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     double* red_m = scratch;                        // [8]
     long long* red_a = (long long*)(scratch + 8);   // [8]
@@ -82,24 +102,36 @@ __device__ void mppi_merge_rows(const double* rows, long long row_stride, int n_
     double* sc = scratch + 32;                      // [kMergeFan] per-row scale
     __shared__ int s_status;
 
-    // pass 1: max / argmax / finite count over the row headers (independent loads)
-    double m = -CUDART_INF, rm_mine[(kMergeFan + BLOCK - 1) / BLOCK], rs_mine[(kMergeFan + BLOCK - 1) / BLOCK];
-    long long a = kNoArg, n = 0;
+    // ---- issue every load of the first column pass: row headers + the first kMergeBatch rows of column tid ----
+    double hm[RPT], hs[RPT];
+    long long ha[RPT], hn[RPT];
 #pragma unroll
-    for (int i = 0; i < (kMergeFan + BLOCK - 1) / BLOCK; ++i) {
+    for (int i = 0; i < RPT; ++i) {
         const int r = tid + i * BLOCK;
-        rm_mine[i] = -CUDART_INF;
-        rs_mine[i] = 0.0;
+        hm[i] = -CUDART_INF; hs[i] = 0.0; ha[i] = -1; hn[i] = 0;
         if (r < n_rows) {
             const double* row = rows + (long long)r * row_stride;
-            const double rm = __ldcg(row + 0);
-            const double rs = __ldcg(row + 1);
-            const long long ra = double_as_ll(__ldcg(row + 2));
-            n += double_as_ll(__ldcg(row + 3));
-            rm_mine[i] = rm;
-            rs_mine[i] = rs;
-            if (ra >= 0 && (rm > m || (rm == m && ra < a))) { m = rm; a = ra; }
+            hm[i] = __ldcg(row + 0);
+            hs[i] = __ldcg(row + 1);
+            ha[i] = double_as_ll(__ldcg(row + 2));
+            hn[i] = double_as_ll(__ldcg(row + 3));
         }
+    }
+    double v0[kMergeBatch];
+    {
+        const double* col = rows + kPartialHdr + tid;
+#pragma unroll
+        for (int i = 0; i < kMergeBatch; ++i)
+            v0[i] = (tid < H && i < n_rows) ? __ldcg(col + (long long)i * row_stride) : 0.0;
+    }
+
+    // ---- max / argmax / finite count over the headers ----
+    double m = -CUDART_INF;
+    long long a = kNoArg, n = 0;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        n += hn[i];
+        if (ha[i] >= 0 && (hm[i] > m || (hm[i] == m && ha[i] < a))) { m = hm[i]; a = ha[i]; }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -119,16 +151,16 @@ __device__ void mppi_merge_rows(const double* rows, long long row_stride, int n_
         if (om > m || (om == m && oa < a)) { m = om; a = oa; }
     }
     const bool any = (a != kNoArg);
-    // pass 2: per-row scale exp((m_r - m)/lambda) and the merged sum of weights
+    // ---- per-row scale exp((m_r - m)/lambda) and the merged sum of weights ----
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < (kMergeFan + BLOCK - 1) / BLOCK; ++i) {
+    for (int i = 0; i < RPT; ++i) {
         const int r = tid + i * BLOCK;
         if (r < n_rows) {
-            const bool empty = (rm_mine[i] == -CUDART_INF);  // the row saw no finite cost
-            const double scale = empty ? 0.0 : exp((rm_mine[i] - m) / lambda);
+            const bool empty = (hm[i] == -CUDART_INF);  // the row saw no finite cost
+            const double scale = empty ? 0.0 : exp((hm[i] - m) / lambda);
             // an empty row's sum_w is 0, or NaN/inf when it saw NaN/+inf costs: keep that poison (f64 semantics)
-            s += empty ? rs_mine[i] : scale * rs_mine[i];
+            s += empty ? hs[i] : scale * hs[i];
             sc[r] = scale;
         }
     }
@@ -139,19 +171,24 @@ __device__ void mppi_merge_rows(const double* rows, long long row_stride, int n_
     s = red_s[0];
 #pragma unroll
     for (int w = 1; w < NW; ++w) s += red_s[w];
-    // pass 3: merged weighted control sums; 8 independent loads in flight per thread
+    // ---- merged weighted control sums ----
     for (int t = tid; t < H; t += BLOCK) {
         double acc = 0.0;
         const double* col = rows + kPartialHdr + t;
-        int r = 0;
-        for (; r + 8 <= n_rows; r += 8) {
-            double v[8];
+        for (int r0 = 0; r0 < n_rows; r0 += kMergeBatch) {
+            double v[kMergeBatch];
+            if (t == tid && r0 == 0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __ldcg(col + (long long)(r + i) * row_stride);
+                for (int i = 0; i < kMergeBatch; ++i) v[i] = v0[i];
+            } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc += sc[r + i] * v[i];  // scale 0 * NaN = NaN keeps the reference's poisoning
+                for (int i = 0; i < kMergeBatch; ++i)
+                    v[i] = (r0 + i < n_rows) ? __ldcg(col + (long long)(r0 + i) * row_stride) : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < kMergeBatch; ++i)
+                if (r0 + i < n_rows) acc += sc[r0 + i] * v[i];  // scale 0 * NaN = NaN keeps the reference's poisoning
         }
-        for (; r < n_rows; ++r) acc += sc[r] * __ldcg(col + (long long)r * row_stride);
         if (final_mode == 1) {
             out_row[kPartialHdr + t] = acc;
         } else {
@@ -227,6 +264,7 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
     const int c = blockIdx.x / p.chunks;      // controller
     const int chunk = blockIdx.x % p.chunks;  // sample chunk of this controller
 
+    MPCB_TS(0);
     // ---- prologue: model constants, x0, u_n ----
     ModelT<real> model;
     model.load(p.mc);
@@ -394,21 +432,27 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
         nfin_run += bn;
 
         // ---- PASS 4-5: weights against the running max, rescale of what was accumulated so far ----
+        // exp(a) is exactly 0 in f64 for a < -745.14: skipping the call there is bit-identical and spares most
+        // warps the FP64 exp (far-from-best samples dominate).
         double w;
-        if constexpr (kExact) {
-            // reference semantics: exp((c - max)/lambda) for every sample, NaN/+inf poison the sums (:71-74)
-            if (!valid || ck == -CUDART_INF) w = 0.0;
-            else w = exp((ck - m_run) / lambda);
-        } else {
-            // FP32 rollouts can overflow where the f64 reference yields a huge finite cost whose weight
-            // underflows to exactly 0: non-finite costs get weight 0 here.
-            w = fin ? exp((ck - m_run) / lambda) : 0.0;
+        {
+            const double arg = (ck - m_run) / lambda;
+            if constexpr (kExact) {
+                // reference semantics: exp((c - max)/lambda) for every sample, NaN/+inf poison the sums (:71-74)
+                if (!valid || ck == -CUDART_INF) w = 0.0;
+                else w = (arg < -746.0) ? 0.0 : exp(arg);
+            } else {
+                // FP32 rollouts can overflow where the f64 reference yields a huge finite cost whose weight
+                // underflows to exactly 0: non-finite costs get weight 0 here.
+                w = (fin && arg >= -746.0) ? exp(arg) : 0.0;
+            }
         }
-        const double resc = (m_old == -CUDART_INF) ? 0.0 : exp((m_old - m_run) / lambda);
         w_s[tid] = (real)w;
         const double wsum = warp_sum_f64(w);
         if (lane == 0) red_s[wid] = wsum;
+        if (tid == 0) red_s[NW] = (m_old == -CUDART_INF) ? 0.0 : exp((m_old - m_run) / lambda);  // block-uniform rescale
         __syncthreads();
+        const double resc = red_s[NW];
         double bs = red_s[0];
 #pragma unroll
         for (int wI = 1; wI < NW; ++wI) bs += red_s[wI];
@@ -430,6 +474,7 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
         __syncthreads();
     }
 
+    MPCB_TS(1);
     // ---- partial row of this block, then the two-level ticket merge ----
     const int PL = kPartialHdr + H;
     double* ctrl_rows = p.partial + (long long)c * (p.chunks + p.groups) * PL;
@@ -448,12 +493,13 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
     int g_rows = p.chunks - g_first;
     if (g_rows > p.group_size) g_rows = p.group_size;
 
-    __threadfence();
+    fence_acq_rel_gpu();
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(&cnt[g], 1u) == (unsigned int)(g_rows - 1));
     __syncthreads();
+    MPCB_TS(2);
     if (!s_last) return;
-    __threadfence();
+    fence_acq_rel_gpu();
     double* u_out_c = p.u_out + (long long)c * H;
     double* u_host_c = p.u_out_host ? p.u_out_host + (long long)c * H : nullptr;
     mpcb_mppi_info* info_host_c = p.info_host ? p.info_host + c : nullptr;
@@ -462,21 +508,25 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
         mppi_merge_rows<BLOCK>(ctrl_rows, PL, p.chunks, H, lambda, p.final_mode, u_out_c, u_host_c, p.info + c,
                                info_host_c, rank_row, scratch);
         if (tid == 0) cnt[0] = 0u;  // ready for the next launch
+        MPCB_TS(3);
         return;
     }
     double* group_rows = ctrl_rows + (long long)p.chunks * PL;
     mppi_merge_rows<BLOCK>(ctrl_rows + (long long)g_first * PL, PL, g_rows, H, lambda, 1, nullptr, nullptr, nullptr,
                            nullptr, group_rows + (long long)g * PL, scratch);
     if (tid == 0) cnt[g] = 0u;
-    __threadfence();
+    MPCB_TS(3);
+    fence_acq_rel_gpu();
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(&cnt[p.groups], 1u) == (unsigned int)(p.groups - 1));
     __syncthreads();
+    MPCB_TS(4);
     if (!s_last) return;
-    __threadfence();
+    fence_acq_rel_gpu();
     mppi_merge_rows<BLOCK>(group_rows, PL, p.groups, H, lambda, p.final_mode, u_out_c, u_host_c, p.info + c, info_host_c,
                            rank_row, scratch);
     if (tid == 0) cnt[p.groups] = 0u;
+    MPCB_TS(5);
 }
 
 // Cross-rank merge: rows[g][c][PL] gathered from all ranks -> u_out / info.  One block per controller.

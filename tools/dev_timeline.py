@@ -1,0 +1,36 @@
+"""Developer probe: per-block timeline of one MPPI launch (MPCB_DEBUG_TS=1)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+os.environ["MPCB_DEBUG_TS"] = "1"
+sys.path.insert(0, ".")
+from mpc_rs_b200 import Mppi, models
+from mpc_rs_b200 import _abi as A
+
+K = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+H = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+L = A.lib()
+L.mpcb_mppi_debug_timeline.restype = C.c_int64
+L.mpcb_mppi_debug_timeline.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+m = Mppi(H, K, model=models.NL, lam=0.5, std_dev=3.0, limit=(-20, 20), precision="f32", dt=0.8 / H)
+p = C.c_void_p()
+A.check(L.mpcb_device_alloc(0, 8 * (4 + 2 * H), C.byref(p)))
+xu = np.concatenate([[0.5, 0, 0.1, 0.0], np.zeros(2 * H)])
+L.mpcb_device_upload(0, p, xu.ctypes.data_as(C.c_void_p), xu.nbytes)
+for _ in range(5):
+    m.compute_device(p.value, p.value + 32, p.value + 32 + 8 * H)
+m.sync()
+buf = np.zeros((4096, 8), dtype=np.uint64)
+n = L.mpcb_mppi_debug_timeline(m._h, buf.ctypes.data_as(C.c_void_p), 4096)
+ts = buf[:n].astype(np.int64)
+t0 = ts[:, 0].min()
+rel = np.where(ts > 0, ts - t0, -1)
+print(f"K={K} H={H} blocks={n}")
+names = ["start", "rollouts done", "ticket1", "group merged", "ticket2", "final done"]
+for i, nm in enumerate(names):
+    col = rel[:, i][rel[:, i] >= 0]
+    if len(col):
+        print(f"  {nm:14s} n={len(col):4d}  min {col.min()/1e3:7.2f} us  median {np.median(col)/1e3:7.2f} us  max {col.max()/1e3:7.2f} us")
