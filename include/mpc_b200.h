@@ -211,6 +211,11 @@ typedef struct mpcb_ukf_cfg {
     int32_t sqrt_mode;   /* mpcb_sqrt_mode */
     int32_t sigma_order; /* mpcb_sigma_order */
     int32_t device;
+    int32_t exact;       /* 0 (default): FMA contraction, symmetric-half covariance sums, shared sigma weight
+                          * factored out — rounding-level (~1e-10) away from the reference order, ~1.5x faster;
+                          * 1: the reference's operation order without FMA (bit-exact vs an f64 restatement
+                          * wherever libm agrees) */
+    int32_t reserved;
     int64_t batch;       /* B filters on this handle (the caller shards B across GPUs; no exchange) */
     mpcb_model_params model;
 } mpcb_ukf_cfg;

@@ -68,6 +68,8 @@ class UkfCfg(C.Structure):
         ("sqrt_mode", C.c_int32),
         ("sigma_order", C.c_int32),
         ("device", C.c_int32),
+        ("exact", C.c_int32),
+        ("reserved", C.c_int32),
         ("batch", C.c_int64),
         ("model", ModelParams),
     ]

@@ -270,7 +270,7 @@ mpcb_status mpcb_ukf_create(mpcb_ukf** out, const mpcb_ukf_cfg* cfg) {
         h->wm0 = LAMBDA / Cc;
         h->wc0 = LAMBDA / Cc + 1.0 - ALPHA * ALPHA + BETA;
     }
-    auto pick = (n == 4) ? ukf_kernel_n4 : ukf_kernel_n6;
+    auto pick = cfg->exact ? ((n == 4) ? ukf_kernel_n4 : ukf_kernel_n6) : ((n == 4) ? ukf_kernel_n4_fast : ukf_kernel_n6_fast);
     h->k_predict = pick(cfg->model_id, cfg->sqrt_mode, cfg->sigma_order, UKF_PREDICT);
     h->k_update = pick(cfg->model_id, cfg->sqrt_mode, cfg->sigma_order, UKF_UPDATE);
     h->k_fused = pick(cfg->model_id, cfg->sqrt_mode, cfg->sigma_order, UKF_FUSED);

@@ -335,40 +335,81 @@ template <int N, int ORDER>
 __device__ __forceinline__ constexpr int col_minus(int i) { return ORDER == MPCB_ORDER_INTERLEAVED ? 2 + 2 * i : 1 + N + i; }
 
 // unscented_transform (src/ukf.rs:96-110): mean = sigmas*wm, P = sum_i wc_i y_i y_i^T + cov
-template <int S, int M>
+//   FAST = false: the reference's operation order, every (r,c) entry accumulated separately, no FMA (TU flag)
+//   FAST = true : the weight shared by i >= 1 is factored out, only the upper triangle is accumulated and then
+//                 mirrored (each y_i y_i^T is symmetric), FMA contraction on — ~40% fewer FP64 instructions;
+//                 differs from the reference order at rounding level (x 1.7e5 weight amplification ~ 1e-10)
+template <int S, int M, bool FAST>
 __device__ __forceinline__ void unscented_transform(const double (&sig)[S][M], double wm0, double wc0, double wi,
                                                     const double* cov, double (&mean)[S], double (&P)[S][S]) {
-#pragma unroll
-    for (int r = 0; r < S; ++r) {
-        double acc = sig[r][0] * wm0;
-#pragma unroll
-        for (int i = 1; i < M; ++i) acc += sig[r][i] * wi;
-        mean[r] = acc;
-    }
-#pragma unroll
-    for (int r = 0; r < S; ++r)
-#pragma unroll
-        for (int c = 0; c < S; ++c) P[r][c] = 0.0;
-#pragma unroll
-    for (int i = 0; i < M; ++i) {
-        double y[S];
-#pragma unroll
-        for (int r = 0; r < S; ++r) y[r] = sig[r][i] - mean[r];
-        const double w = (i == 0) ? wc0 : wi;
+    if constexpr (!FAST) {
 #pragma unroll
         for (int r = 0; r < S; ++r) {
-            const double wy = w * y[r];
+            double acc = sig[r][0] * wm0;
 #pragma unroll
-            for (int c = 0; c < S; ++c) P[r][c] += wy * y[c];
+            for (int i = 1; i < M; ++i) acc += sig[r][i] * wi;
+            mean[r] = acc;
+        }
+#pragma unroll
+        for (int r = 0; r < S; ++r)
+#pragma unroll
+            for (int c = 0; c < S; ++c) P[r][c] = 0.0;
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            double y[S];
+#pragma unroll
+            for (int r = 0; r < S; ++r) y[r] = sig[r][i] - mean[r];
+            const double w = (i == 0) ? wc0 : wi;
+#pragma unroll
+            for (int r = 0; r < S; ++r) {
+                const double wy = w * y[r];
+#pragma unroll
+                for (int c = 0; c < S; ++c) P[r][c] += wy * y[c];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < S; ++r)
+#pragma unroll
+            for (int c = 0; c < S; ++c) P[r][c] = P[r][c] + cov[r * S + c];
+    } else {
+#pragma unroll
+        for (int r = 0; r < S; ++r) {
+            double acc = sig[r][1];
+#pragma unroll
+            for (int i = 2; i < M; ++i) acc += sig[r][i];
+            mean[r] = fma(acc, wi, sig[r][0] * wm0);
+        }
+#pragma unroll
+        for (int r = 0; r < S; ++r)
+#pragma unroll
+            for (int c = r; c < S; ++c) P[r][c] = 0.0;
+#pragma unroll
+        for (int i = 1; i < M; ++i) {
+            double y[S];
+#pragma unroll
+            for (int r = 0; r < S; ++r) y[r] = sig[r][i] - mean[r];
+#pragma unroll
+            for (int r = 0; r < S; ++r)
+#pragma unroll
+                for (int c = r; c < S; ++c) P[r][c] = fma(y[r], y[c], P[r][c]);
+        }
+        double y0[S];
+#pragma unroll
+        for (int r = 0; r < S; ++r) y0[r] = sig[r][0] - mean[r];
+#pragma unroll
+        for (int r = 0; r < S; ++r) {
+            const double wy = wc0 * y0[r];
+#pragma unroll
+            for (int c = r; c < S; ++c) {
+                const double v = fma(wi, P[r][c], fma(wy, y0[c], cov[r * S + c]));
+                P[r][c] = v;
+                P[c][r] = v;
+            }
         }
     }
-#pragma unroll
-    for (int r = 0; r < S; ++r)
-#pragma unroll
-        for (int c = 0; c < S; ++c) P[r][c] = P[r][c] + cov[r * S + c];
 }
 
-template <int N, int O, int MODEL, int SQRT, int ORDER, int MODE>
+template <int N, int O, int MODEL, int SQRT, int ORDER, int MODE, bool FAST>
 __global__ void __launch_bounds__(128) ukf_kernel(const __grid_constant__ UkfParams p) {
     constexpr int M = 2 * N + 1;
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -430,7 +471,7 @@ __global__ void __launch_bounds__(128) ukf_kernel(const __grid_constant__ UkfPar
 #pragma unroll
                 for (int r = 0; r < N; ++r) sig[r][i] = col[r];
             }
-            unscented_transform<N, M>(sig, p.wm0, p.wc0, p.wi, p.Q, x, P);
+            unscented_transform<N, M, FAST>(sig, p.wm0, p.wc0, p.wi, p.Q, x, P);
         }
         if constexpr (MODE != UKF_PREDICT) {
             // ---- update (src/ukf.rs:54-74) ----
@@ -445,20 +486,46 @@ __global__ void __launch_bounds__(128) ukf_kernel(const __grid_constant__ UkfPar
                 for (int r = 0; r < O; ++r) zs[r][i] = zz[r];
             }
             double zp[O], pz[O][O];
-            unscented_transform<O, M>(zs, p.wm0, p.wc0, p.wi, p.R, zp, pz);
+            unscented_transform<O, M, FAST>(zs, p.wm0, p.wc0, p.wi, p.R, zp, pz);
             double pxz[N][O];
+            if constexpr (!FAST) {
 #pragma unroll
-            for (int r = 0; r < N; ++r)
+                for (int r = 0; r < N; ++r)
 #pragma unroll
-                for (int c = 0; c < O; ++c) pxz[r][c] = 0.0;
+                    for (int c = 0; c < O; ++c) pxz[r][c] = 0.0;
 #pragma unroll
-            for (int i = 0; i < M; ++i) {
-                const double w = (i == 0) ? p.wc0 : p.wi;
+                for (int i = 0; i < M; ++i) {
+                    const double w = (i == 0) ? p.wc0 : p.wi;
+#pragma unroll
+                    for (int r = 0; r < N; ++r) {
+                        const double wdx = w * (sig[r][i] - x[r]);
+#pragma unroll
+                        for (int c = 0; c < O; ++c) pxz[r][c] += wdx * (zs[c][i] - zp[c]);
+                    }
+                }
+            } else {
+                // sum_{i>=1} dx_i dz_i^T first (shared weight factored out), then the i = 0 term
+#pragma unroll
+                for (int r = 0; r < N; ++r)
+#pragma unroll
+                    for (int c = 0; c < O; ++c) pxz[r][c] = 0.0;
+#pragma unroll
+                for (int i = 1; i < M; ++i) {
+                    double dz[O];
+#pragma unroll
+                    for (int c = 0; c < O; ++c) dz[c] = zs[c][i] - zp[c];
+#pragma unroll
+                    for (int r = 0; r < N; ++r) {
+                        const double dx = sig[r][i] - x[r];
+#pragma unroll
+                        for (int c = 0; c < O; ++c) pxz[r][c] = fma(dx, dz[c], pxz[r][c]);
+                    }
+                }
 #pragma unroll
                 for (int r = 0; r < N; ++r) {
-                    const double wdx = w * (sig[r][i] - x[r]);
+                    const double wdx = p.wc0 * (sig[r][0] - x[r]);
 #pragma unroll
-                    for (int c = 0; c < O; ++c) pxz[r][c] += wdx * (zs[c][i] - zp[c]);
+                    for (int c = 0; c < O; ++c) pxz[r][c] = fma(p.wi, pxz[r][c], wdx * (zs[c][0] - zp[c]));
                 }
             }
             double pzi[O][O];
@@ -493,23 +560,38 @@ __global__ void __launch_bounds__(128) ukf_kernel(const __grid_constant__ UkfPar
                     for (int j = 1; j < O; ++j) acc += k[r][j] * pz[j][c];
                     kp[r][c] = acc;
                 }
+            if constexpr (!FAST) {
 #pragma unroll
-            for (int r = 0; r < N; ++r)
+                for (int r = 0; r < N; ++r)
 #pragma unroll
-                for (int c = 0; c < N; ++c) {
-                    double acc = kp[r][0] * k[c][0];
+                    for (int c = 0; c < N; ++c) {
+                        double acc = kp[r][0] * k[c][0];
 #pragma unroll
-                    for (int j = 1; j < O; ++j) acc += kp[r][j] * k[c][j];
-                    P[r][c] -= acc;
-                }
+                        for (int j = 1; j < O; ++j) acc += kp[r][j] * k[c][j];
+                        P[r][c] -= acc;
+                    }
 #pragma unroll
-            for (int r = 0; r < N; ++r)
+                for (int r = 0; r < N; ++r)
 #pragma unroll
-                for (int c = r; c < N; ++c) {
-                    const double a = (P[r][c] + P[c][r]) / 2.0;
-                    P[r][c] = a;
-                    P[c][r] = a;
-                }
+                    for (int c = r; c < N; ++c) {
+                        const double a = (P[r][c] + P[c][r]) / 2.0;
+                        P[r][c] = a;
+                        P[c][r] = a;
+                    }
+            } else {
+                // K Pz K^T is symmetric and P is kept exactly symmetric by the fast transform: upper triangle only
+#pragma unroll
+                for (int r = 0; r < N; ++r)
+#pragma unroll
+                    for (int c = r; c < N; ++c) {
+                        double acc = kp[r][0] * k[c][0];
+#pragma unroll
+                        for (int j = 1; j < O; ++j) acc = fma(kp[r][j], k[c][j], acc);
+                        const double a = P[r][c] - acc;
+                        P[r][c] = a;
+                        P[c][r] = a;
+                    }
+            }
         }
     }
 
@@ -535,7 +617,10 @@ __global__ void ukf_soa_to_aos(const double* __restrict__ in, double* __restrict
 __global__ void ukf_broadcast(const double* __restrict__ row, double* __restrict__ out, long long B, int W);
 
 using UkfKernelFn = void (*)(const UkfParams);
+// exact: reference operation order, no FMA (ukf_n4.cu / ukf_n6.cu, -fmad=false); fast: see unscented_transform
 UkfKernelFn ukf_kernel_n4(int model_id, int sqrt_mode, int order, int mode);
 UkfKernelFn ukf_kernel_n6(int model_id, int sqrt_mode, int order, int mode);
+UkfKernelFn ukf_kernel_n4_fast(int model_id, int sqrt_mode, int order, int mode);
+UkfKernelFn ukf_kernel_n6_fast(int model_id, int sqrt_mode, int order, int mode);
 
 }  // namespace mpcb

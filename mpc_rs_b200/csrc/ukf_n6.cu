@@ -2,19 +2,24 @@
 // Only the library sigma-point order (src/ukf2.rs:129-135) exists for n = 6 in the reference.
 #include "ukf_kernel.cuh"
 
+#ifndef MPCB_UKF_FAST
+#define MPCB_UKF_FAST false
+#define MPCB_UKF_ENTRY ukf_kernel_n6
+#endif
+
 namespace mpcb {
 
 template <int MODEL, int SQRT>
 static UkfKernelFn pick_mode6(int mode) {
     switch (mode) {
-        case UKF_PREDICT: return ukf_kernel<6, 5, MODEL, SQRT, MPCB_ORDER_LIBRARY, UKF_PREDICT>;
-        case UKF_UPDATE: return ukf_kernel<6, 5, MODEL, SQRT, MPCB_ORDER_LIBRARY, UKF_UPDATE>;
-        case UKF_FUSED: return ukf_kernel<6, 5, MODEL, SQRT, MPCB_ORDER_LIBRARY, UKF_FUSED>;
+        case UKF_PREDICT: return ukf_kernel<6, 5, MODEL, SQRT, MPCB_ORDER_LIBRARY, UKF_PREDICT, MPCB_UKF_FAST>;
+        case UKF_UPDATE: return ukf_kernel<6, 5, MODEL, SQRT, MPCB_ORDER_LIBRARY, UKF_UPDATE, MPCB_UKF_FAST>;
+        case UKF_FUSED: return ukf_kernel<6, 5, MODEL, SQRT, MPCB_ORDER_LIBRARY, UKF_FUSED, MPCB_UKF_FAST>;
         default: return nullptr;
     }
 }
 
-UkfKernelFn ukf_kernel_n6(int model_id, int sqrt_mode, int order, int mode) {
+UkfKernelFn MPCB_UKF_ENTRY(int model_id, int sqrt_mode, int order, int mode) {
     if (order != MPCB_ORDER_LIBRARY) return nullptr;
     const bool chol = sqrt_mode == MPCB_SQRT_CHOLESKY;
     switch (model_id) {

@@ -49,11 +49,11 @@ class BatchedUkf:
     """B independent unscented Kalman filters on one GPU (FP64, structure-of-arrays on the device)."""
 
     def __init__(self, model: DeviceModel, batch: int = 1, *, sqrt_mode: str = None, sigma_order: str = None,
-                 device: int = 0, dt: float = None, params: dict = None):
+                 device: int = 0, dt: float = None, params: dict = None, exact: bool = False):
         L = A.lib()
         cfg = A.UkfCfg()
         A.check(L.mpcb_ukf_default_cfg(model.model_id, C.byref(cfg)))
-        cfg.batch, cfg.device = int(batch), int(device)
+        cfg.batch, cfg.device, cfg.exact = int(batch), int(device), int(bool(exact))
         if sqrt_mode is not None:
             cfg.sqrt_mode = {"cholesky": A.SQRT_CHOLESKY, "eig": A.SQRT_EIG, "svd": A.SQRT_EIG}[sqrt_mode]
         if sigma_order is not None:

@@ -53,14 +53,21 @@ def make_problem(name, B, T, seed, dt=0.0):
     ("NL6_UKF", "eig", "library"),           # config #4 filter
     ("NL6_UKF", "cholesky", "library"),
 ])
-def test_fused_step_parity_per_step(gpu_required, name, sqrt_mode, order):
-    """Every step starts from the oracle's state on both sides: isolates one predict+update."""
+@pytest.mark.parametrize("exact", [True, False])
+def test_fused_step_parity_per_step(gpu_required, name, sqrt_mode, order, exact):
+    """Every step starts from the oracle's state on both sides: isolates one predict+update.
+    exact=True: reference operation order without FMA; exact=False: the default fast arithmetic (FMA, symmetric
+    half sums), which differs at rounding level times the 1.7e5 weight amplification."""
     B, T = 257, 6
+    # NL6_UKF is ill-conditioned (P entries 3e4 -> 1e2 through a 5x5 inverse): two correct f64 evaluation orders
+    # differ by up to ~1e-6 after one update there (tests/test_oracle_cpu.py measures the same between the oracle
+    # and numpy); the bar for it is the north star's 1e-5
+    tol = 1e-9 if exact else (1e-5 if name == "NL6_UKF" else 1e-7)
     dt = 0.01 if name == "NL6_UKF" else 0.0
     model, oid, p, n, o, Q, R, P0, u, zs = make_problem(name, B, T, 7, dt)
     x = np.zeros((B, n))
     P = np.tile(P0, (B, 1, 1))
-    with BatchedUkf(model, B, sqrt_mode=sqrt_mode, sigma_order=order) as f:
+    with BatchedUkf(model, B, sqrt_mode=sqrt_mode, sigma_order=order, exact=exact) as f:
         f.init(np.zeros(n), P0, Q, R)
         for t in range(T):
             f.set_state(x, P)
@@ -68,8 +75,8 @@ def test_fused_step_parity_per_step(gpu_required, name, sqrt_mode, order):
             xg, Pg = f.get_state()
             x, P, st = O.ukf_step_batch(oid, p, x, P, Q, R, u, zs[t], dt, SQRT[sqrt_mode], ORDER[order])
             assert not st.any()
-            assert relerr(xg, x) < 1e-9, (t, relerr(xg, x))
-            assert relerr(Pg, P) < 1e-9, (t, relerr(Pg, P))
+            assert relerr(xg, x) < tol, (t, relerr(xg, x))
+            assert relerr(Pg, P) < tol, (t, relerr(Pg, P))
 
 
 def test_trajectory_config3(gpu_required):
@@ -116,7 +123,7 @@ def test_reference_style_single_filter(gpu_required):
     rng = np.random.default_rng(2)
     x_est, P = np.zeros(4), P0.copy()
     x_act = np.zeros(4)
-    f = UnscentedKalmanFilter.new(x_est, P0, Q, R, fx=models.PEN_NL)
+    f = UnscentedKalmanFilter.new(x_est, P0, Q, R, fx=models.PEN_NL, exact=True)
     for i in range(5):  # per-step (the filter is chaotic beyond ~10 steps, SURVEY.md finding 5)
         x_act = O.fx(oid, p, x_act, 0.1)
         z = O.hx(oid, p, x_act) + np.array([100.0, 100.0, 0.5]) * rng.standard_normal(3)
@@ -138,7 +145,7 @@ def test_per_filter_u_set_q_set_r(gpu_required):
     us = rng.uniform(-1, 1, B)
     Q2 = O.gen_q(0.012)
     R2 = R * 2.0
-    with BatchedUkf(model, B) as f:
+    with BatchedUkf(model, B, exact=True) as f:
         f.init(np.zeros(n), P0, Q, R)
         f.set_q(Q2)
         f.set_r(R2)
