@@ -199,7 +199,7 @@ def upload(A, dev, dptr, arr):
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from mpc_rs_b200 import BatchedUkf, Mppi, comm_unique_id, models
+    from mpc_rs_b200 import BatchedUkf, Mppi, models
     from mpc_rs_b200 import _abi as A
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -231,11 +231,8 @@ def run_gpu(args):
     mppi = Mppi(H, K_PER_GPU * world, model=models.NL, lam=LAMBDA, std_dev=SIGMA, limit=LIMIT, precision="f32", dt=DT,
                 device=dev, rank=rank, world_size=world, seed=20240001)
     if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        mppi.attach_comm(bytes(uid.cpu().numpy().tobytes()))
+        from mpc_rs_b200.distributed import attach_mppi
+        attach_mppi(mppi)  # rank 0's ncclUniqueId -> everyone (torch.distributed broadcast), then ncclCommInitRank
 
     stream = torch.cuda.ExternalStream(mppi.stream, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2

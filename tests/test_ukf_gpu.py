@@ -200,3 +200,24 @@ def test_multi_step_device_run(gpu_required):
         np.testing.assert_array_equal(xa, xb)
         np.testing.assert_array_equal(Pa, Pb)
     A.lib().mpcb_device_free(0, d_z)
+
+
+def test_golden_fixtures_gpu(gpu_required):
+    """The CUDA path against the committed golden vectors (tests/golden, made from the oracle by make_golden.py)."""
+    import os
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    for name in ("PEN_LIN", "PEN_NL", "PEN6", "NL6_UKF"):
+        g = np.load(os.path.join(gold, f"ukf_{name}.npz"))
+        model = MODELS[name][0]
+        sq = "cholesky" if int(g["sqrt_mode"]) == O.SQRT_CHOLESKY else "eig"
+        order = "interleaved" if int(g["order"]) == O.ORDER_INTERLEAVED else "library"
+        B, n = g["x_0"].shape
+        for exact, tol in ((True, 1e-9), (False, 1e-5 if name == "NL6_UKF" else 1e-7)):
+            with BatchedUkf(model, B, sqrt_mode=sq, sigma_order=order, exact=exact) as f:
+                f.init(np.zeros(n), g["P0"], g["Q"], g["R"])
+                for t in range(5):
+                    if t > 0:
+                        f.set_state(g[f"x_{t-1}"], g[f"P_{t-1}"])  # per step from the golden state
+                    f.step(float(g["u"]), g[f"z_{t}"], float(g["dt"]))
+                    xg, Pg = f.get_state()
+                    assert relerr(xg, g[f"x_{t}"]) < tol and relerr(Pg, g[f"P_{t}"]) < tol, (name, exact, t)
