@@ -114,52 +114,50 @@ def run_reference(args):
 
 # ---- helpers ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons every ~2 ms through NVML in a background thread while the timed
+    regions run (nvidia-smi -lms cannot sample a region that lasts a few milliseconds)."""
 
     def __init__(self, index: int):
-        self.index, self.proc, self.path = index, None, f"/tmp/mpcb_clocks_{os.getpid()}.csv"
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop, self._thr = False, None
 
     def start(self):
         try:
-            self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+            import threading
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
+
+            def loop():
+                while not self._stop:
+                    try:
+                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for nm, bit in bits.items():
+                            if r & bit:
+                                self.reasons.add(nm)
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+
+            self._thr = threading.Thread(target=loop, daemon=True)
+            self._thr.start()
         except Exception:
-            self.proc = None
+            self._thr = None
 
     def stop(self) -> dict:
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.f.close()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in open(self.path):
-            parts = [s.strip() for s in ln.split(",")]
-            if len(parts) < 8:
-                continue
-            try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, parts[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
-        try:
-            os.remove(self.path)
-        except OSError:
-            pass
-        return out
+        self._stop = True
+        if self._thr is not None:
+            self._thr.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
 
 
 def measured_peaks():

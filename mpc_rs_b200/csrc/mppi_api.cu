@@ -41,6 +41,9 @@ struct mpcb_mppi {
     double* h_out_dev = nullptr;         // device alias of h_out
     mpcb_mppi_info* h_info = nullptr;    // mapped: [C]
     mpcb_mppi_info* h_info_dev = nullptr;
+    unsigned int* h_done = nullptr;      // mapped completion word the host spins on (C == 1)
+    unsigned int* h_done_dev = nullptr;
+    unsigned int epoch = 0;
     bool costs_valid = false;
     uint32_t call_idx = 0;
     int64_t launches = 0;
@@ -176,8 +179,21 @@ mpcb_status stage_inputs(mpcb_mppi* h, MppiParams& p, const double* x, const dou
 }
 
 // Waits for the step and hands u_out/info to the caller (results were written straight into mapped host memory).
-mpcb_status finish_host(mpcb_mppi* h, double* u_out, mpcb_mppi_info* info) {
-    MPCB_CUDA_TRY(cudaStreamSynchronize(h->stream));
+// Single controller: the final block stores an epoch word after the results; spinning on it avoids the wake-up
+// latency of cudaStreamSynchronize.  After ~2 ms without completion (or for C > 1) fall back to the stream sync,
+// which also surfaces any launch/runtime error.
+mpcb_status finish_host(mpcb_mppi* h, double* u_out, mpcb_mppi_info* info, bool spin) {
+    bool done = false;
+    if (spin) {
+        volatile unsigned int* flag = h->h_done;
+        const unsigned int want = h->epoch;
+        for (long i = 0; i < 4000000; ++i) {
+            if (*flag == want) { done = true; break; }
+            __builtin_ia32_pause();
+        }
+        __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    }
+    if (!done) MPCB_CUDA_TRY(cudaStreamSynchronize(h->stream));
     memcpy(u_out, h->h_out, (size_t)h->C * h->H * sizeof(double));
     if (info) memcpy(info, h->h_info, (size_t)h->C * sizeof(mpcb_mppi_info));
     if (h->C == 1) return (mpcb_status)h->h_info[0].status;
@@ -205,13 +221,19 @@ mpcb_status compute_host(mpcb_mppi* h, const double* x, const double* u_in, cons
         p.u_out_host = h->h_out_dev;
         p.info_host = h->h_info_dev;
     }
+    const bool spin = (h->C == 1);
+    h->epoch += 1;
+    if (spin && !sharded) {
+        p.done_host = h->h_done_dev;
+        p.epoch = h->epoch;
+    }
     st = launch(h, p);
     if (st != MPCB_OK) return st;
     if (sharded) {
         st = exchange_and_combine(h);
         if (st != MPCB_OK) return st;
     }
-    return finish_host(h, u_out, info);
+    return finish_host(h, u_out, info, spin);
 }
 
 mpcb_status run_combine(mpcb_mppi* h, const double* rows, int G) {
@@ -225,6 +247,8 @@ mpcb_status run_combine(mpcb_mppi* h, const double* rows, int G) {
     cp.u_out_host = h->h_out_dev;
     cp.info = h->d_info;
     cp.info_host = h->h_info_dev;
+    cp.done_host = (h->C == 1) ? h->h_done_dev : nullptr;
+    cp.epoch = h->epoch;
     mppi_combine_kernel<128><<<h->C, 128, 0, h->stream>>>(cp);
     MPCB_CUDA_TRY(cudaGetLastError());
     h->launches += 1;
@@ -354,6 +378,9 @@ mpcb_status mpcb_mppi_create(mpcb_mppi** out, const mpcb_mppi_cfg* cfg) {
     memset(h->h_info, 0, C * sizeof(mpcb_mppi_info));
     TRY_OR_FAIL(cudaHostGetDevicePointer((void**)&h->h_out_dev, h->h_out, 0));
     TRY_OR_FAIL(cudaHostGetDevicePointer((void**)&h->h_info_dev, h->h_info, 0));
+    TRY_OR_FAIL(cudaHostAlloc(&h->h_done, 64, cudaHostAllocMapped));
+    memset(h->h_done, 0, 64);
+    TRY_OR_FAIL(cudaHostGetDevicePointer((void**)&h->h_done_dev, h->h_done, 0));
 #undef TRY_OR_FAIL
     *out = h;
     return MPCB_OK;
@@ -379,6 +406,7 @@ void mpcb_mppi_destroy(mpcb_mppi* h) {
     if (h->h_in) cudaFreeHost(h->h_in);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_info) cudaFreeHost(h->h_info);
+    if (h->h_done) cudaFreeHost(h->h_done);
     if (h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
     delete h;
@@ -456,6 +484,8 @@ mpcb_status mpcb_mppi_compute_device(mpcb_mppi* h, const double* d_x, const doub
         cp.u_out_host = nullptr;
         cp.info = h->d_info;
         cp.info_host = nullptr;
+        cp.done_host = nullptr;
+        cp.epoch = 0;
         mppi_combine_kernel<128><<<h->C, 128, 0, h->stream>>>(cp);
         MPCB_CUDA_TRY(cudaGetLastError());
         h->launches += 1;
@@ -518,9 +548,10 @@ mpcb_status mpcb_mppi_combine(mpcb_mppi* h, const double* d_partials, int32_t n_
     MPCB_REQUIRE(h && d_partials && u_out, "null pointer");
     MPCB_REQUIRE(n_ranks >= 1 && n_ranks <= h->cfg.world_size, "n_ranks exceeds cfg.world_size");
     MPCB_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    h->epoch += 1;
     mpcb_status st = run_combine(h, d_partials, n_ranks);
     if (st != MPCB_OK) return st;
-    return finish_host(h, u_out, info);
+    return finish_host(h, u_out, info, h->C == 1);
 }
 
 mpcb_status mpcb_comm_unique_id(char id[128]) { return nccl_unique_id(id); }

@@ -56,6 +56,8 @@ struct MppiParams {
     mpcb_mppi_info* info;    // [C]
     mpcb_mppi_info* info_host;
     double* rank_partial;    // [C][kPartialHdr + H]
+    unsigned int* done_host;       // mapped host word; the final block stores `epoch` after u_out/info (C == 1 only)
+    unsigned int epoch, pad1;
     unsigned long long* debug_ts;  // optional [blocks][8] %globaltimer stamps (diagnostics)
     ModelConsts mc;
     double xu_inline[4 + kInlineHorizon];
@@ -91,7 +93,8 @@ constexpr int kMergeBatch = 16;
 template <int BLOCK>
 __device__ void mppi_merge_rows(const double* rows, long long row_stride, int n_rows, int H, double lambda,
                                 int final_mode, double* u_out, double* u_out_host, mpcb_mppi_info* info,
-                                mpcb_mppi_info* info_host, double* out_row, double* scratch) {
+                                mpcb_mppi_info* info_host, double* out_row, double* scratch,
+                                unsigned int* done_host = nullptr, unsigned int epoch = 0) {
     constexpr int NW = BLOCK / 32;
     constexpr int RPT = (kMergeFan + BLOCK - 1) / BLOCK;  // header rows per thread
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -204,6 +207,7 @@ __device__ void mppi_merge_rows(const double* rows, long long row_stride, int n_
             if (u_out_host) u_out_host[t] = uo;
         }
     }
+    if (done_host) __threadfence_system();  // every writer orders its host stores before the completion word
     __syncthreads();
     if (tid == 0) {
         if (final_mode == 1) {
@@ -221,6 +225,11 @@ __device__ void mppi_merge_rows(const double* rows, long long row_stride, int n_
             out.n_finite = n;
             *info = out;
             if (info_host) *info_host = out;
+            if (done_host) {
+                // results first, then the completion word the host spins on (system-scope release)
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned int*>(done_host) = epoch;
+            }
         }
     }
 }
@@ -377,10 +386,14 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
             }
         };
 
+        // Software pipeline: the noise of group g+1 (independent of the state) is drawn while group g rolls out,
+        // so the scheduler has Philox/Box-Muller work to fill the dependency stalls of the serial dynamics chain.
         const int H4 = H & ~3;
+        real e[4];
+        noise4(0, e);
         for (int t0 = 0; t0 < H4; t0 += 4) {
-            real e[4];
-            noise4(t0, e);
+            real en[4];
+            noise4(t0 + 4, en);  // the last prefetch (t0 + 4 >= H4) feeds the tail below or is discarded
 #pragma unroll
             for (int i = 0; i < 4; ++i) step(t0 + i, e[i]);
             if constexpr (!kExact) {
@@ -390,10 +403,10 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
                 cw = (real)0;
                 cu = (real)0;
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) e[i] = en[i];
         }
         if (H4 < H) {
-            real e[4];
-            noise4(H4, e);
 #pragma unroll
             for (int i = 0; i < 3; ++i)
                 if (H4 + i < H) step(H4 + i, e[i]);
@@ -506,7 +519,7 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
     double* rank_row = p.rank_partial ? p.rank_partial + (long long)c * PL : nullptr;
     if (p.groups == 1) {
         mppi_merge_rows<BLOCK>(ctrl_rows, PL, p.chunks, H, lambda, p.final_mode, u_out_c, u_host_c, p.info + c,
-                               info_host_c, rank_row, scratch);
+                               info_host_c, rank_row, scratch, p.done_host, p.epoch);
         if (tid == 0) cnt[0] = 0u;  // ready for the next launch
         MPCB_TS(3);
         return;
@@ -524,7 +537,7 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
     if (!s_last) return;
     fence_acq_rel_gpu();
     mppi_merge_rows<BLOCK>(group_rows, PL, p.groups, H, lambda, p.final_mode, u_out_c, u_host_c, p.info + c, info_host_c,
-                           rank_row, scratch);
+                           rank_row, scratch, p.done_host, p.epoch);
     if (tid == 0) cnt[p.groups] = 0u;
     MPCB_TS(5);
 }
@@ -538,6 +551,8 @@ struct MppiCombineParams {
     double* u_out_host;
     mpcb_mppi_info* info;
     mpcb_mppi_info* info_host;
+    unsigned int* done_host;
+    unsigned int epoch;
 };
 
 template <int BLOCK>
@@ -547,7 +562,7 @@ __global__ void __launch_bounds__(BLOCK) mppi_combine_kernel(const MppiCombinePa
     const int PL = kPartialHdr + p.H;
     mppi_merge_rows<BLOCK>(p.rows + (long long)c * PL, (long long)p.C * PL, p.G, p.H, p.lambda, 0,
                            p.u_out + (long long)c * p.H, p.u_out_host ? p.u_out_host + (long long)c * p.H : nullptr,
-                           p.info + c, p.info_host ? p.info_host + c : nullptr, nullptr, scratch);
+                           p.info + c, p.info_host ? p.info_host + c : nullptr, nullptr, scratch, p.done_host, p.epoch);
 }
 
 // kernel entry table (defined in mppi_f32.cu / mppi_f64.cu)

@@ -105,22 +105,47 @@ class Mppi:
         u_n = np.ascontiguousarray(u_n, dtype=np.float64).reshape(self.C, self.N)
         return x, u_n
 
+    def _info_dicts(self, infos):
+        return [dict(status=i.status, argmax=i.argmax, max=i.max, sum=i.sum, n_finite=i.n_finite) for i in infos]
+
     def _finish(self, st, u_out, infos, squeeze):
-        self.info = [dict(status=i.status, argmax=i.argmax, max=i.max, sum=i.sum, n_finite=i.n_finite) for i in infos]
+        self.info = self._info_dicts(infos)
         if st in (A.NO_FINITE_COST, A.SUM_ZERO, A.U_INVALID):
             raise MppiError(st)
         A.check(st)
         return u_out[0] if squeeze else u_out
 
+    def _fast_path(self):
+        """Persistent host buffers + pre-bound pointers for compute(): the per-call Python cost is two small
+        copies and one ctypes call."""
+        fp = getattr(self, "_fp", None)
+        if fp is None:
+            x = np.zeros((self.C, self.S))
+            u = np.zeros((self.C, self.N))
+            out = np.zeros((self.C, self.N))
+            infos = (A.MppiInfo * self.C)()
+            fp = self._fp = (x, u, out, infos, _dp(x), _dp(u), _dp(out), A.lib().mpcb_mppi_compute)
+        return fp
+
     # -- Mppi::compute (src/mppi.rs:33) --
     def compute(self, x, u_n):
         """Generate mode: noise drawn in-register (Philox).  Returns the new control sequence [N] (or [C][N])."""
+        xb, ub, out, infos, px, pu, po, fn = self._fast_path()
         squeeze = self.C == 1 and np.ndim(u_n) == 1
-        x, u_n = self._inputs(x, u_n)
-        u_out = np.empty((self.C, self.N))
-        infos = (A.MppiInfo * self.C)()
-        st = A.lib().mpcb_mppi_compute(self._h, _dp(x), _dp(u_n), _dp(u_out), infos)
-        return self._finish(st, u_out, infos, squeeze)
+        xb.reshape(-1)[:] = np.ravel(x)
+        ub.reshape(-1)[:] = np.ravel(u_n)
+        st = fn(self._h, px, pu, po, infos)
+        self._last_infos = infos
+        if st != A.OK:
+            return self._finish(st, out.copy(), infos, squeeze)
+        self.info = None  # filled lazily by last_call_info()
+        return out[0].copy() if squeeze else out.copy()
+
+    def last_call_info(self):
+        """Diagnostics (status, argmax, max, sum, n_finite) of the last compute()."""
+        if self.info is None and getattr(self, "_last_infos", None) is not None:
+            self.info = self._info_dicts(self._last_infos)
+        return self.info
 
     def compute_replay(self, x, u_n, eps):
         """Replay mode: eps[(C,)K,N] ~ N(0, std_dev^2) supplied by the caller (float32 or float64)."""
