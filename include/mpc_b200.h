@@ -42,7 +42,8 @@ typedef enum mpcb_status {
     MPCB_BAD_ARG = 6,
     MPCB_CUDA_ERROR = 7,
     MPCB_NCCL_ERROR = 8,
-    MPCB_NOT_PREDICTED = 9   /* update() before any predict(): the reference yields NaN (src/ukf.rs:32) */
+    MPCB_NOT_PREDICTED = 9,  /* update() before any predict(): the reference yields NaN (src/ukf.rs:32) */
+    MPCB_PEER_TIMEOUT = 10   /* multi-GPU exchange: a peer's partial row did not arrive within 20 s */
 } mpcb_status;
 
 /* Message for a status; for MPCB_NO_FINITE_COST/SUM_ZERO/U_INVALID/INVERSE_FAIL/CHOLESKY_FAIL it is
@@ -185,6 +186,19 @@ mpcb_status mpcb_mppi_combine(mpcb_mppi* h, const double* d_partials, int32_t n_
  * mpcb_comm_unique_id on rank 0 and distributed by the caller (file, torch.distributed, MPI ...). */
 mpcb_status mpcb_comm_unique_id(char id[128]);
 mpcb_status mpcb_mppi_attach_comm(mpcb_mppi* h, const char id[128]);
+/* Fused exchange over peer memory (NVLink / NVSwitch), no collective call: every rank owns a mailbox in its own
+ * HBM; the kernel's final block stores this rank's partial row straight into every peer's mailbox, releases one
+ * flag per peer, waits for the peers' rows and combines them — one kernel per control step.
+ *   1. every rank: mpcb_mppi_peer_handle(h, mine)       (128 bytes: CUDA IPC handle of the mailbox + owner info)
+ *   2. the caller gathers the handles of all ranks in rank order (file, torch.distributed, MPI ...)
+ *   3. every rank: mpcb_mppi_attach_peers(h, all)       (all = world_size x 128 bytes)
+ * Ranks may be separate processes (cudaIpcOpenMemHandle) or handles of one process (cudaDeviceEnablePeerAccess).
+ * After attach, mpcb_mppi_compute / _replay / _device use this path; it takes precedence over an attached NCCL
+ * communicator.  All ranks must make the same sequence of compute calls.  A rank whose peers never arrive gets
+ * MPCB_PEER_TIMEOUT in info.status after 20 s instead of hanging. */
+#define MPCB_PEER_HANDLE_BYTES 128
+mpcb_status mpcb_mppi_peer_handle(mpcb_mppi* h, char out[MPCB_PEER_HANDLE_BYTES]);
+mpcb_status mpcb_mppi_attach_peers(mpcb_mppi* h, const char* handles /* [world_size][MPCB_PEER_HANDLE_BYTES] */);
 
 /* ------------------------------------------------------------------------------------------
  * UKF  (replaces mpc::ukf::UnscentedKalmanFilter n=4,o=3, mpc::ukf2::… n=6,o=5, and the free

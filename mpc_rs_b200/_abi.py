@@ -12,7 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmpc_b200.so")
 
 # ---- enums (include/mpc_b200.h) ----
-OK, NO_FINITE_COST, SUM_ZERO, U_INVALID, INVERSE_FAIL, CHOLESKY_FAIL, BAD_ARG, CUDA_ERROR, NCCL_ERROR, NOT_PREDICTED = range(10)
+OK, NO_FINITE_COST, SUM_ZERO, U_INVALID, INVERSE_FAIL, CHOLESKY_FAIL, BAD_ARG, CUDA_ERROR, NCCL_ERROR, NOT_PREDICTED, \
+    PEER_TIMEOUT = range(11)
 MODEL_L, MODEL_NL, MODEL_NL6 = 0, 1, 2
 MODEL_PEN_LIN, MODEL_PEN_NL, MODEL_PEN6, MODEL_NL6_UKF = 16, 17, 18, 19
 F32, F64 = 0, 1
@@ -104,6 +105,8 @@ SYMBOLS = {
     "mpcb_mppi_combine": (C.c_int, [_H, _vp, C.c_int32, _dp, C.POINTER(MppiInfo)]),
     "mpcb_comm_unique_id": (C.c_int, [C.c_char_p]),
     "mpcb_mppi_attach_comm": (C.c_int, [_H, C.c_char_p]),
+    "mpcb_mppi_peer_handle": (C.c_int, [_H, C.c_char_p]),
+    "mpcb_mppi_attach_peers": (C.c_int, [_H, C.c_char_p]),
     "mpcb_ukf_default_cfg": (C.c_int, [C.c_int32, C.POINTER(UkfCfg)]),
     "mpcb_ukf_default_noise": (C.c_int, [C.c_int32, C.c_double, _dp, _dp, _dp]),
     "mpcb_ukf_create": (C.c_int, [C.POINTER(_H), C.POINTER(UkfCfg)]),

@@ -105,6 +105,7 @@ const char* mpcb_status_string(mpcb_status s) {
         case MPCB_CUDA_ERROR: return "CUDA error";
         case MPCB_NCCL_ERROR: return "NCCL error";
         case MPCB_NOT_PREDICTED: return "update before predict";
+        case MPCB_PEER_TIMEOUT: return "peer exchange timed out";
         default: return "unknown status";
     }
 }

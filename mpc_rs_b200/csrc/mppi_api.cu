@@ -2,6 +2,7 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <stdlib.h>
+#include <unistd.h>
 
 #include <new>
 
@@ -17,7 +18,8 @@ struct mpcb_mppi {
     long long K_local = 0, k_offset = 0;
     int H = 0, C = 0, PL = 0;
     int block = 0, chunks = 0, group_size = 0, groups = 0;
-    long long batches_per_chunk = 0;
+    int Hp = 8, lgHp = 3;
+    long long W = 0;  // warps of 32 samples in K_local
     size_t smem = 0;
     ModelConsts mc;
     MppiKernelFn k_noise[3] = {nullptr, nullptr, nullptr};  // indexed by MppiNoise
@@ -49,33 +51,91 @@ struct mpcb_mppi {
     int64_t launches = 0;
     // NCCL
     void* comm = nullptr;
+    // fused peer exchange: own mailbox + flags, the peers' mappings, device tables of both
+    void* d_mailbox = nullptr;  // [flags: 2*G*C u32, padded][mailbox: 2*G*C*PL doubles]
+    size_t mailbox_bytes = 0, mailbox_flag_bytes = 0;
+    void* peer_base[kMergeFan] = {};
+    bool peer_ipc[kMergeFan] = {};
+    double** d_peer_mbox = nullptr;
+    unsigned int** d_peer_flags = nullptr;
+    bool peers_attached = false;
+    unsigned int xepoch = 0;
 };
+
+// 128-byte blob exchanged between ranks by mpcb_mppi_peer_handle / mpcb_mppi_attach_peers
+struct PeerBlob {
+    uint32_t magic;
+    int32_t pid;
+    int32_t device;
+    int32_t rank;
+    uint64_t ptr;
+    uint64_t bytes;
+    uint64_t flag_bytes;
+    int32_t world, controllers, horizon, pad;
+    cudaIpcMemHandle_t ipc;  // 64 bytes
+    char reserved[MPCB_PEER_HANDLE_BYTES - 56 - 64];
+};
+static_assert(sizeof(PeerBlob) == MPCB_PEER_HANDLE_BYTES, "peer blob must be 128 bytes");
+constexpr uint32_t kPeerMagic = 0x4d504258u;  // "MPBX"
 
 namespace {
 
 size_t elt_size(const mpcb_mppi* h) { return h->cfg.precision == MPCB_F64 ? sizeof(double) : sizeof(float); }
 
+// Chooses block size, blocks per controller and merge-tree shape (see the header of mppi_kernel.cuh).
+//   * If the controller's W warps fit on the GPU in ONE batch per block with about one block per SM, take
+//     chunks = min(num_sms / C, W) ranges and the smallest BLOCK in {128, 256, 512} that covers a range: every SM gets
+//     the same number of samples and only `chunks` rows remain to merge (K = 65536, H = 100: 148 blocks of 512).
+//   * Otherwise (large K, many controllers, or a horizon whose v tile limits the block): BLOCK = 128 (or the
+//     largest smaller block that fits), as many resident blocks as the GPU holds, each walking several batches.
 mpcb_status pick_kernels(mpcb_mppi* h) {
     const bool f64 = h->cfg.precision == MPCB_F64;
     cudaDeviceProp prop;
     MPCB_CUDA_TRY(cudaGetDeviceProperties(&prop, h->cfg.device));
     h->num_sms = prop.multiProcessorCount;
     const size_t smem_max = prop.sharedMemPerBlockOptin;
-    const int blocks[3] = {128, 64, 32};
-    for (int b : blocks) {
-        const size_t need = f64 ? mppi_smem_bytes<double>(h->H, b) : mppi_smem_bytes<float>(h->H, b);
-        if (need + 1024 <= smem_max) {  // 1 KB reserved per block by the driver
-            h->block = b;
-            h->smem = need;
-            break;
+    h->Hp = mppi_pow2_horizon(h->H, &h->lgHp);
+    h->W = (h->K_local + 31) / 32;
+    auto smem_of = [&](int b) { return f64 ? mppi_smem_bytes<double>(h->H, b) : mppi_smem_bytes<float>(h->H, b); };
+    auto kernel_of = [&](int b, int noise) {
+        return f64 ? mppi_kernel_f64(h->cfg.model_id, b, noise) : mppi_kernel_f32(h->cfg.model_id, b, noise);
+    };
+    auto fits = [&](int b) { return kernel_of(b, NOISE_GENERATE) != nullptr && smem_of(b) + 1024 <= smem_max; };
+
+    long long chunks1 = h->num_sms / h->C;
+    if (chunks1 < 1) chunks1 = 1;
+    if (chunks1 > h->W) chunks1 = h->W;
+    const long long wpc = (h->W + chunks1 - 1) / chunks1;  // warps per range if there is about one block per SM
+    int block = 0;
+    bool single_batch = false;
+    const char* force = getenv("MPCB_MPPI_BLOCK");  // developer override
+    if (force && fits(atoi(force))) {
+        block = atoi(force);
+    } else {
+        for (int b : {128, 256, 512}) {
+            if (wpc * 32 <= b && fits(b)) {
+                block = b;
+                single_batch = true;
+                break;
+            }
+        }
+        if (block == 0) {
+            for (int b : {128, 64, 32}) {
+                if (fits(b)) {
+                    block = b;
+                    break;
+                }
+            }
         }
     }
-    if (h->block == 0) {
+    if (block == 0) {
         set_error("horizon %d needs more shared memory than one SM has", h->H);
         return MPCB_BAD_ARG;
     }
+    h->block = block;
+    h->smem = smem_of(block);
     for (int noise = 0; noise < 3; ++noise) {
-        h->k_noise[noise] = f64 ? mppi_kernel_f64(h->cfg.model_id, h->block, noise) : mppi_kernel_f32(h->cfg.model_id, h->block, noise);
+        h->k_noise[noise] = kernel_of(block, noise);
         if (!h->k_noise[noise]) {
             set_error("no MPPI kernel for model %d", h->cfg.model_id);
             return MPCB_BAD_ARG;
@@ -83,20 +143,26 @@ mpcb_status pick_kernels(mpcb_mppi* h) {
         MPCB_CUDA_TRY(cudaFuncSetAttribute((const void*)h->k_noise[noise], cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)h->smem));
     }
-    int occ = 0;
-    MPCB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)h->k_noise[NOISE_GENERATE], h->block, h->smem));
-    if (occ < 1) occ = 1;
-    const long long resident = (long long)occ * h->num_sms;
-    const long long nbatches = (h->K_local + h->block - 1) / h->block;
-    long long per_ctrl = resident / h->C;
-    if (per_ctrl < 1) per_ctrl = 1;
-    if (per_ctrl > nbatches) per_ctrl = nbatches;
-    h->batches_per_chunk = (nbatches + per_ctrl - 1) / per_ctrl;
-    if (per_ctrl > kMergeFan * kMergeFan) per_ctrl = kMergeFan * kMergeFan;
-    h->batches_per_chunk = (nbatches + per_ctrl - 1) / per_ctrl;
-    h->chunks = (int)((nbatches + h->batches_per_chunk - 1) / h->batches_per_chunk);
-    // two-level merge tree with fan-in <= kMergeFan
-    if (h->chunks <= kMergeFan) {
+    long long chunks;
+    if (single_batch) {
+        chunks = (h->W + wpc - 1) / wpc;  // ranges of wpc or wpc-1 warps, none empty
+    } else {
+        int occ = 0;
+        MPCB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)h->k_noise[NOISE_GENERATE], block, h->smem));
+        if (occ < 1) occ = 1;
+        chunks = (long long)occ * h->num_sms / h->C;
+        const long long nbatches = (h->W * 32 + block - 1) / block;
+        if (chunks > nbatches) chunks = nbatches;
+        if (chunks < 1) chunks = 1;
+    }
+    if (chunks > (long long)kMergeFan * kMergeFan) chunks = (long long)kMergeFan * kMergeFan;
+    h->chunks = (int)chunks;
+    // merge tree: one level while the last block can take the rows in <= 3 load batches per thread
+    // (its threads split the rows nq ways, nq = BLOCK / Hp), else two levels with fan-in ~ sqrt(rows)
+    int nq = block >> h->lgHp;
+    if (nq < 1) nq = 1;
+    if (nq > 16) nq = 16;
+    if (h->chunks <= kMergeFan && h->chunks <= 3 * kMergeBatch * nq) {
         h->group_size = h->chunks;
         h->groups = 1;
     } else {
@@ -111,6 +177,9 @@ mpcb_status pick_kernels(mpcb_mppi* h) {
 void fill_params(const mpcb_mppi* h, MppiParams* p) {
     memset(p, 0, sizeof(*p));
     p->H = h->H;
+    p->Hp = h->Hp;
+    p->lgHp = h->lgHp;
+    p->W = h->W;
     p->C = h->C;
     p->chunks = h->chunks;
     p->group_size = h->group_size;
@@ -118,7 +187,6 @@ void fill_params(const mpcb_mppi* h, MppiParams* p) {
     p->K_local = h->K_local;
     p->K_global = h->cfg.samples;
     p->k_offset = h->k_offset;
-    p->batches_per_chunk = h->batches_per_chunk;
     p->seed_lo = (unsigned int)(h->cfg.seed & 0xffffffffull);
     p->seed_hi = (unsigned int)(h->cfg.seed >> 32);
     p->call_idx = h->call_idx;
@@ -202,6 +270,17 @@ mpcb_status finish_host(mpcb_mppi* h, double* u_out, mpcb_mppi_info* info, bool 
 
 mpcb_status exchange_and_combine(mpcb_mppi* h);
 
+// One more step of the fused peer exchange: every rank advances the same epoch counter.
+void set_peer_params(mpcb_mppi* h, MppiParams& p) {
+    h->xepoch += 1;
+    p.final_mode = FINAL_PEER_EXCHANGE;
+    p.peer_mbox = h->d_peer_mbox;
+    p.peer_flags = h->d_peer_flags;
+    p.G = h->cfg.world_size;
+    p.rank = h->cfg.rank;
+    p.xepoch = h->xepoch;
+}
+
 mpcb_status compute_host(mpcb_mppi* h, const double* x, const double* u_in, const void* d_eps, int eps_dtype,
                          void* d_dump, double* u_out, mpcb_mppi_info* info) {
     MPCB_REQUIRE(h && x && u_in && u_out, "null pointer");
@@ -214,22 +293,25 @@ mpcb_status compute_host(mpcb_mppi* h, const double* x, const double* u_in, cons
     p.eps_f64 = (eps_dtype == MPCB_DT_F64);
     p.eps_dump = d_dump;
     const bool sharded = h->cfg.world_size > 1;
-    if (sharded) {
-        MPCB_REQUIRE(h->comm != nullptr, "world_size > 1 needs mpcb_mppi_attach_comm (or use compute_partial + combine)");
-        p.final_mode = 1;
+    const bool peer = sharded && h->peers_attached;
+    const bool spin = (h->C == 1);
+    h->epoch += 1;
+    if (sharded && !peer) {
+        MPCB_REQUIRE(h->comm != nullptr,
+                     "world_size > 1 needs mpcb_mppi_attach_peers or mpcb_mppi_attach_comm (or use compute_partial + combine)");
+        p.final_mode = FINAL_RANK_ROW;
     } else {
         p.u_out_host = h->h_out_dev;
         p.info_host = h->h_info_dev;
-    }
-    const bool spin = (h->C == 1);
-    h->epoch += 1;
-    if (spin && !sharded) {
-        p.done_host = h->h_done_dev;
-        p.epoch = h->epoch;
+        if (spin) {
+            p.done_host = h->h_done_dev;
+            p.epoch = h->epoch;
+        }
+        if (peer) set_peer_params(h, p);
     }
     st = launch(h, p);
     if (st != MPCB_OK) return st;
-    if (sharded) {
+    if (sharded && !peer) {
         st = exchange_and_combine(h);
         if (st != MPCB_OK) return st;
     }
@@ -391,6 +473,11 @@ void mpcb_mppi_destroy(mpcb_mppi* h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm) nccl_destroy(h->comm);
+    for (int r = 0; r < kMergeFan; ++r)
+        if (h->peer_ipc[r] && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
+    cudaFree(h->d_peer_mbox);
+    cudaFree(h->d_peer_flags);
+    cudaFree(h->d_mailbox);
     cudaFree(h->d_x);
     cudaFree(h->d_u);
     cudaFree(h->d_u_out);
@@ -458,7 +545,8 @@ mpcb_status mpcb_mppi_get_costs(mpcb_mppi* h, double* c_out) {
 mpcb_status mpcb_mppi_compute_device(mpcb_mppi* h, const double* d_x, const double* d_u_in, const void* d_eps,
                                      int32_t eps_dtype, double* d_u_out) {
     MPCB_REQUIRE(h && d_x && d_u_in && d_u_out, "null pointer");
-    MPCB_REQUIRE(h->cfg.world_size == 1 || h->comm != nullptr, "sharded handle needs mpcb_mppi_attach_comm");
+    MPCB_REQUIRE(h->cfg.world_size == 1 || h->comm != nullptr || h->peers_attached,
+                 "sharded handle needs mpcb_mppi_attach_peers or mpcb_mppi_attach_comm");
     MPCB_CUDA_TRY(cudaSetDevice(h->cfg.device));
     MppiParams p;
     fill_params(h, &p);
@@ -468,10 +556,12 @@ mpcb_status mpcb_mppi_compute_device(mpcb_mppi* h, const double* d_x, const doub
     p.eps_f64 = (eps_dtype == MPCB_DT_F64);
     p.u_out = d_u_out;
     const bool sharded = h->cfg.world_size > 1;
-    p.final_mode = sharded ? 1 : 0;
+    const bool peer = sharded && h->peers_attached;
+    p.final_mode = sharded ? FINAL_RANK_ROW : FINAL_NORMALISE;
+    if (peer) set_peer_params(h, p);
     mpcb_status st = launch(h, p);
     if (st != MPCB_OK) return st;
-    if (sharded) {
+    if (sharded && !peer) {
         st = nccl_all_gather(h->comm, h->d_rank_partial, h->d_gather, (size_t)h->C * h->PL, h->stream);
         if (st != MPCB_OK) return st;
         MppiCombineParams cp;
@@ -535,7 +625,7 @@ mpcb_status mpcb_mppi_compute_partial(mpcb_mppi* h, const double* x, const doubl
     if (st != MPCB_OK) return st;
     p.eps = d_eps;
     p.eps_f64 = (eps_dtype == MPCB_DT_F64);
-    p.final_mode = 1;
+    p.final_mode = FINAL_RANK_ROW;
     p.rank_partial = d_partial;
     st = launch(h, p);
     if (st != MPCB_OK) return st;
@@ -564,6 +654,86 @@ mpcb_status mpcb_mppi_attach_comm(mpcb_mppi* h, const char id[128]) {
         h->comm = nullptr;
     }
     return nccl_init_rank(&h->comm, id, h->cfg.rank, h->cfg.world_size);
+}
+
+namespace {
+mpcb_status ensure_mailbox(mpcb_mppi* h) {
+    if (h->d_mailbox) return MPCB_OK;
+    const size_t G = h->cfg.world_size, C = h->C;
+    h->mailbox_flag_bytes = ((2 * G * C * sizeof(unsigned int)) + 255) & ~(size_t)255;
+    h->mailbox_bytes = h->mailbox_flag_bytes + 2 * G * C * (size_t)h->PL * sizeof(double);
+    MPCB_CUDA_TRY(cudaMalloc(&h->d_mailbox, h->mailbox_bytes));
+    MPCB_CUDA_TRY(cudaMemset(h->d_mailbox, 0, h->mailbox_bytes));
+    MPCB_CUDA_TRY(cudaDeviceSynchronize());  // zeroed before anyone can learn the handle
+    return MPCB_OK;
+}
+}  // namespace
+
+mpcb_status mpcb_mppi_peer_handle(mpcb_mppi* h, char out[MPCB_PEER_HANDLE_BYTES]) {
+    MPCB_REQUIRE(h && out, "null pointer");
+    MPCB_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    mpcb_status st = ensure_mailbox(h);
+    if (st != MPCB_OK) return st;
+    PeerBlob b;
+    memset(&b, 0, sizeof(b));
+    b.magic = kPeerMagic;
+    b.pid = (int32_t)getpid();
+    b.device = h->cfg.device;
+    b.rank = h->cfg.rank;
+    b.ptr = (uint64_t)(uintptr_t)h->d_mailbox;
+    b.bytes = h->mailbox_bytes;
+    b.flag_bytes = h->mailbox_flag_bytes;
+    b.world = h->cfg.world_size;
+    b.controllers = h->C;
+    b.horizon = h->H;
+    MPCB_CUDA_TRY(cudaIpcGetMemHandle(&b.ipc, h->d_mailbox));
+    memcpy(out, &b, sizeof(b));
+    return MPCB_OK;
+}
+
+mpcb_status mpcb_mppi_attach_peers(mpcb_mppi* h, const char* handles) {
+    MPCB_REQUIRE(h && handles, "null pointer");
+    MPCB_REQUIRE(!h->peers_attached, "peers already attached");
+    MPCB_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    mpcb_status st = ensure_mailbox(h);
+    if (st != MPCB_OK) return st;
+    const int G = h->cfg.world_size;
+    double* mbox[kMergeFan];
+    unsigned int* flags[kMergeFan];
+    for (int r = 0; r < G; ++r) {
+        PeerBlob b;
+        memcpy(&b, handles + (size_t)r * MPCB_PEER_HANDLE_BYTES, sizeof(b));
+        MPCB_REQUIRE(b.magic == kPeerMagic && b.rank == r, "handles must be the mpcb_mppi_peer_handle blobs in rank order");
+        MPCB_REQUIRE(b.world == G && b.controllers == h->C && b.horizon == h->H && b.bytes == h->mailbox_bytes,
+                     "peer handle was made by a controller of a different shape");
+        void* base = nullptr;
+        if (r == h->cfg.rank) {
+            base = h->d_mailbox;
+        } else if (b.pid == (int32_t)getpid()) {
+            // another handle of this process: plain peer access
+            if (b.device != h->cfg.device) {
+                int can = 0;
+                MPCB_CUDA_TRY(cudaDeviceCanAccessPeer(&can, h->cfg.device, b.device));
+                MPCB_REQUIRE(can, "devices cannot access each other's memory");
+                cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) MPCB_CUDA_TRY(e);
+                cudaGetLastError();
+            }
+            base = (void*)(uintptr_t)b.ptr;
+        } else {
+            MPCB_CUDA_TRY(cudaIpcOpenMemHandle(&base, b.ipc, cudaIpcMemLazyEnablePeerAccess));
+            h->peer_ipc[r] = true;
+        }
+        h->peer_base[r] = base;
+        flags[r] = (unsigned int*)base;
+        mbox[r] = (double*)((char*)base + h->mailbox_flag_bytes);
+    }
+    MPCB_CUDA_TRY(cudaMalloc(&h->d_peer_mbox, G * sizeof(double*)));
+    MPCB_CUDA_TRY(cudaMalloc(&h->d_peer_flags, G * sizeof(unsigned int*)));
+    MPCB_CUDA_TRY(cudaMemcpy(h->d_peer_mbox, mbox, G * sizeof(double*), cudaMemcpyHostToDevice));
+    MPCB_CUDA_TRY(cudaMemcpy(h->d_peer_flags, flags, G * sizeof(unsigned int*), cudaMemcpyHostToDevice));
+    h->peers_attached = true;
+    return MPCB_OK;
 }
 
 }  // extern "C"

@@ -5,14 +5,24 @@
 //   PASS 1  noise: Philox4x32-10 + Box-Muller in registers (generate) or a coalesced tile load of the
 //           caller's eps (replay);  v = clamp(u_n + eps)                                   (:38-45)
 //   PASS 2  H-step rollout of the model + stage cost + control term                        (:48-63)
-//   PASS 3-6 as an ONLINE softmax: block max over finite c_k (warp shuffles), w = exp((c-m)/lambda),
+//   PASS 3-6 as an ONLINE softmax: block max over finite c_k (redux), w = exp((c-m)/lambda),
 //           running (m, sum_w, sum_w*v[t]) rescaled when the max moves                     (:65-84)
-// v stays in shared memory ([H][BLOCK+1], conflict-free both for the per-thread writes and for the
-// per-t weighted sums).  Each block leaves one partial row [m, sum_w, argmax, n_finite, sum_w*v[0..H)].
-// Rows are merged by a two-level ticket tree (fan-in <= 64): the last block of a group to arrive merges
-// the group's rows, the last group to arrive merges the group rows and writes u_out/info — or, when the
-// samples are sharded over GPUs, the merged un-normalised row for the cross-rank exchange.  Every load of
-// a merge is independent, so the tail costs a few L2 round trips instead of one per row.
+// v stays in shared memory ([H][BLOCK+4]: conflict-free scalar column writes by the sample threads and
+// conflict-free 128-bit row reads by the per-t weighted sums).  Each block leaves one partial row
+// [m, sum_w, argmax, n_finite, sum_w*v[0..H)].
+//
+// Work split: the K_local samples of a controller are cut into `chunks` contiguous ranges of whole warps
+// (range i = warps [W*i/chunks, W*(i+1)/chunks)), one block per range; a block walks its range in batches of
+// BLOCK samples.  When the whole controller fits on the GPU in one batch per block the host picks ONE block per
+// SM sized to its range (e.g. K = 65536 on 148 SMs: 148 blocks of 512 threads, 13-14 live warps each), so every
+// SM gets the same number of samples and there are only num_sms rows to merge.
+//
+// Rows are merged by the last block to arrive at a ticket (single level, fan-in <= kMergeFan rows handled by
+// all threads of the block: columns x row-partitions), or by a two-level ticket tree when there are more rows.
+// The final merge writes u_out/info — or, when the samples are sharded over GPUs, either the merged
+// un-normalised row (NCCL exchange done by the host code) or it runs the cross-GPU exchange itself: the row is
+// stored straight into every peer's mailbox over NVLink, a flag per (peer, controller) is released, and the same
+// block waits for the peers' rows and combines them (one kernel per control step, no collective call).
 #pragma once
 
 #include <math_constants.h>
@@ -24,13 +34,18 @@
 namespace mpcb {
 
 constexpr int kPartialHdr = 4;   // m, sum_w, argmax (bits), n_finite (bits)
-constexpr int kMergeFan = 64;    // max rows merged by one block
-constexpr int kScratchDoubles = 32 + kMergeFan;
+constexpr int kMergeFan = 256;   // max rows merged by one block
+constexpr int kMaxWarps = 16;    // warps per block (BLOCK <= 512)
+// shared scratch (doubles): red_m[16] red_a[16] red_n[16] red_s[24] sc[kMergeFan]
+constexpr int kScratchDoubles = 16 + 16 + 16 + 24 + kMergeFan;
 
 enum MppiNoise { NOISE_GENERATE = 0, NOISE_GENERATE_DUMP = 1, NOISE_REPLAY = 2 };
+enum MppiFinal { FINAL_NORMALISE = 0, FINAL_RANK_ROW = 1, FINAL_PEER_EXCHANGE = 2 };
 
 struct MppiParams {
     int H;
+    int Hp;          // H rounded up to a power of two (>= 8)
+    int lgHp;
     int C;
     int chunks;      // blocks per controller (level-0 rows)
     int group_size;  // level-0 rows per group (<= kMergeFan)
@@ -39,12 +54,12 @@ struct MppiParams {
     long long K_local;
     long long K_global;
     long long k_offset;  // global index of this rank's first sample
-    long long batches_per_chunk;
+    long long W;         // warps of 32 samples in K_local
     const double* x;  // [C][4]
     const double* u;  // [C][H]
     const void* eps;  // replay: [C][K_global][H]
     int eps_f64;
-    int final_mode;  // 0: normalise into u_out/info; 1: merged partial row into rank_partial
+    int final_mode;  // MppiFinal
     void* eps_dump;  // generate+dump: [C][K_local][H] of real
     double* costs;   // optional [C][K_local]
     unsigned int seed_lo, seed_hi, call_idx, pad0;
@@ -58,6 +73,12 @@ struct MppiParams {
     double* rank_partial;    // [C][kPartialHdr + H]
     unsigned int* done_host;       // mapped host word; the final block stores `epoch` after u_out/info (C == 1 only)
     unsigned int epoch, pad1;
+    // FINAL_PEER_EXCHANGE: device tables [G] of every rank's mailbox / flag base (own entry included)
+    //   mailbox: [2 parity][G source ranks][C][kPartialHdr + H] doubles;  flags: [2][G][C] u32
+    double* const* peer_mbox;
+    unsigned int* const* peer_flags;
+    int G, rank;
+    unsigned int xepoch, pad2;     // exchange epoch (same on every rank), parity = xepoch & 1
     unsigned long long* debug_ts;  // optional [blocks][8] %globaltimer stamps (diagnostics)
     ModelConsts mc;
     double xu_inline[4 + kInlineHorizon];
@@ -70,7 +91,7 @@ constexpr long long kNoArg = 0x7fffffffffffffffll;
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
 #define MPCB_TS(slot)                                                                       \
@@ -81,31 +102,102 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // gpu-scope release/acquire fence around the ticket atomics (cheaper than the sequentially consistent
 // __threadfence(); the ticket pattern only needs release on the producer and acquire on the consumer side)
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void st_release_sys_u32(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Order-preserving map double -> u64 (larger value, larger key); used to run max/argmax on redux.sync.
+__device__ __forceinline__ unsigned long long order_key(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// Warp max over the lanes with `fin`, lowest lane on ties.  Returns (in every lane) the max value, the `tag` of
+// the winning lane and the number of fin lanes; value -inf / tag kNoArg when no lane is fin.
+__device__ __forceinline__ void warp_argmax(double v, long long tag, bool fin, double* vmax, long long* tmax, int* nfin) {
+    const unsigned int full = 0xffffffffu;
+    const unsigned long long key = order_key(v);
+    const unsigned int hi = fin ? (unsigned int)(key >> 32) : 0u;
+    const unsigned int mh = __reduce_max_sync(full, hi);
+    const bool top = fin && hi == mh;
+    const unsigned int lo = top ? (unsigned int)key : 0u;
+    const unsigned int ml = __reduce_max_sync(full, lo);
+    const unsigned int cand = __ballot_sync(full, top && (unsigned int)key == ml);
+    const unsigned int finmask = __ballot_sync(full, fin);
+    *nfin = __popc(finmask);
+    if (cand != 0u) {
+        const int src = __ffs(cand) - 1;
+        int vlo = __double2loint(v), vhi = __double2hiint(v);
+        vlo = __shfl_sync(full, vlo, src);
+        vhi = __shfl_sync(full, vhi, src);
+        *vmax = __hiloint2double(vhi, vlo);
+        int tlo = (int)(tag & 0xffffffffll), thi = (int)(tag >> 32);
+        tlo = __shfl_sync(full, tlo, src);
+        thi = __shfl_sync(full, thi, src);
+        *tmax = ((long long)thi << 32) | (unsigned int)tlo;
+    } else {
+        *vmax = -CUDART_INF;
+        *tmax = kNoArg;
+    }
+}
+
+// 4 consecutive elements of shared memory (16-byte aligned for float, 32-byte for double)
+struct Vec4f { float a, b, c, d; };
+__device__ __forceinline__ void lds4(const float* p, float (&o)[4]) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+__device__ __forceinline__ void lds4(const double* p, double (&o)[4]) {
+    const double2 a = *reinterpret_cast<const double2*>(p);
+    const double2 b = *reinterpret_cast<const double2*>(p + 2);
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+__device__ __forceinline__ bool all_zero_bits(const float (&w)[4]) {
+    return ((__float_as_uint(w[0]) | __float_as_uint(w[1]) | __float_as_uint(w[2]) | __float_as_uint(w[3])) << 1) == 0u;
+}
+__device__ __forceinline__ bool all_zero_bits(const double (&w)[4]) {
+    return (((unsigned long long)__double_as_longlong(w[0]) | (unsigned long long)__double_as_longlong(w[1]) |
+             (unsigned long long)__double_as_longlong(w[2]) | (unsigned long long)__double_as_longlong(w[3])) << 1) == 0ull;
+}
 
 // Merges n_rows (<= kMergeFan) partial rows (row r at rows + r*row_stride) of one controller; the whole
-// block participates.  scratch: kScratchDoubles doubles of shared memory.
-//   final_mode 1: the merged, un-normalised row is written to out_row
-//   final_mode 0: u_out = sum_w*v / sum_w, info, status                      (src/mppi.rs:76-91)
-// All global loads of a merge are issued up front (headers and up to kMergeBatch values per thread), so a
-// level costs about one L2 round trip instead of one per pass.
+// block participates.  scratch: kScratchDoubles doubles, part: max(BLOCK, Hp) doubles of shared memory.
+//   final_mode FINAL_RANK_ROW : the merged, un-normalised row is written to out_row
+//   final_mode FINAL_NORMALISE: u_out = sum_w*v / sum_w, info, status                      (src/mppi.rs:76-91)
+// Columns are split over (t, q): thread item (t, q) sums the rows of partition q for column t, with the loads of
+// up to kMergeBatch rows in flight at once; the partitions are then added in a fixed order, so the result does
+// not depend on timing.  The first batch of column loads is issued before the header reductions.
 constexpr int kMergeBatch = 16;
 
 template <int BLOCK>
-__device__ void mppi_merge_rows(const double* rows, long long row_stride, int n_rows, int H, double lambda,
-                                int final_mode, double* u_out, double* u_out_host, mpcb_mppi_info* info,
-                                mpcb_mppi_info* info_host, double* out_row, double* scratch,
-                                unsigned int* done_host = nullptr, unsigned int epoch = 0) {
+__device__ void mppi_merge_rows(const double* rows, long long row_stride, int n_rows, int H, int Hp, int lgHp,
+                                double lambda, int final_mode, double* u_out, double* u_out_host, mpcb_mppi_info* info,
+                                mpcb_mppi_info* info_host, double* out_row, double* scratch, double* part,
+                                unsigned int* done_host = nullptr, unsigned int epoch = 0,
+                                int forced_status = MPCB_OK, unsigned long long* ts = nullptr) {
     constexpr int NW = BLOCK / 32;
     constexpr int RPT = (kMergeFan + BLOCK - 1) / BLOCK;  // header rows per thread
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    double* red_m = scratch;                        // [8]
-    long long* red_a = (long long*)(scratch + 8);   // [8]
-    long long* red_n = (long long*)(scratch + 16);  // [8]
-    double* red_s = scratch + 24;                   // [8]
-    double* sc = scratch + 32;                      // [kMergeFan] per-row scale
+    double* red_m = scratch;                        // [16]
+    long long* red_a = (long long*)(scratch + 16);  // [16]
+    long long* red_n = (long long*)(scratch + 32);  // [16]
+    double* red_s = scratch + 48;                   // [24]
+    double* sc = scratch + 72;                      // [kMergeFan] per-row scale
     __shared__ int s_status;
 
-    // ---- issue every load of the first column pass: row headers + the first kMergeBatch rows of column tid ----
+    // (t, q) item of this thread for the first column pass
+    int nq = BLOCK >> lgHp;  // row partitions (power of two)
+    if (nq < 1) nq = 1;
+    if (nq > 16) nq = 16;
+    const int rq = (n_rows + nq - 1) / nq;  // rows per partition
+    const int items = Hp * nq;
+
+    // ---- issue every load of the first pass: row headers + the first kMergeBatch rows of item tid ----
     double hm[RPT], hs[RPT];
     long long ha[RPT], hn[RPT];
 #pragma unroll
@@ -122,10 +214,13 @@ __device__ void mppi_merge_rows(const double* rows, long long row_stride, int n_
     }
     double v0[kMergeBatch];
     {
-        const double* col = rows + kPartialHdr + tid;
+        const int t = tid & (Hp - 1), q = tid >> lgHp;
+        const int r0 = q * rq;
+        const double* col = rows + kPartialHdr + t + (long long)r0 * row_stride;
+        const bool live = tid < items && t < H;
 #pragma unroll
         for (int i = 0; i < kMergeBatch; ++i)
-            v0[i] = (tid < H && i < n_rows) ? __ldcg(col + (long long)i * row_stride) : 0.0;
+            v0[i] = (live && i < rq && r0 + i < n_rows) ? __ldcg(col + (long long)i * row_stride) : 0.0;
     }
 
     // ---- max / argmax / finite count over the headers ----
@@ -174,31 +269,45 @@ __device__ void mppi_merge_rows(const double* rows, long long row_stride, int n_
     s = red_s[0];
 #pragma unroll
     for (int w = 1; w < NW; ++w) s += red_s[w];
-    // ---- merged weighted control sums ----
-    for (int t = tid; t < H; t += BLOCK) {
+    if (ts != nullptr && tid == 0) ts[3] = globaltimer_ns();
+    // ---- merged weighted control sums: partition sums, then the partitions in order ----
+    for (int item = tid; item < items; item += BLOCK) {
+        const int t = item & (Hp - 1), q = item >> lgHp;
+        if (t >= H) continue;
+        const int r0 = q * rq;
+        int r1 = r0 + rq;
+        if (r1 > n_rows) r1 = n_rows;
         double acc = 0.0;
         const double* col = rows + kPartialHdr + t;
-        for (int r0 = 0; r0 < n_rows; r0 += kMergeBatch) {
+        for (int rb = r0; rb < r1; rb += kMergeBatch) {
             double v[kMergeBatch];
-            if (t == tid && r0 == 0) {
+            if (item == tid && rb == r0) {
 #pragma unroll
                 for (int i = 0; i < kMergeBatch; ++i) v[i] = v0[i];
             } else {
 #pragma unroll
                 for (int i = 0; i < kMergeBatch; ++i)
-                    v[i] = (r0 + i < n_rows) ? __ldcg(col + (long long)(r0 + i) * row_stride) : 0.0;
+                    v[i] = (rb + i < r1) ? __ldcg(col + (long long)(rb + i) * row_stride) : 0.0;
             }
 #pragma unroll
             for (int i = 0; i < kMergeBatch; ++i)
-                if (r0 + i < n_rows) acc += sc[r0 + i] * v[i];  // scale 0 * NaN = NaN keeps the reference's poisoning
+                if (rb + i < r1) acc += sc[rb + i] * v[i];  // scale 0 * NaN = NaN keeps the reference's poisoning
         }
-        if (final_mode == 1) {
+        part[q * Hp + t] = acc;
+    }
+    __syncthreads();
+    if (ts != nullptr && tid == 0) ts[4] = globaltimer_ns();
+    for (int t = tid; t < H; t += BLOCK) {
+        double acc = part[t];
+        for (int q = 1; q < nq; ++q) acc += part[q * Hp + t];
+        if (final_mode == FINAL_RANK_ROW) {
             out_row[kPartialHdr + t] = acc;
         } else {
             const double uo = any ? acc / s : 0.0;
             if (t == 0) {
                 int st = MPCB_OK;
-                if (!any) st = MPCB_NO_FINITE_COST;            // src/mppi.rs:69
+                if (forced_status != MPCB_OK) st = forced_status;
+                else if (!any) st = MPCB_NO_FINITE_COST;       // src/mppi.rs:69
                 else if (s == 0.0) st = MPCB_SUM_ZERO;          // :76-78
                 else if (!finite_f64(uo)) st = MPCB_U_INVALID;  // :87-89 (element 0 only)
                 s_status = st;
@@ -210,7 +319,7 @@ __device__ void mppi_merge_rows(const double* rows, long long row_stride, int n_
     if (done_host) __threadfence_system();  // every writer orders its host stores before the completion word
     __syncthreads();
     if (tid == 0) {
-        if (final_mode == 1) {
+        if (final_mode == FINAL_RANK_ROW) {
             out_row[0] = any ? m : -CUDART_INF;
             out_row[1] = s;
             out_row[2] = ll_as_double(any ? a : -1ll);
@@ -245,35 +354,63 @@ struct RealTraits<double> {
     static constexpr bool kExact = true;
 };
 
+__host__ __device__ inline int mppi_pow2_horizon(int H, int* lg) {
+    int hp = 8, l = 3;
+    while (hp < H) { hp <<= 1; ++l; }
+    if (lg) *lg = l;
+    return hp;
+}
+
 // Shared-memory bytes of one block.
 template <typename real>
 __host__ __device__ inline size_t mppi_smem_bytes(int H, int block) {
-    size_t dbl = (size_t)H + kScratchDoubles;                     // U_run + reduction/merge scratch
-    size_t rl = (size_t)2 * H + block + (size_t)H * (block + 1);  // su, sui, w_s, v_s
+    const int Hp = mppi_pow2_horizon(H, nullptr);
+    const size_t npart = (size_t)(block > Hp ? block : Hp);
+    size_t dbl = ((size_t)H + kScratchDoubles + npart + 3) & ~(size_t)3;  // U_run + scratch + partition sums (32 B)
+    size_t rl = (size_t)2 * ((H + 3) & ~3) + block + (size_t)H * (block + 4);  // su, sui, w_s, v_s
     size_t bytes = dbl * sizeof(double) + rl * sizeof(real);
     return (bytes + 15) & ~(size_t)15;
+}
+
+// w = exp(a) for the FP32 path: a <= 0 is computed in f64 by the caller; ex2.approx (2 ulp) on a*log2(e).
+// Underflows to exactly 0 below a ~ -87; the f64 reference would keep weights down to e^-745, all of which
+// are < 1e-37 of the block maximum.
+__device__ __forceinline__ float fast_exp_neg(double a) {
+    const float t = (float)(a * 1.4426950408889634074);
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+    return r;
 }
 
 template <template <typename> class ModelT, typename real, int BLOCK, int NOISE>
 __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_constant__ MppiParams p) {
     constexpr int NW = BLOCK / 32;
-    constexpr int LD = BLOCK + 1;
+    constexpr int LD = BLOCK + 4;
     constexpr bool kExact = RealTraits<real>::kExact;
     constexpr bool kReplay = (NOISE == NOISE_REPLAY);
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int H = p.H;
-    double* U_run = reinterpret_cast<double*>(smem_raw);            // [H]
-    double* scratch = U_run + H;                                    // [kScratchDoubles]
-    real* su = reinterpret_cast<real*>(scratch + kScratchDoubles);  // [H]  u_n
-    real* sui = su + H;                                             // [H]  u_n * sigma^-2
-    real* w_s = sui + H;                                            // [BLOCK]
-    real* v_s = w_s + BLOCK;                                        // [H][LD]
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    const int H = p.H, Hp = p.Hp, lgHp = p.lgHp;
+    const int H4a = (H + 3) & ~3;
+    double* U_run = reinterpret_cast<double*>(smem_raw);             // [H]
+    double* scratch = U_run + H;                                     // [kScratchDoubles]
+    double* part_d = scratch + kScratchDoubles;                      // [max(BLOCK, Hp)]
+    real* part_r = reinterpret_cast<real*>(part_d);
+    const int ndbl = (H + kScratchDoubles + (BLOCK > Hp ? BLOCK : Hp) + 3) & ~3;
+    real* su = reinterpret_cast<real*>(U_run + ndbl);                // [H4a]  u_n (16-byte aligned rows from here on)
+    real* sui = su + H4a;                                            // [H4a]  u_n * sigma^-2
+    real* w_s = sui + H4a;                                           // [BLOCK]
+    real* v_s = w_s + BLOCK;                                         // [H][LD]
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int c = blockIdx.x / p.chunks;      // controller
-    const int chunk = blockIdx.x % p.chunks;  // sample chunk of this controller
+    const int chunk = blockIdx.x % p.chunks;  // sample range of this controller
 
     MPCB_TS(0);
+    if (p.debug_ts != nullptr && threadIdx.x == 0) {
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        p.debug_ts[(size_t)blockIdx.x * 8 + 6] = smid + 1;
+    }
     // ---- prologue: model constants, x0, u_n ----
     ModelT<real> model;
     model.load(p.mc);
@@ -299,196 +436,222 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
     const real lo = (real)p.lo, hi = (real)p.hi;
     const float neg2s2ln2 = (float)(-2.0 * p.std_dev * p.std_dev * 0.693147180559945309417);
     const double lambda = p.lambda;
+    const double inv_lambda = 1.0 / lambda;
 
     double m_run = -CUDART_INF, S_run = 0.0;
     long long arg_run = kNoArg, nfin_run = 0;
 
-    double* red_m = scratch;                       // [8]
-    long long* red_a = (long long*)(scratch + 8);  // [8]
-    int* red_n = (int*)(scratch + 16);             // [8]
-    double* red_s = scratch + 24;                  // [8]
+    double* red_m = scratch;                        // [16]
+    long long* red_a = (long long*)(scratch + 16);  // [16]
+    int* red_n = (int*)(scratch + 32);              // [16]
+    double* red_s = scratch + 48;                   // [24]: [0..15] warp sums, [16] rescale
 
-    const long long batch0 = (long long)chunk * p.batches_per_chunk;
-    const long long nbatches_total = (p.K_local + BLOCK - 1) / BLOCK;
-    long long batch_end = batch0 + p.batches_per_chunk;
-    if (batch_end > nbatches_total) batch_end = nbatches_total;
+    // this block's range of whole warps, walked in batches of NW warps
+    const long long w_begin = p.W * chunk / p.chunks;
+    const long long w_end = p.W * (chunk + 1) / p.chunks;
     __syncthreads();
 
-    for (long long b = batch0; b < batch_end; ++b) {
-        const long long kl = b * BLOCK + tid;  // local sample index
-        const bool valid = kl < p.K_local;
+    for (long long wb = w_begin; wb < w_end; wb += NW) {
+        const long long gw = wb + wid;         // this warp's index in the controller's sample range
+        const bool warp_live = gw < w_end;     // whole warps beyond the range skip the rollout
+        const long long kl = gw * 32 + lane;   // local sample index
+        const bool valid = warp_live && kl < p.K_local;
         const long long kg = p.k_offset + kl;  // global sample index (Philox counter / replay row / argmax)
 
         if constexpr (kReplay) {
-            // coalesced tile load: BLOCK consecutive sample rows of H values -> v_s[t][k]
-            const long long k_first = b * BLOCK;
-            long long nrows = p.K_local - k_first;
+            // coalesced tile load: the batch's consecutive sample rows of H values -> v_s[t][k]
+            const long long k_first = wb * 32;
+            long long nrows = (w_end - wb) * 32;
             if (nrows > BLOCK) nrows = BLOCK;
+            if (nrows > p.K_local - k_first) nrows = p.K_local - k_first;
             const long long base = ((long long)c * p.K_global + p.k_offset + k_first) * H;
-            const int total = BLOCK * H;
             const int live = (int)nrows * H;
-            for (int i = tid; i < total; i += BLOCK) {
-                real e = (real)0;
-                if (i < live) {
-                    e = p.eps_f64 ? (real) reinterpret_cast<const double*>(p.eps)[base + i]
-                                  : (real) reinterpret_cast<const float*>(p.eps)[base + i];
-                }
+            for (int i = tid; i < live; i += BLOCK) {
+                const real e = p.eps_f64 ? (real) reinterpret_cast<const double*>(p.eps)[base + i]
+                                         : (real) reinterpret_cast<const float*>(p.eps)[base + i];
                 const int kr = i / H, t = i - kr * H;
                 v_s[t * LD + kr] = e;
             }
             __syncthreads();
         }
 
-        // ---- PASS 1+2: noise, clamp, rollout, cost ----
-        real x[4] = {x0[0], x0[1], x0[2], x0[3]};
-        double J = 0.0, CT = 0.0;
-        real cw = (real)0, cu = (real)0;
-        const unsigned int c0 = (unsigned int)(kg & 0xffffffffll);
-        const unsigned int khi = (unsigned int)((kg >> 32) & 0xffff) << 16;
-        real* vcol = v_s + tid;
+        double ck = -CUDART_INF;
+        if (warp_live) {
+            // ---- PASS 1+2: noise, clamp, rollout, cost ----
+            real x[4] = {x0[0], x0[1], x0[2], x0[3]};
+            double J = 0.0, CT = 0.0;
+            real cw = (real)0, cu = (real)0;
+            const unsigned int c0 = (unsigned int)(kg & 0xffffffffll);
+            const unsigned int khi = (unsigned int)((kg >> 32) & 0xffff) << 16;
+            real* vcol = v_s + tid;
 
-        // four N(0, sigma^2) draws for steps t0..t0+3
-        auto noise4 = [&](int t0, real(&e)[4]) {
-            if constexpr (kReplay) {
+            // four N(0, sigma^2) draws for steps t0..t0+3
+            auto noise4 = [&](int t0, real(&e)[4]) {
+                if constexpr (kReplay) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) e[i] = (t0 + i < H) ? vcol[(t0 + i) * LD] : (real)0;
-            } else {
-                const Philox4 r = philox4x32_10(c0, p.call_idx, (unsigned int)c, (unsigned int)(t0 >> 2) | khi,
-                                                p.seed_lo, p.seed_hi);
-                float z[4];
-                philox_normal4(r, neg2s2ln2, z);
+                    for (int i = 0; i < 4; ++i) e[i] = (valid && t0 + i < H) ? vcol[(t0 + i) * LD] : (real)0;
+                } else {
+                    const Philox4 r = philox4x32_10(c0, p.call_idx, (unsigned int)c, (unsigned int)(t0 >> 2) | khi,
+                                                    p.seed_lo, p.seed_hi);
+                    float z[4];
+                    philox_normal4(r, neg2s2ln2, z);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) e[i] = (real)z[i];
-                if constexpr (NOISE == NOISE_GENERATE_DUMP) {
-                    if (valid) {
-                        real* dump = reinterpret_cast<real*>(p.eps_dump) + ((long long)c * p.K_local + kl) * H;
+                    for (int i = 0; i < 4; ++i) e[i] = (real)z[i];
+                    if constexpr (NOISE == NOISE_GENERATE_DUMP) {
+                        if (valid) {
+                            real* dump = reinterpret_cast<real*>(p.eps_dump) + ((long long)c * p.K_local + kl) * H;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if (t0 + i < H) dump[t0 + i] = e[i];
+                            for (int i = 0; i < 4; ++i)
+                                if (t0 + i < H) dump[t0 + i] = e[i];
+                        }
                     }
                 }
-            }
-        };
-        // one rollout step: v = clamp(u_n[t] + eps), x <- dynamics(x, v), cost, control term
-        auto step = [&](int t, real eps) {
-            real v = su[t] + eps;
-            if constexpr (kExact) v = clampr(v, lo, hi);  // f64::clamp, NaN stays NaN
-            else v = fminf(fmaxf(v, lo), hi);
-            vcol[t * LD] = v;
-            model.step(x, v);
-            const real ct = model.cost(x);
-            if constexpr (kExact) {
-                J = J + ct;         // :57 c + cost(x_n)
-                CT += sui[t] * v;   // :60 (u*inv)*v, summed in order
-            } else {
-                cw += ct;
-                cu = fmaf(sui[t], v, cu);
-            }
-        };
+            };
+            // one rollout step: v = clamp(u_n[t] + eps), x <- dynamics(x, v), cost, control term
+            auto step = [&](int t, real eps, real ut, real uit) {
+                real v = ut + eps;
+                if constexpr (kExact) v = clampr(v, lo, hi);  // f64::clamp, NaN stays NaN
+                else v = fminf(fmaxf(v, lo), hi);
+                vcol[t * LD] = v;
+                model.step(x, v);
+                if constexpr (kExact) {
+                    const real ct = model.cost(x);
+                    J = J + ct;      // :57 c + cost(x_n)
+                    CT += uit * v;   // :60 (u*inv)*v, summed in order
+                } else {
+                    cw = model.cost.acc(x, cw);
+                    cu = fmaf(uit, v, cu);
+                }
+            };
 
-        // Software pipeline: the noise of group g+1 (independent of the state) is drawn while group g rolls out,
-        // so the scheduler has Philox/Box-Muller work to fill the dependency stalls of the serial dynamics chain.
-        const int H4 = H & ~3;
-        real e[4];
-        noise4(0, e);
-        for (int t0 = 0; t0 < H4; t0 += 4) {
-            real en[4];
-            noise4(t0 + 4, en);  // the last prefetch (t0 + 4 >= H4) feeds the tail below or is discarded
+            // Software pipeline: the noise of group g+1 (independent of the state) is drawn while group g rolls
+            // out, so the scheduler has Philox/Box-Muller work to fill the dependency stalls of the serial chain.
+            const int H4 = H & ~3;
+            real e[4];
+            noise4(0, e);
+            for (int t0 = 0; t0 < H4; t0 += 4) {
+                real en[4], u4[4], ui4[4];
+                lds4(su + t0, u4);
+                lds4(sui + t0, ui4);
+                noise4(t0 + 4, en);  // the last prefetch (t0 + 4 >= H4) feeds the tail below or is discarded
 #pragma unroll
-            for (int i = 0; i < 4; ++i) step(t0 + i, e[i]);
-            if constexpr (!kExact) {
-                // FP32 partial sums over 4 steps are flushed into the FP64 accumulators
-                J += (double)cw;
-                CT += (double)cu;
-                cw = (real)0;
-                cu = (real)0;
+                for (int i = 0; i < 4; ++i) step(t0 + i, e[i], u4[i], ui4[i]);
+                if constexpr (!kExact) {
+                    // FP32 partial sums over 4 steps are flushed into the FP64 accumulators
+                    J += (double)cw;
+                    CT += (double)cu;
+                    cw = (real)0;
+                    cu = (real)0;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) e[i] = en[i];
             }
+            if (H4 < H) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) e[i] = en[i];
-        }
-        if (H4 < H) {
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-                if (H4 + i < H) step(H4 + i, e[i]);
-            if constexpr (!kExact) {
-                J += (double)cw;
-                CT += (double)cu;
+                for (int i = 0; i < 3; ++i)
+                    if (H4 + i < H) step(H4 + i, e[i], su[H4 + i], sui[H4 + i]);
+                if constexpr (!kExact) {
+                    J += (double)cw;
+                    CT += (double)cu;
+                }
             }
+            ck = -J - CT;  // :61
+            if (p.costs != nullptr && valid) p.costs[(long long)c * p.K_local + kl] = ck;
         }
-        const double ck = -J - CT;  // :61
-        if (p.costs != nullptr && valid) p.costs[(long long)c * p.K_local + kl] = ck;
 
         // ---- PASS 3: block max over finite c_k, lowest index on ties ----
         const bool fin = valid && finite_f64(ck);
-        double bm = fin ? ck : -CUDART_INF;
-        long long ba = fin ? kg : kNoArg;
-        int bn = fin ? 1 : 0;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double om = shfl_down_f64(bm, off);
-            const long long oa = shfl_down_i64(ba, off);
-            bn += __shfl_down_sync(0xffffffffu, bn, off);
-            if (om > bm || (om == bm && oa < ba)) { bm = om; ba = oa; }
-        }
+        double bm;
+        long long ba;
+        int bn;
+        warp_argmax(ck, kg, fin, &bm, &ba, &bn);
         if (lane == 0) { red_m[wid] = bm; red_a[wid] = ba; red_n[wid] = bn; }
         __syncthreads();
-        bm = red_m[0]; ba = red_a[0]; bn = red_n[0];
-#pragma unroll
-        for (int w = 1; w < NW; ++w) {
-            const double om = red_m[w];
-            const long long oa = red_a[w];
-            bn += red_n[w];
-            if (om > bm || (om == bm && oa < ba)) { bm = om; ba = oa; }
+        {
+            // every warp reduces the NW warp results again (lane l holds warp l's entry; warps are in index order)
+            const bool has = lane < NW;
+            const double wm = has ? red_m[lane] : -CUDART_INF;
+            const long long wa = has ? red_a[lane] : kNoArg;
+            const int wn = has ? red_n[lane] : 0;
+            int dummy;
+            warp_argmax(wm, wa, has && wa != kNoArg, &bm, &ba, &dummy);
+            bn = __reduce_add_sync(0xffffffffu, wn);
         }
         const double m_old = m_run;
         if (bm > m_run) { m_run = bm; arg_run = ba; }
         nfin_run += bn;
 
         // ---- PASS 4-5: weights against the running max, rescale of what was accumulated so far ----
-        // exp(a) is exactly 0 in f64 for a < -745.14: skipping the call there is bit-identical and spares most
-        // warps the FP64 exp (far-from-best samples dominate).
-        double w;
-        {
+        real w;
+        if constexpr (kExact) {
+            // reference semantics: exp((c - max)/lambda) for every sample, NaN/+inf poison the sums (:71-74);
+            // exp(a) is exactly 0 in f64 for a < -745.14, so skipping the call there is bit-identical
             const double arg = (ck - m_run) / lambda;
-            if constexpr (kExact) {
-                // reference semantics: exp((c - max)/lambda) for every sample, NaN/+inf poison the sums (:71-74)
-                if (!valid || ck == -CUDART_INF) w = 0.0;
-                else w = (arg < -746.0) ? 0.0 : exp(arg);
-            } else {
-                // FP32 rollouts can overflow where the f64 reference yields a huge finite cost whose weight
-                // underflows to exactly 0: non-finite costs get weight 0 here.
-                w = (fin && arg >= -746.0) ? exp(arg) : 0.0;
-            }
+            if (!valid || ck == -CUDART_INF) w = 0.0;
+            else w = (arg < -746.0) ? 0.0 : exp(arg);
+        } else {
+            // FP32 rollouts can overflow where the f64 reference yields a huge finite cost whose weight
+            // underflows to exactly 0: non-finite costs get weight 0 here.
+            w = fin ? fast_exp_neg((ck - m_run) * inv_lambda) : 0.0f;
         }
-        w_s[tid] = (real)w;
-        const double wsum = warp_sum_f64(w);
-        if (lane == 0) red_s[wid] = wsum;
-        if (tid == 0) red_s[NW] = (m_old == -CUDART_INF) ? 0.0 : exp((m_old - m_run) / lambda);  // block-uniform rescale
+        w_s[tid] = w;
+        {
+            real ws = w;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                if constexpr (kExact) ws += shfl_down_f64(ws, off);
+                else ws += __shfl_down_sync(0xffffffffu, ws, off);
+            }
+            if (lane == 0) red_s[wid] = (double)ws;
+        }
+        if (tid == 0) red_s[16] = (m_old == -CUDART_INF) ? 0.0 : exp((m_old - m_run) / lambda);  // block-uniform rescale
         __syncthreads();
-        const double resc = red_s[NW];
+        const double resc = red_s[16];
         double bs = red_s[0];
 #pragma unroll
         for (int wI = 1; wI < NW; ++wI) bs += red_s[wI];
         S_run = S_run * resc + bs;
 
-        // ---- PASS 6: sum_k w_k * v[k][t], one thread per t, conflict-free column reads ----
-        for (int t = tid; t < H; t += BLOCK) {
-            const real* col = v_s + t * LD;
-            real a0 = (real)0, a1 = (real)0, a2 = (real)0, a3 = (real)0;
-#pragma unroll 4
-            for (int k = 0; k < BLOCK; k += 4) {
-                a0 += w_s[k + 0] * col[k + 0];
-                a1 += w_s[k + 1] * col[k + 1];
-                a2 += w_s[k + 2] * col[k + 2];
-                a3 += w_s[k + 3] * col[k + 3];
+        // ---- PASS 6: sum_k w_k * v[k][t].  Item (t, q): column t, sample partition q; 128-bit shared loads of
+        // four weights (broadcast) and four samples (conflict-free); groups whose weights are all zero —
+        // samples far from the best, and warps beyond the range — are skipped, which leaves the sums unchanged. ----
+        {
+            int nq = BLOCK >> lgHp;
+            if (nq < 1) nq = 1;
+            if (nq > BLOCK / 8) nq = BLOCK / 8;
+            const int kper = BLOCK / nq;
+            const int items = Hp * nq;
+            for (int item = tid; item < items; item += BLOCK) {
+                const int t = item & (Hp - 1), q = item >> lgHp;
+                if (t >= H) continue;
+                const real* col = v_s + t * LD + q * kper;
+                const real* wq = w_s + q * kper;
+                real a0 = (real)0, a1 = (real)0, a2 = (real)0, a3 = (real)0;
+#pragma unroll 2
+                for (int k = 0; k < kper; k += 4) {
+                    real w4[4], v4[4];
+                    lds4(wq + k, w4);
+                    if (all_zero_bits(w4)) continue;
+                    lds4(col + k, v4);
+                    a0 += w4[0] * v4[0];
+                    a1 += w4[1] * v4[1];
+                    a2 += w4[2] * v4[2];
+                    a3 += w4[3] * v4[3];
+                }
+                part_r[q * Hp + t] = (a0 + a1) + (a2 + a3);
             }
-            U_run[t] = U_run[t] * resc + (double)((a0 + a1) + (a2 + a3));
+            __syncthreads();
+            for (int t = tid; t < H; t += BLOCK) {
+                real acc = part_r[t];
+                for (int q = 1; q < nq; ++q) acc += part_r[q * Hp + t];
+                U_run[t] = U_run[t] * resc + (double)acc;
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 
     MPCB_TS(1);
-    // ---- partial row of this block, then the two-level ticket merge ----
+    // ---- partial row of this block, then the ticket merge ----
     const int PL = kPartialHdr + H;
     double* ctrl_rows = p.partial + (long long)c * (p.chunks + p.groups) * PL;
     double* my_row = ctrl_rows + (long long)chunk * PL;
@@ -513,33 +676,78 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
     MPCB_TS(2);
     if (!s_last) return;
     fence_acq_rel_gpu();
+    const double* final_rows = ctrl_rows;
+    int final_n = p.chunks;
+    if (p.groups > 1) {
+        double* group_rows = ctrl_rows + (long long)p.chunks * PL;
+        mppi_merge_rows<BLOCK>(ctrl_rows + (long long)g_first * PL, PL, g_rows, H, Hp, lgHp, lambda, FINAL_RANK_ROW,
+                               nullptr, nullptr, nullptr, nullptr, group_rows + (long long)g * PL, scratch, part_d);
+        if (tid == 0) cnt[g] = 0u;
+        MPCB_TS(3);
+        fence_acq_rel_gpu();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(&cnt[p.groups], 1u) == (unsigned int)(p.groups - 1));
+        __syncthreads();
+        MPCB_TS(4);
+        if (!s_last) return;
+        fence_acq_rel_gpu();
+        final_rows = group_rows;
+        final_n = p.groups;
+    }
+    // ---- final merge of this controller ----
     double* u_out_c = p.u_out + (long long)c * H;
     double* u_host_c = p.u_out_host ? p.u_out_host + (long long)c * H : nullptr;
     mpcb_mppi_info* info_host_c = p.info_host ? p.info_host + c : nullptr;
-    double* rank_row = p.rank_partial ? p.rank_partial + (long long)c * PL : nullptr;
-    if (p.groups == 1) {
-        mppi_merge_rows<BLOCK>(ctrl_rows, PL, p.chunks, H, lambda, p.final_mode, u_out_c, u_host_c, p.info + c,
-                               info_host_c, rank_row, scratch, p.done_host, p.epoch);
-        if (tid == 0) cnt[0] = 0u;  // ready for the next launch
-        MPCB_TS(3);
+    const int last_cnt = (p.groups > 1) ? p.groups : 0;
+    if (p.final_mode != FINAL_PEER_EXCHANGE) {
+        double* rank_row = p.rank_partial ? p.rank_partial + (long long)c * PL : nullptr;
+        mppi_merge_rows<BLOCK>(final_rows, PL, final_n, H, Hp, lgHp, lambda, p.final_mode, u_out_c, u_host_c, p.info + c,
+                               info_host_c, rank_row, scratch, part_d, p.done_host, p.epoch, MPCB_OK,
+                               (p.debug_ts != nullptr && p.groups == 1) ? p.debug_ts + (size_t)blockIdx.x * 8 : nullptr);
+        if (tid == 0) cnt[last_cnt] = 0u;  // ready for the next launch
+        MPCB_TS(5);
         return;
     }
-    double* group_rows = ctrl_rows + (long long)p.chunks * PL;
-    mppi_merge_rows<BLOCK>(ctrl_rows + (long long)g_first * PL, PL, g_rows, H, lambda, 1, nullptr, nullptr, nullptr,
-                           nullptr, group_rows + (long long)g * PL, scratch);
-    if (tid == 0) cnt[g] = 0u;
-    MPCB_TS(3);
-    fence_acq_rel_gpu();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(&cnt[p.groups], 1u) == (unsigned int)(p.groups - 1));
-    __syncthreads();
-    MPCB_TS(4);
-    if (!s_last) return;
-    fence_acq_rel_gpu();
-    mppi_merge_rows<BLOCK>(group_rows, PL, p.groups, H, lambda, p.final_mode, u_out_c, u_host_c, p.info + c, info_host_c,
-                           rank_row, scratch, p.done_host, p.epoch);
-    if (tid == 0) cnt[p.groups] = 0u;
-    MPCB_TS(5);
+    // ---- cross-GPU exchange inside the kernel: this rank's merged row goes into every rank's
+    // mailbox slot [parity][rank][c] (peer stores over NVLink), then one flag per peer is released; the block
+    // then acquires the G flags of its own mailbox and combines the G rows exactly like the rows of one GPU.
+    // Slots alternate with the exchange epoch: a peer can only be one step ahead, so two slots never collide. ----
+    {
+        const int G = p.G;
+        const unsigned int par = p.xepoch & 1u;
+        const long long slot_self = ((long long)(par * G + p.rank) * p.C + c);
+        double* own_box = p.peer_mbox[p.rank];
+        double* my_slot = own_box + slot_self * PL;
+        mppi_merge_rows<BLOCK>(final_rows, PL, final_n, H, Hp, lgHp, lambda, FINAL_RANK_ROW, nullptr, nullptr, nullptr,
+                               nullptr, my_slot, scratch, part_d);
+        if (tid == 0) cnt[last_cnt] = 0u;
+        __syncthreads();  // the slot (header by thread 0, columns by the others) is complete in this GPU's memory
+        for (int r = 0; r < G; ++r) {
+            if (r == p.rank) continue;
+            double* dst = p.peer_mbox[r] + slot_self * PL;
+            for (int i = tid; i < PL; i += BLOCK) dst[i] = __ldcg(my_slot + i);
+        }
+        __threadfence_system();
+        __syncthreads();
+        for (int r = tid; r < G; r += BLOCK) st_release_sys_u32(p.peer_flags[r] + slot_self, p.xepoch);
+        // wait for every rank's row of this step (bounded: a missing peer becomes MPCB_PEER_TIMEOUT, not a hang)
+        __shared__ int s_timeout;
+        if (tid == 0) s_timeout = 0;
+        __syncthreads();
+        for (int r = tid; r < G; r += BLOCK) {
+            const unsigned int* f = p.peer_flags[p.rank] + ((long long)(par * G + r) * p.C + c);
+            const unsigned long long t_start = globaltimer_ns();
+            while (ld_acquire_sys_u32(f) != p.xepoch) {
+                if (globaltimer_ns() - t_start > 20000000000ull) { s_timeout = 1; break; }
+            }
+        }
+        __syncthreads();
+        const int forced = s_timeout ? MPCB_PEER_TIMEOUT : MPCB_OK;
+        mppi_merge_rows<BLOCK>(own_box + (long long)(par * G) * p.C * PL + (long long)c * PL, (long long)p.C * PL, G, H, Hp,
+                               lgHp, lambda, FINAL_NORMALISE, u_out_c, u_host_c, p.info + c, info_host_c, nullptr, scratch,
+                               part_d, p.done_host, p.epoch, forced);
+        MPCB_TS(5);
+    }
 }
 
 // Cross-rank merge: rows[g][c][PL] gathered from all ranks -> u_out / info.  One block per controller.
@@ -558,14 +766,17 @@ struct MppiCombineParams {
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) mppi_combine_kernel(const MppiCombineParams p) {
     __shared__ double scratch[kScratchDoubles];
+    __shared__ double part[kMaxHorizon > BLOCK ? kMaxHorizon : BLOCK];
     const int c = blockIdx.x;
     const int PL = kPartialHdr + p.H;
-    mppi_merge_rows<BLOCK>(p.rows + (long long)c * PL, (long long)p.C * PL, p.G, p.H, p.lambda, 0,
+    int lg;
+    const int Hp = mppi_pow2_horizon(p.H, &lg);
+    mppi_merge_rows<BLOCK>(p.rows + (long long)c * PL, (long long)p.C * PL, p.G, p.H, Hp, lg, p.lambda, FINAL_NORMALISE,
                            p.u_out + (long long)c * p.H, p.u_out_host ? p.u_out_host + (long long)c * p.H : nullptr,
-                           p.info + c, p.info_host ? p.info_host + c : nullptr, nullptr, scratch, p.done_host, p.epoch);
+                           p.info + c, p.info_host ? p.info_host + c : nullptr, nullptr, scratch, part, p.done_host, p.epoch);
 }
 
-// kernel entry table (defined in mppi_f32.cu / mppi_f64.cu)
+// kernel entry table (defined in mppi_f32*.cu / mppi_f64.cu)
 using MppiKernelFn = void (*)(const MppiParams);
 MppiKernelFn mppi_kernel_f32(int model_id, int block, int noise);
 MppiKernelFn mppi_kernel_f64(int model_id, int block, int noise);

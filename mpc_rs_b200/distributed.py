@@ -1,9 +1,11 @@
 """Host-side plumbing for the multi-GPU path: shard arithmetic and NCCL-id rendezvous.
 
 One process per GPU.  MPPI shards the K samples of a controller contiguously over the ranks and needs ONE small
-exchange per control step (done inside libmpc_b200 with ncclAllGather once a communicator is attached); batched
-UKF filters / closed-loop controllers shard without any exchange.  torch.distributed is only the rendezvous that
-carries the 128-byte ncclUniqueId from rank 0 to the others — any backend works (gloo on CPU in the tests).
+exchange per control step, done inside libmpc_b200 either by the rollout kernel itself over peer memory
+(attach_mppi_peers: every rank's final block stores its partial row into the peers' mailboxes over NVLink and
+combines the rows it receives — no collective call) or with one ncclAllGather (attach_mppi); batched UKF filters /
+closed-loop controllers shard without any exchange.  torch.distributed is only the rendezvous that carries the
+128-byte handles between the ranks — any backend works (gloo on CPU in the tests).
 """
 from __future__ import annotations
 
@@ -37,4 +39,22 @@ def attach_mppi(mppi, group=None):
     """Gives a sharded Mppi handle (rank/world_size set at construction) its NCCL communicator."""
     from .mppi import comm_unique_id
     mppi.attach_comm(exchange_unique_id(comm_unique_id, group))
+    return mppi
+
+
+def exchange_handles(mine: bytes, group=None):
+    """All-gathers one fixed-size byte string per rank; returns the list in rank order."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(dev)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)
+    return [bytes(o.cpu().numpy().tobytes()) for o in out]
+
+
+def attach_mppi_peers(mppi, group=None):
+    """Gives a sharded Mppi handle the peer-memory mailboxes of all ranks (fused in-kernel exchange)."""
+    mppi.attach_peers(exchange_handles(mppi.peer_handle(), group))
     return mppi

@@ -217,6 +217,27 @@ class Mppi:
         A.check(A.lib().mpcb_mppi_attach_comm(self._h, unique_id))
 
 
+PEER_HANDLE_BYTES = 128
+
+
+def _peer_handle(self) -> bytes:
+    """128-byte handle of this rank's exchange mailbox (mpcb_mppi_peer_handle)."""
+    buf = C.create_string_buffer(PEER_HANDLE_BYTES)
+    A.check(A.lib().mpcb_mppi_peer_handle(self._h, buf))
+    return buf.raw
+
+
+def _attach_peers(self, handles):
+    """handles: the peer_handle() of every rank, in rank order -> fused peer-memory exchange inside the kernel."""
+    blob = b"".join(handles)
+    assert len(blob) == PEER_HANDLE_BYTES * self.cfg.world_size
+    A.check(A.lib().mpcb_mppi_attach_peers(self._h, blob))
+
+
+Mppi.peer_handle = _peer_handle
+Mppi.attach_peers = _attach_peers
+
+
 def comm_unique_id() -> bytes:
     buf = C.create_string_buffer(128)
     A.check(A.lib().mpcb_comm_unique_id(buf))

@@ -198,6 +198,69 @@ def test_sharded_partials_combine_on_one_gpu(gpu_required):
     A.lib().mpcb_device_free(0, d_eps)
 
 
+def test_peer_exchange_on_one_gpu(gpu_required):
+    """The fused in-kernel exchange (mpcb_mppi_attach_peers): G sharded handles of ONE process on device 0, each on
+    its own stream.  Every handle's final block stores its row into all mailboxes, waits for the others and
+    combines — so all G handles must end with the single-handle result, over several steps (slot/flag reuse)."""
+    import ctypes as C
+    model, oid, H, dt, lam, sig, lim = CASES["NL_h100"]
+    K, G = 20000, 3
+    rng = np.random.default_rng(31)
+    u_n = rng.uniform(-2, 2, H)
+    d = [C.c_void_p() for _ in range(2 + G)]
+    for q, n in zip(d, [32, 8 * H] + [8 * H] * G):
+        A.check(A.lib().mpcb_device_alloc(0, n, C.byref(q)))
+    A.check(A.lib().mpcb_device_upload(0, d[0], X0.ctypes.data_as(C.c_void_p), 32))
+    A.check(A.lib().mpcb_device_upload(0, d[1], u_n.ctypes.data_as(C.c_void_p), 8 * H))
+    for prec, tol in (("f64", 1e-12), ("f32", 2e-6)):
+        hs = [Mppi(H, K, model=model, lam=lam, std_dev=sig, limit=lim, precision=prec, dt=dt, rank=r, world_size=G, seed=5)
+              for r in range(G)]
+        handles = [h.peer_handle() for h in hs]
+        for h in hs:
+            h.attach_peers(handles)
+        with Mppi(H, K, model=model, lam=lam, std_dev=sig, limit=lim, precision=prec, dt=dt, seed=5) as one:
+            for step in range(4):
+                u_one = one.compute(X0, u_n)
+                for r, h in enumerate(hs):  # asynchronous: the kernels of the G handles wait for each other
+                    h.compute_device(d[0].value, d[1].value, d[2 + r].value)
+                for r, h in enumerate(hs):
+                    h.sync()
+                    info = h.last_info()[0]
+                    assert info["status"] == 0 and info["n_finite"] == K
+                    assert info["argmax"] == one.last_call_info()[0]["argmax"]
+                    out = np.empty(H)
+                    A.check(A.lib().mpcb_device_download(0, out.ctypes.data_as(C.c_void_p), d[2 + r], 8 * H))
+                    assert rel_err(out, u_one) < tol, (prec, step, r)
+                    if r:
+                        assert np.array_equal(out, first), "ranks must agree bitwise"
+                    first = out
+        for h in hs:
+            h.close()
+    for q in d:
+        A.lib().mpcb_device_free(0, q)
+
+
+def test_launch_shapes(gpu_required):
+    """Work split (mppi_kernel.cuh header): sample counts around the one-block-per-SM boundary, block sizes 128/256/512,
+    ragged last warps, multi-batch ranges, many controllers — replay parity against the oracle for each."""
+    model, oid, H, dt, lam, sig, lim = CASES["NL_shipped"]
+    p = O.model_defaults(oid, dt=dt)
+    rng = np.random.default_rng(41)
+    for K in (1, 31, 33, 4097, 148 * 128 - 5, 148 * 256 + 77, 148 * 512 - 1, 148 * 512 + 1, 300001):
+        eps = sig * rng.standard_normal((K, H))
+        u_n = rng.uniform(-1, 1, H)
+        st, u_o, io, _ = O.mppi_compute(oid, p, K, H, lam, sig, lim[0], lim[1], X0, u_n, eps)
+        assert st == 0
+        for prec, tol in (("f64", 1e-9), ("f32", 1e-5)):
+            with Mppi(H, K, model=model, lam=lam, std_dev=sig, limit=lim, precision=prec, dt=dt) as m:
+                u_g = m.compute_replay(X0, u_n, eps)
+                assert m.info[0]["argmax"] == io["argmax"], (K, prec)
+                assert m.info[0]["n_finite"] == io["n_finite"] == K
+                assert rel_err(u_g, u_o) < tol, (K, prec, rel_err(u_g, u_o))
+                # sum_k exp((c_k - max)/lambda): FP32 rollout costs carry ~1e-5 absolute error, lambda = 0.5
+                assert abs(m.info[0]["sum"] - io["sum"]) <= (1e-9 if prec == "f64" else 1e-4) * io["sum"]
+
+
 def test_golden_fixtures_gpu(gpu_required):
     """The CUDA path against the committed golden vectors (tests/golden, made from the oracle by make_golden.py)."""
     import os

@@ -29,8 +29,22 @@ ts = buf[:n].astype(np.int64)
 t0 = ts[:, 0].min()
 rel = np.where(ts > 0, ts - t0, -1)
 print(f"K={K} H={H} blocks={n}")
-names = ["start", "rollouts done", "ticket1", "group merged", "ticket2", "final done"]
+names = ["start", "rollouts done", "ticket1", "group merged | final: headers done", "ticket2 | final: columns done", "final done"]
 for i, nm in enumerate(names):
     col = rel[:, i][rel[:, i] >= 0]
     if len(col):
-        print(f"  {nm:14s} n={len(col):4d}  min {col.min()/1e3:7.2f} us  median {np.median(col)/1e3:7.2f} us  max {col.max()/1e3:7.2f} us")
+        print(f"  {nm:38s} n={len(col):4d}  min {col.min()/1e3:7.2f} us  median {np.median(col)/1e3:7.2f} us  max {col.max()/1e3:7.2f} us")
+
+# blocks per SM and when each SM's last block finished its rollouts
+smid = ts[:, 6] - 1
+if (smid >= 0).all():
+    per_sm = {}
+    for b in range(n):
+        per_sm.setdefault(int(smid[b]), []).append(rel[b, 1] / 1e3)
+    by_load = {}
+    for sm, v in per_sm.items():
+        by_load.setdefault(len(v), []).append(max(v))
+    print(f"  SMs used: {len(per_sm)}")
+    for load in sorted(by_load):
+        v = by_load[load]
+        print(f"  {len(v):4d} SMs hold {load} blocks: last rollout done min {min(v):6.2f} median {np.median(v):6.2f} max {max(v):6.2f} us")
