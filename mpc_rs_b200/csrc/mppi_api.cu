@@ -19,6 +19,8 @@ struct mpcb_mppi {
     int H = 0, C = 0, PL = 0;
     int block = 0, chunks = 0, group_size = 0, groups = 0;
     int Hp = 8, lgHp = 3;
+    int mergers = 0;        // blocks sharing the final merge (0: last arriver merges alone)
+    unsigned int seq = 0;   // launches so far (arrival counters are monotonic)
     long long W = 0;  // warps of 32 samples in K_local
     size_t smem = 0;
     ModelConsts mc;
@@ -52,7 +54,7 @@ struct mpcb_mppi {
     // NCCL
     void* comm = nullptr;
     // fused peer exchange: own mailbox + flags, the peers' mappings, device tables of both
-    void* d_mailbox = nullptr;  // [flags: 2*G*C u32, padded][mailbox: 2*G*C*PL doubles]
+    void* d_mailbox = nullptr;  // [flags: 2*G*C*kMaxMergers u32, padded][mailbox: 2*G*C*PL doubles]
     size_t mailbox_bytes = 0, mailbox_flag_bytes = 0;
     void* peer_base[kMergeFan] = {};
     bool peer_ipc[kMergeFan] = {};
@@ -157,19 +159,39 @@ mpcb_status pick_kernels(mpcb_mppi* h) {
     }
     if (chunks > (long long)kMergeFan * kMergeFan) chunks = (long long)kMergeFan * kMergeFan;
     h->chunks = (int)chunks;
-    // merge tree: one level while the last block can take the rows in <= 3 load batches per thread
-    // (its threads split the rows nq ways, nq = BLOCK / Hp), else two levels with fan-in ~ sqrt(rows)
-    int nq = block >> h->lgHp;
-    if (nq < 1) nq = 1;
-    if (nq > 16) nq = 16;
-    if (h->chunks <= kMergeFan && h->chunks <= 3 * kMergeBatch * nq) {
-        h->group_size = h->chunks;
-        h->groups = 1;
-    } else {
-        int gs = (int)ceil(sqrt((double)h->chunks));
-        if (gs > kMergeFan) gs = kMergeFan;
-        h->group_size = gs;
-        h->groups = (h->chunks + gs - 1) / gs;
+    // designated mergers (first blocks of a controller wait for the arrival counters) only when the whole launch
+    // is resident at once; the final merge is then split column-wise over up to kMaxMergers of them
+    {
+        int occ = 0;
+        MPCB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)h->k_noise[NOISE_GENERATE], block, h->smem));
+        const bool resident = ((long long)h->C * h->chunks <= (long long)occ * h->num_sms) && !getenv("MPCB_MPPI_NO_SPIN");
+        const int ncol2 = (h->H + 3) / 2;
+        int nm = (ncol2 - 1) / 3;  // at least three column pairs per merger
+        if (nm > kMaxMergers) nm = kMaxMergers;
+        if (nm > h->chunks) nm = h->chunks;
+        if (nm < 1) nm = 1;
+        h->mergers = resident ? nm : 0;
+    }
+    // merge tree: one level while one merger block can take its column slice of the rows in <= 2 load batches per
+    // thread (its threads split the rows nq ways), else two levels with fan-in ~ sqrt(rows)
+    {
+        const int nm = h->mergers > 0 ? h->mergers : 1;
+        const int ncol2 = (h->H + 3) / 2;
+        const int npl = 1 + (ncol2 - 1 + nm - 1) / nm;
+        int Hpm = 2;
+        while (Hpm < npl) Hpm <<= 1;
+        int nq = block / Hpm;
+        if (nq < 1) nq = 1;
+        if (nq > kMergeMaxPart) nq = kMergeMaxPart;
+        if (h->chunks <= kMergeFan && h->chunks <= 2 * kMergeBatch * nq) {
+            h->group_size = h->chunks;
+            h->groups = 1;
+        } else {
+            int gs = (int)ceil(sqrt((double)h->chunks));
+            if (gs > kMergeFan) gs = kMergeFan;
+            h->group_size = gs;
+            h->groups = (h->chunks + gs - 1) / gs;
+        }
     }
     return MPCB_OK;
 }
@@ -179,6 +201,8 @@ void fill_params(const mpcb_mppi* h, MppiParams* p) {
     p->H = h->H;
     p->Hp = h->Hp;
     p->lgHp = h->lgHp;
+    p->PL = h->PL;
+    p->mergers = h->mergers;
     p->W = h->W;
     p->C = h->C;
     p->chunks = h->chunks;
@@ -210,6 +234,8 @@ mpcb_status launch(mpcb_mppi* h, MppiParams& p) {
     const int noise = p.eps != nullptr ? NOISE_REPLAY : (p.eps_dump != nullptr ? NOISE_GENERATE_DUMP : NOISE_GENERATE);
     MppiKernelFn fn = h->k_noise[noise];
     const dim3 grid((unsigned)(h->C * h->chunks)), block((unsigned)h->block);
+    h->seq += 1;
+    p.seq = h->seq;
     fn<<<grid, block, h->smem, h->stream>>>(p);
     MPCB_CUDA_TRY(cudaGetLastError());
     h->launches += 1;
@@ -250,13 +276,16 @@ mpcb_status stage_inputs(mpcb_mppi* h, MppiParams& p, const double* x, const dou
 // Single controller: the final block stores an epoch word after the results; spinning on it avoids the wake-up
 // latency of cudaStreamSynchronize.  After ~2 ms without completion (or for C > 1) fall back to the stream sync,
 // which also surfaces any launch/runtime error.
-mpcb_status finish_host(mpcb_mppi* h, double* u_out, mpcb_mppi_info* info, bool spin) {
+mpcb_status finish_host(mpcb_mppi* h, double* u_out, mpcb_mppi_info* info, bool spin, int words) {
     bool done = false;
     if (spin) {
+        // one completion word per merger block of the final merge
         volatile unsigned int* flag = h->h_done;
         const unsigned int want = h->epoch;
         for (long i = 0; i < 4000000; ++i) {
-            if (*flag == want) { done = true; break; }
+            bool all = true;
+            for (int w = 0; w < words; ++w) all = all && (flag[w] == want);
+            if (all) { done = true; break; }
             __builtin_ia32_pause();
         }
         __atomic_thread_fence(__ATOMIC_ACQUIRE);
@@ -315,7 +344,8 @@ mpcb_status compute_host(mpcb_mppi* h, const double* x, const double* u_in, cons
         st = exchange_and_combine(h);
         if (st != MPCB_OK) return st;
     }
-    return finish_host(h, u_out, info, spin);
+    const int words = (sharded && !peer) ? 1 : (h->mergers > 0 ? h->mergers : 1);
+    return finish_host(h, u_out, info, spin, words);
 }
 
 mpcb_status run_combine(mpcb_mppi* h, const double* rows, int G) {
@@ -405,7 +435,7 @@ mpcb_status mpcb_mppi_create(mpcb_mppi** out, const mpcb_mppi_cfg* cfg) {
     h->cfg = *cfg;
     h->H = cfg->horizon;
     h->C = cfg->controllers;
-    h->PL = kPartialHdr + h->H;
+    h->PL = mppi_partial_len(h->H);
     // contiguous shard of the global sample index
     const long long K = cfg->samples, G = cfg->world_size, r = cfg->rank;
     h->k_offset = K * r / G;
@@ -449,8 +479,8 @@ mpcb_status mpcb_mppi_create(mpcb_mppi** out, const mpcb_mppi_cfg* cfg) {
     TRY_OR_FAIL(cudaMalloc(&h->d_info, C * sizeof(mpcb_mppi_info)));
     TRY_OR_FAIL(cudaMemset(h->d_info, 0, C * sizeof(mpcb_mppi_info)));
     if (getenv("MPCB_DEBUG_TS")) {
-        TRY_OR_FAIL(cudaMalloc(&h->d_ts, C * (size_t)h->chunks * 8 * sizeof(unsigned long long)));
-        TRY_OR_FAIL(cudaMemset(h->d_ts, 0, C * (size_t)h->chunks * 8 * sizeof(unsigned long long)));
+        TRY_OR_FAIL(cudaMalloc(&h->d_ts, C * (size_t)h->chunks * 16 * sizeof(unsigned long long)));
+        TRY_OR_FAIL(cudaMemset(h->d_ts, 0, C * (size_t)h->chunks * 16 * sizeof(unsigned long long)));
     }
     if (cfg->keep_costs) TRY_OR_FAIL(cudaMalloc(&h->d_costs, C * (size_t)h->K_local * sizeof(double)));
     TRY_OR_FAIL(cudaHostAlloc(&h->h_in, C * (4 + H) * sizeof(double), cudaHostAllocDefault));
@@ -598,7 +628,7 @@ mpcb_status mpcb_mppi_last_info(mpcb_mppi* h, mpcb_mppi_info* info) {
     return MPCB_OK;
 }
 
-// Diagnostics (MPCB_DEBUG_TS=1 at create): %globaltimer stamps [blocks][8] of the last launch:
+// Diagnostics (MPCB_DEBUG_TS=1 at create): %globaltimer stamps [blocks][16] of the last launch:
 // 0 block start, 1 rollouts done, 2 ticket taken, 3 group merged, 4 second ticket, 5 final merge done.
 int64_t mpcb_mppi_debug_timeline(mpcb_mppi* h, unsigned long long* out, int64_t max_blocks) {
     if (!h || !h->d_ts || !out) return 0;
@@ -606,7 +636,7 @@ int64_t mpcb_mppi_debug_timeline(mpcb_mppi* h, unsigned long long* out, int64_t 
     cudaStreamSynchronize(h->stream);
     int64_t n = (int64_t)h->C * h->chunks;
     if (n > max_blocks) n = max_blocks;
-    cudaMemcpy(out, h->d_ts, (size_t)n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaMemcpy(out, h->d_ts, (size_t)n * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     return n;
 }
 
@@ -641,7 +671,7 @@ mpcb_status mpcb_mppi_combine(mpcb_mppi* h, const double* d_partials, int32_t n_
     h->epoch += 1;
     mpcb_status st = run_combine(h, d_partials, n_ranks);
     if (st != MPCB_OK) return st;
-    return finish_host(h, u_out, info, h->C == 1);
+    return finish_host(h, u_out, info, h->C == 1, 1);
 }
 
 mpcb_status mpcb_comm_unique_id(char id[128]) { return nccl_unique_id(id); }
@@ -660,7 +690,7 @@ namespace {
 mpcb_status ensure_mailbox(mpcb_mppi* h) {
     if (h->d_mailbox) return MPCB_OK;
     const size_t G = h->cfg.world_size, C = h->C;
-    h->mailbox_flag_bytes = ((2 * G * C * sizeof(unsigned int)) + 255) & ~(size_t)255;
+    h->mailbox_flag_bytes = ((2 * G * C * kMaxMergers * sizeof(unsigned int)) + 255) & ~(size_t)255;
     h->mailbox_bytes = h->mailbox_flag_bytes + 2 * G * C * (size_t)h->PL * sizeof(double);
     MPCB_CUDA_TRY(cudaMalloc(&h->d_mailbox, h->mailbox_bytes));
     MPCB_CUDA_TRY(cudaMemset(h->d_mailbox, 0, h->mailbox_bytes));

@@ -33,7 +33,7 @@
 
 namespace mpcb {
 
-constexpr int kPartialHdr = 4;   // m, sum_w, argmax (bits), n_finite (bits)
+constexpr int kPartialHdr = 4;   // m, argmax (bits), sum_w, n_finite (as double)
 constexpr int kMergeFan = 256;   // max rows merged by one block
 constexpr int kMaxWarps = 16;    // warps per block (BLOCK <= 512)
 // shared scratch (doubles): red_m[16] red_a[16] red_n[16] red_s[24] sc[kMergeFan]
@@ -44,8 +44,12 @@ enum MppiFinal { FINAL_NORMALISE = 0, FINAL_RANK_ROW = 1, FINAL_PEER_EXCHANGE = 
 
 struct MppiParams {
     int H;
-    int Hp;          // H rounded up to a power of two (>= 8)
+    int Hp;          // H rounded up to a power of two (>= 8): column index space of the weighted sums
     int lgHp;
+    int PL;          // doubles per partial row: kPartialHdr + H rounded up to even
+    int mergers;     // >= 1: every block of the launch is resident at once, the first `mergers` blocks of a controller
+                     // share the final merge column-wise and group leaders wait for their group; 0: last arriver merges
+    unsigned int seq;  // 1-based launch number of this handle: arrival counters are monotonic (seq * rows)
     int C;
     int chunks;      // blocks per controller (level-0 rows)
     int group_size;  // level-0 rows per group (<= kMergeFan)
@@ -91,12 +95,12 @@ constexpr long long kNoArg = 0x7fffffffffffffffll;
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
     return t;
 }
 #define MPCB_TS(slot)                                                                       \
     do {                                                                                    \
-        if (p.debug_ts != nullptr && threadIdx.x == 0) p.debug_ts[(size_t)blockIdx.x * 8 + (slot)] = globaltimer_ns(); \
+        if (p.debug_ts != nullptr && threadIdx.x == 0) p.debug_ts[(size_t)blockIdx.x * 16 + (slot)] = globaltimer_ns(); \
     } while (0)
 
 // gpu-scope release/acquire fence around the ticket atomics (cheaper than the sequentially consistent
@@ -104,6 +108,18 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_release_sys_u32(unsigned int* p, unsigned int v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// arrival: the barrier before it orders the block's row stores before thread 0's release (cumulativity), so no
+// block-wide fence is needed; acq_rel also makes it the acquire side of the last-arriver pattern
+__device__ __forceinline__ unsigned int atom_add_acq_rel_gpu_u32(unsigned int* p, unsigned int v) {
+    unsigned int old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p) {
     unsigned int v;
@@ -165,180 +181,227 @@ __device__ __forceinline__ bool all_zero_bits(const double (&w)[4]) {
              (unsigned long long)__double_as_longlong(w[2]) | (unsigned long long)__double_as_longlong(w[3])) << 1) == 0ull;
 }
 
-// Merges n_rows (<= kMergeFan) partial rows (row r at rows + r*row_stride) of one controller; the whole
-// block participates.  scratch: kScratchDoubles doubles, part: max(BLOCK, Hp) doubles of shared memory.
+// Row layout (PL doubles, PL even): [0] m = max finite c_k (or -inf), [1] argmax (bits), [2] sum_w, [3] n_finite
+// (as a double: exact below 2^53), [4 .. 4+H) sum_w * v[t], optional zero pad.  Seen as column PAIRS (16 bytes):
+// pair -1 = (m, argmax), pair 0 = (sum_w, n_finite), pair j >= 1 = (U[2j-2], U[2j-1]).
+//
+// Merges n_rows (<= kMergeFan) partial rows (row r at rows + r*row_stride) of one controller; the whole block
+// participates.  scratch: kScratchDoubles doubles, part: mppi_part_doubles of shared memory.
 //   final_mode FINAL_RANK_ROW : the merged, un-normalised row is written to out_row
 //   final_mode FINAL_NORMALISE: u_out = sum_w*v / sum_w, info, status                      (src/mppi.rs:76-91)
-// Columns are split over (t, q): thread item (t, q) sums the rows of partition q for column t, with the loads of
-// up to kMergeBatch rows in flight at once; the partitions are then added in a fixed order, so the result does
-// not depend on timing.  The first batch of column loads is issued before the header reductions.
-constexpr int kMergeBatch = 16;
+// The merge is COLUMN-SPLIT over nm merger blocks: merger mi owns the pairs [1 + mi*cp, 1 + (mi+1)*cp) and every
+// merger also sums pair 0 (it needs sum_w to normalise) and reduces the (m, argmax) headers.  What bounds a merge
+// is the bytes one SM can pull from L2 (~32 B/clk): 148 rows of H = 100 are 122 KB — 2 us through one SM, a few
+// hundred ns through 8-16 of them.  Merger 0 writes info/status (it owns u[0], the element src/mppi.rs:87 checks).
+// Thread item (jl, q) sums the rows of partition q for local pair jl (jl = 0: pair 0); every global load of the
+// merge is issued before anything is consumed; the partitions are then added in a fixed order, so the result does
+// not depend on timing.
+constexpr int kMergeBatch = 8;    // 16-byte loads in flight per thread (register budget: the kernel is capped at 128)
+constexpr int kMergeMaxPart = 32;  // row partitions per column pair
+constexpr int kMaxMergers = 16;
+
+struct MergeOut {
+    double* u_out;
+    double* u_out_host;
+    mpcb_mppi_info* info;
+    mpcb_mppi_info* info_host;
+    double* out_row;
+    unsigned int* done_host;  // [nm] completion words (mapped host memory) or nullptr
+    unsigned int epoch;
+    int forced_status;
+    unsigned long long* ts;
+};
 
 template <int BLOCK>
-__device__ void mppi_merge_rows(const double* rows, long long row_stride, int n_rows, int H, int Hp, int lgHp,
-                                double lambda, int final_mode, double* u_out, double* u_out_host, mpcb_mppi_info* info,
-                                mpcb_mppi_info* info_host, double* out_row, double* scratch, double* part,
-                                unsigned int* done_host = nullptr, unsigned int epoch = 0,
-                                int forced_status = MPCB_OK, unsigned long long* ts = nullptr) {
+__device__ __noinline__ void mppi_merge_rows(const double* rows, long long row_stride, int n_rows, int H, int mi, int nm,
+                                             double inv_lambda, int final_mode, const MergeOut& o, double* scratch,
+                                             double* part) {
     constexpr int NW = BLOCK / 32;
     constexpr int RPT = (kMergeFan + BLOCK - 1) / BLOCK;  // header rows per thread
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     double* red_m = scratch;                        // [16]
     long long* red_a = (long long*)(scratch + 16);  // [16]
-    long long* red_n = (long long*)(scratch + 32);  // [16]
-    double* red_s = scratch + 48;                   // [24]
     double* sc = scratch + 72;                      // [kMergeFan] per-row scale
-    __shared__ int s_status;
+    double2* part2 = reinterpret_cast<double2*>(part);
+    unsigned long long* ts = o.ts;
 
-    // (t, q) item of this thread for the first column pass
-    int nq = BLOCK >> lgHp;  // row partitions (power of two)
+    const int ncol2 = (H + 3) >> 1;             // pairs 0 .. ncol2-1
+    const int cp = (ncol2 - 1 + nm - 1) / nm;   // pairs owned per merger
+    const int p_lo = 1 + mi * cp;
+    int p_hi = p_lo + cp;
+    if (p_hi > ncol2) p_hi = ncol2;
+    const int npl = 1 + (p_hi > p_lo ? p_hi - p_lo : 0);  // local pairs: pair 0 + the owned ones
+    int Hpm = 2, lgHpm = 1;
+    while (Hpm < npl) { Hpm <<= 1; ++lgHpm; }
+    int nq = BLOCK >> lgHpm;  // row partitions (power of two)
     if (nq < 1) nq = 1;
-    if (nq > 16) nq = 16;
+    if (nq > kMergeMaxPart) nq = kMergeMaxPart;
     const int rq = (n_rows + nq - 1) / nq;  // rows per partition
-    const int items = Hp * nq;
+    const int items = Hpm * nq;
+    if (ts != nullptr && tid == 0) ts[7] = globaltimer_ns();
 
-    // ---- issue every load of the first pass: row headers + the first kMergeBatch rows of item tid ----
-    double hm[RPT], hs[RPT];
-    long long ha[RPT], hn[RPT];
+    // ---- issue every load of the first pass ----
+    double2 hd[RPT];
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
         const int r = tid + i * BLOCK;
-        hm[i] = -CUDART_INF; hs[i] = 0.0; ha[i] = -1; hn[i] = 0;
-        if (r < n_rows) {
-            const double* row = rows + (long long)r * row_stride;
-            hm[i] = __ldcg(row + 0);
-            hs[i] = __ldcg(row + 1);
-            ha[i] = double_as_ll(__ldcg(row + 2));
-            hn[i] = double_as_ll(__ldcg(row + 3));
-        }
+        hd[i] = make_double2(-CUDART_INF, ll_as_double(-1ll));
+        if (r < n_rows) hd[i] = __ldcg(reinterpret_cast<const double2*>(rows + (long long)r * row_stride));
     }
-    double v0[kMergeBatch];
+    double2 v0[kMergeBatch];
     {
-        const int t = tid & (Hp - 1), q = tid >> lgHp;
+        const int jl = tid & (Hpm - 1), q = tid >> lgHpm;
+        const int pair = (jl == 0) ? 0 : p_lo + jl - 1;
         const int r0 = q * rq;
-        const double* col = rows + kPartialHdr + t + (long long)r0 * row_stride;
-        const bool live = tid < items && t < H;
+        const double2* col = reinterpret_cast<const double2*>(rows + 2 + 2 * pair + (long long)r0 * row_stride);
+        const bool live = tid < items && jl < npl;
 #pragma unroll
         for (int i = 0; i < kMergeBatch; ++i)
-            v0[i] = (live && i < rq && r0 + i < n_rows) ? __ldcg(col + (long long)i * row_stride) : 0.0;
+            v0[i] = (live && i < rq && r0 + i < n_rows) ? __ldcg(col + (long long)i * (row_stride >> 1)) : make_double2(0.0, 0.0);
     }
+    if (ts != nullptr && tid == 0) ts[8] = globaltimer_ns();
 
-    // ---- max / argmax / finite count over the headers ----
+    // ---- max / argmax over the headers (lowest sample index on ties) ----
     double m = -CUDART_INF;
-    long long a = kNoArg, n = 0;
+    long long a = kNoArg;
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
-        n += hn[i];
-        if (ha[i] >= 0 && (hm[i] > m || (hm[i] == m && ha[i] < a))) { m = hm[i]; a = ha[i]; }
+        const long long ai = double_as_ll(hd[i].y);
+        if (ai >= 0 && (hd[i].x > m || (hd[i].x == m && ai < a))) { m = hd[i].x; a = ai; }
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const double om = shfl_down_f64(m, off);
-        const long long oa = shfl_down_i64(a, off);
-        n += shfl_down_i64(n, off);
-        if (om > m || (om == m && oa < a)) { m = om; a = oa; }
-    }
-    if (lane == 0) { red_m[wid] = m; red_a[wid] = a; red_n[wid] = n; }
+    // equal maxima in different rows: the row order is not the sample order after a two-level merge, so ties are
+    // resolved on the sample index itself — first the max value, then the min index among its holders
+    auto reduce_max_minidx = [&](double& mv, long long& av, bool has) {
+        double wm;
+        long long wa;
+        int dummy;
+        warp_argmax(mv, av, has && av != kNoArg, &wm, &wa, &dummy);
+        const bool holds = has && av != kNoArg && mv == wm;
+        const unsigned int ahi = holds ? (unsigned int)((unsigned long long)av >> 32) : 0xffffffffu;
+        const unsigned int mh = __reduce_min_sync(0xffffffffu, ahi);
+        const unsigned int alo = (holds && ahi == mh) ? (unsigned int)av : 0xffffffffu;
+        const unsigned int ml = __reduce_min_sync(0xffffffffu, alo);
+        mv = wm;
+        av = (wa == kNoArg) ? kNoArg : (long long)(((unsigned long long)mh << 32) | ml);
+    };
+    reduce_max_minidx(m, a, true);
+    if (lane == 0) { red_m[wid] = m; red_a[wid] = a; }
     __syncthreads();
-    m = red_m[0]; a = red_a[0]; n = red_n[0];
-#pragma unroll
-    for (int w = 1; w < NW; ++w) {
-        const double om = red_m[w];
-        const long long oa = red_a[w];
-        n += red_n[w];
-        if (om > m || (om == m && oa < a)) { m = om; a = oa; }
-    }
+    if (ts != nullptr && tid == 0) ts[9] = globaltimer_ns();
+    m = (lane < NW) ? red_m[lane] : -CUDART_INF;
+    a = (lane < NW) ? red_a[lane] : kNoArg;
+    reduce_max_minidx(m, a, lane < NW);
     const bool any = (a != kNoArg);
-    // ---- per-row scale exp((m_r - m)/lambda) and the merged sum of weights ----
-    double s = 0.0;
+    // ---- per-row scale exp((m_r - m)/lambda); rows that saw no finite cost get 0 (0 * NaN keeps their poison) ----
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
         const int r = tid + i * BLOCK;
-        if (r < n_rows) {
-            const bool empty = (hm[i] == -CUDART_INF);  // the row saw no finite cost
-            const double scale = empty ? 0.0 : exp((hm[i] - m) / lambda);
-            // an empty row's sum_w is 0, or NaN/inf when it saw NaN/+inf costs: keep that poison (f64 semantics)
-            s += empty ? hs[i] : scale * hs[i];
-            sc[r] = scale;
-        }
+        if (r < n_rows) sc[r] = (hd[i].x == -CUDART_INF) ? 0.0 : exp((hd[i].x - m) * inv_lambda);
     }
-    s = warp_sum_f64(s);
-    if (lane == 0) red_s[wid] = s;
-    if (tid == 0) s_status = MPCB_OK;
     __syncthreads();
-    s = red_s[0];
-#pragma unroll
-    for (int w = 1; w < NW; ++w) s += red_s[w];
     if (ts != nullptr && tid == 0) ts[3] = globaltimer_ns();
-    // ---- merged weighted control sums: partition sums, then the partitions in order ----
+    // ---- column pairs: partition sums ----
     for (int item = tid; item < items; item += BLOCK) {
-        const int t = item & (Hp - 1), q = item >> lgHp;
-        if (t >= H) continue;
+        const int jl = item & (Hpm - 1), q = item >> lgHpm;
+        if (jl >= npl) continue;
+        const int pair = (jl == 0) ? 0 : p_lo + jl - 1;
         const int r0 = q * rq;
         int r1 = r0 + rq;
         if (r1 > n_rows) r1 = n_rows;
-        double acc = 0.0;
-        const double* col = rows + kPartialHdr + t;
+        double ax = 0.0, ay = 0.0;
+        const double2* col = reinterpret_cast<const double2*>(rows + 2 + 2 * pair);
         for (int rb = r0; rb < r1; rb += kMergeBatch) {
-            double v[kMergeBatch];
+            double2 v[kMergeBatch];
             if (item == tid && rb == r0) {
 #pragma unroll
                 for (int i = 0; i < kMergeBatch; ++i) v[i] = v0[i];
             } else {
 #pragma unroll
                 for (int i = 0; i < kMergeBatch; ++i)
-                    v[i] = (rb + i < r1) ? __ldcg(col + (long long)(rb + i) * row_stride) : 0.0;
+                    v[i] = (rb + i < r1) ? __ldcg(col + (long long)(rb + i) * (row_stride >> 1)) : make_double2(0.0, 0.0);
             }
 #pragma unroll
-            for (int i = 0; i < kMergeBatch; ++i)
-                if (rb + i < r1) acc += sc[rb + i] * v[i];  // scale 0 * NaN = NaN keeps the reference's poisoning
+            for (int i = 0; i < kMergeBatch; ++i) {
+                if (rb + i < r1) {
+                    const double f = sc[rb + i];
+                    ax += f * v[i].x;                       // scale 0 * NaN = NaN keeps the reference's poisoning
+                    ay += (pair == 0) ? v[i].y : f * v[i].y;  // pair 0 = (sum_w, n_finite): the count is not scaled
+                }
+            }
         }
-        part[q * Hp + t] = acc;
+        part2[q * Hpm + jl] = make_double2(ax, ay);
     }
+    if (ts != nullptr && tid == 0) ts[10] = globaltimer_ns();
     __syncthreads();
     if (ts != nullptr && tid == 0) ts[4] = globaltimer_ns();
-    for (int t = tid; t < H; t += BLOCK) {
-        double acc = part[t];
-        for (int q = 1; q < nq; ++q) acc += part[q * Hp + t];
+    // ---- the nq (<= 32) partition sums of a pair: one warp per pair, fixed xor tree over the lanes ----
+    double2* tot2 = part2 + nq * Hpm;  // [npl]
+    for (int jl = wid; jl < npl; jl += NW) {
+        double2 t0 = (lane < nq) ? part2[lane * Hpm + jl] : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            t0.x += __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(t0.x), off),
+                                     __shfl_xor_sync(0xffffffffu, __double2loint(t0.x), off));
+            t0.y += __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(t0.y), off),
+                                     __shfl_xor_sync(0xffffffffu, __double2loint(t0.y), off));
+        }
+        if (lane == 0) tot2[jl] = t0;
+    }
+    __shared__ int s_status;
+    __syncthreads();
+    const double s = tot2[0].x, nf = tot2[0].y;  // pair 0: sum_w, n_finite
+    if (tid == 0)
+        s_status = (o.forced_status != MPCB_OK) ? o.forced_status : (!any ? MPCB_NO_FINITE_COST : (s == 0.0 ? MPCB_SUM_ZERO : MPCB_OK));
+    __syncthreads();
+    for (int jl = tid; jl < npl; jl += BLOCK) {
+        const double ax = tot2[jl].x, ay = tot2[jl].y;
+        const int pair = (jl == 0) ? 0 : p_lo + jl - 1;
         if (final_mode == FINAL_RANK_ROW) {
-            out_row[kPartialHdr + t] = acc;
-        } else {
-            const double uo = any ? acc / s : 0.0;
-            if (t == 0) {
-                int st = MPCB_OK;
-                if (forced_status != MPCB_OK) st = forced_status;
-                else if (!any) st = MPCB_NO_FINITE_COST;       // src/mppi.rs:69
-                else if (s == 0.0) st = MPCB_SUM_ZERO;          // :76-78
-                else if (!finite_f64(uo)) st = MPCB_U_INVALID;  // :87-89 (element 0 only)
-                s_status = st;
+            if (pair == 0) {
+                if (mi == 0) {
+                    o.out_row[0] = any ? m : -CUDART_INF;
+                    o.out_row[1] = ll_as_double(any ? a : -1ll);
+                    o.out_row[2] = ax;
+                    o.out_row[3] = ay;
+                }
+            } else {
+                o.out_row[2 + 2 * pair] = ax;
+                o.out_row[3 + 2 * pair] = ay;  // for odd H the last pair's second slot is the row's zero pad
             }
-            u_out[t] = uo;
-            if (u_out_host) u_out_host[t] = uo;
+        } else if (pair > 0) {
+            const int t0 = 2 * pair - 2;
+            const double u0 = any ? ax / s : 0.0;
+            const double u1 = any ? ay / s : 0.0;
+            // src/mppi.rs:69 no finite cost, :76-78 sum is zero, :87-89 u[0] not finite (element 0 only)
+            if (t0 == 0 && s_status == MPCB_OK && !finite_f64(u0)) s_status = MPCB_U_INVALID;
+            o.u_out[t0] = u0;
+            if (o.u_out_host) o.u_out_host[t0] = u0;
+            if (t0 + 1 < H) {
+                o.u_out[t0 + 1] = u1;
+                if (o.u_out_host) o.u_out_host[t0 + 1] = u1;
+            }
         }
     }
-    if (done_host) __threadfence_system();  // every writer orders its host stores before the completion word
+    if (final_mode == FINAL_RANK_ROW) return;
+    if (ts != nullptr && tid == 0) ts[11] = globaltimer_ns();
+    if (o.done_host) __threadfence_system();  // every writer orders its host stores before the completion word
     __syncthreads();
     if (tid == 0) {
-        if (final_mode == FINAL_RANK_ROW) {
-            out_row[0] = any ? m : -CUDART_INF;
-            out_row[1] = s;
-            out_row[2] = ll_as_double(any ? a : -1ll);
-            out_row[3] = ll_as_double(n);
-        } else {
+        if (mi == 0) {
             mpcb_mppi_info out;
             out.status = s_status;
             out.reserved = 0;
             out.argmax = any ? a : -1ll;
             out.max = any ? m : 0.0;
             out.sum = s;
-            out.n_finite = n;
-            *info = out;
-            if (info_host) *info_host = out;
-            if (done_host) {
-                // results first, then the completion word the host spins on (system-scope release)
-                __threadfence_system();
-                *reinterpret_cast<volatile unsigned int*>(done_host) = epoch;
-            }
+            out.n_finite = (long long)nf;
+            *o.info = out;
+            if (o.info_host) *o.info_host = out;
+        }
+        if (o.done_host) {
+            // results first, then this merger's completion word the host spins on (system-scope release)
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned int*>(o.done_host + mi) = o.epoch;
         }
     }
 }
@@ -361,11 +424,25 @@ __host__ __device__ inline int mppi_pow2_horizon(int H, int* lg) {
     return hp;
 }
 
+__host__ __device__ inline int mppi_pow2_pairs(int H, int* lg) {
+    int hp = 4, l = 2;
+    while (hp < ((H + 3) >> 1)) { hp <<= 1; ++l; }
+    if (lg) *lg = l;
+    return hp;
+}
+__host__ __device__ inline int mppi_partial_len(int H) { return (kPartialHdr + H + 1) & ~1; }
+// doubles of the partition-sum area: the merge keeps double2 per (pair, partition), the weighted sums one real
+__host__ __device__ inline size_t mppi_part_doubles(int H, int block) {
+    const int Hp = mppi_pow2_horizon(H, nullptr), Hp2 = mppi_pow2_pairs(H, nullptr);
+    size_t a = (size_t)(block > Hp ? block : Hp);
+    size_t b = 2 * ((size_t)(block > Hp2 ? block : Hp2) + Hp2);  // partition sums + totals, double2 each
+    return a > b ? a : b;
+}
+
 // Shared-memory bytes of one block.
 template <typename real>
 __host__ __device__ inline size_t mppi_smem_bytes(int H, int block) {
-    const int Hp = mppi_pow2_horizon(H, nullptr);
-    const size_t npart = (size_t)(block > Hp ? block : Hp);
+    const size_t npart = mppi_part_doubles(H, block);
     size_t dbl = ((size_t)H + kScratchDoubles + npart + 3) & ~(size_t)3;  // U_run + scratch + partition sums (32 B)
     size_t rl = (size_t)2 * ((H + 3) & ~3) + block + (size_t)H * (block + 4);  // su, sui, w_s, v_s
     size_t bytes = dbl * sizeof(double) + rl * sizeof(real);
@@ -391,12 +468,12 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int H = p.H, Hp = p.Hp, lgHp = p.lgHp;
     const int H4a = (H + 3) & ~3;
-    double* U_run = reinterpret_cast<double*>(smem_raw);             // [H]
-    double* scratch = U_run + H;                                     // [kScratchDoubles]
-    double* part_d = scratch + kScratchDoubles;                      // [max(BLOCK, Hp)]
+    double* scratch = reinterpret_cast<double*>(smem_raw);           // [kScratchDoubles] (even)
+    double* part_d = scratch + kScratchDoubles;                      // [mppi_part_doubles] (even): 16-byte aligned
     real* part_r = reinterpret_cast<real*>(part_d);
-    const int ndbl = (H + kScratchDoubles + (BLOCK > Hp ? BLOCK : Hp) + 3) & ~3;
-    real* su = reinterpret_cast<real*>(U_run + ndbl);                // [H4a]  u_n (16-byte aligned rows from here on)
+    double* U_run = part_d + mppi_part_doubles(H, BLOCK);            // [H]
+    const int ndbl = (H + kScratchDoubles + (int)mppi_part_doubles(H, BLOCK) + 3) & ~3;
+    real* su = reinterpret_cast<real*>(scratch + ndbl);              // [H4a]  u_n (16-byte aligned rows from here on)
     real* sui = su + H4a;                                            // [H4a]  u_n * sigma^-2
     real* w_s = sui + H4a;                                           // [BLOCK]
     real* v_s = w_s + BLOCK;                                         // [H][LD]
@@ -409,7 +486,7 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
     if (p.debug_ts != nullptr && threadIdx.x == 0) {
         unsigned int smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        p.debug_ts[(size_t)blockIdx.x * 8 + 6] = smid + 1;
+        p.debug_ts[(size_t)blockIdx.x * 16 + 6] = smid + 1;
     }
     // ---- prologue: model constants, x0, u_n ----
     ModelT<real> model;
@@ -651,66 +728,116 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
     }
 
     MPCB_TS(1);
-    // ---- partial row of this block, then the ticket merge ----
-    const int PL = kPartialHdr + H;
+    // ---- partial row of this block, then the merge ----
+    // Arrival counters only ever grow (launch `seq` expects seq*rows arrivals), so nothing has to be reset and any
+    // number of blocks can wait on one counter.  With every block of the launch resident at once (p.mergers >= 1)
+    // the first block of a group merges the group and the first p.mergers blocks of the controller share the final
+    // merge column-wise — the same blocks, on the same SMs, every launch; otherwise (grids of several waves) the
+    // last block to arrive merges alone.
+    const int PL = p.PL;
+    const double inv_lambda_m = 1.0 / lambda;
     double* ctrl_rows = p.partial + (long long)c * (p.chunks + p.groups) * PL;
     double* my_row = ctrl_rows + (long long)chunk * PL;
     for (int t = tid; t < H; t += BLOCK) my_row[kPartialHdr + t] = U_run[t];
     if (tid == 0) {
         my_row[0] = m_run;
-        my_row[1] = S_run;
-        my_row[2] = ll_as_double(arg_run == kNoArg ? -1ll : arg_run);
-        my_row[3] = ll_as_double(nfin_run);
+        my_row[1] = ll_as_double(arg_run == kNoArg ? -1ll : arg_run);
+        my_row[2] = S_run;
+        my_row[3] = (double)nfin_run;
+        if (PL > kPartialHdr + H) my_row[kPartialHdr + H] = 0.0;
     }
-    __shared__ int s_last;
+    __shared__ int s_go;
     unsigned int* cnt = p.counters + (long long)c * (p.groups + 1);
     const int g = chunk / p.group_size;
     const int g_first = g * p.group_size;
     int g_rows = p.chunks - g_first;
     if (g_rows > p.group_size) g_rows = p.group_size;
+    unsigned long long* dbg = (p.debug_ts != nullptr) ? p.debug_ts + (size_t)blockIdx.x * 16 : nullptr;
+    const bool spin = p.mergers >= 1;
+    const int nm = spin ? p.mergers : 1;
 
-    fence_acq_rel_gpu();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(&cnt[g], 1u) == (unsigned int)(g_rows - 1));
-    __syncthreads();
-    MPCB_TS(2);
-    if (!s_last) return;
-    fence_acq_rel_gpu();
+    // publish this block's writes and count it in; in last-arriver mode returns whether it completed the count
+    auto arrive = [&](int slot, int expect) -> bool {
+        __syncthreads();
+        if (tid == 0) s_go = (atom_add_acq_rel_gpu_u32(&cnt[slot], 1u) + 1u == p.seq * (unsigned int)expect);
+        __syncthreads();
+        return s_go != 0;
+    };
+    // wait until `expect` blocks of this launch have arrived at `slot` (bounded, see MPCB_PEER_TIMEOUT)
+    auto await = [&](int slot, int expect) {
+        if (tid == 0) {
+            const unsigned int want = p.seq * (unsigned int)expect;
+            const unsigned long long t_start = globaltimer_ns();
+            while (ld_acquire_gpu_u32(&cnt[slot]) != want) {
+                if (globaltimer_ns() - t_start > 5000000000ull) break;
+            }
+        }
+        __syncthreads();  // thread 0's acquire + this barrier order every thread's (L2) loads after the arrivals
+    };
+
+    int mi = 0;  // which column slice of the final merge this block takes
     const double* final_rows = ctrl_rows;
     int final_n = p.chunks;
-    if (p.groups > 1) {
+    MergeOut none;
+    none.u_out = nullptr; none.u_out_host = nullptr; none.info = nullptr; none.info_host = nullptr; none.out_row = nullptr;
+    none.done_host = nullptr; none.epoch = 0u; none.forced_status = MPCB_OK; none.ts = nullptr;
+    if (p.groups == 1) {
+        const bool last = arrive(0, p.chunks);
+        MPCB_TS(2);
+        if (spin) {
+            if (chunk >= nm) return;
+            mi = chunk;
+            await(0, p.chunks);
+        } else {
+            if (!last) return;
+        }
+    } else {
         double* group_rows = ctrl_rows + (long long)p.chunks * PL;
-        mppi_merge_rows<BLOCK>(ctrl_rows + (long long)g_first * PL, PL, g_rows, H, Hp, lgHp, lambda, FINAL_RANK_ROW,
-                               nullptr, nullptr, nullptr, nullptr, group_rows + (long long)g * PL, scratch, part_d);
-        if (tid == 0) cnt[g] = 0u;
-        MPCB_TS(3);
-        fence_acq_rel_gpu();
-        __syncthreads();
-        if (tid == 0) s_last = (atomicAdd(&cnt[p.groups], 1u) == (unsigned int)(p.groups - 1));
-        __syncthreads();
+        const bool last = arrive(g, g_rows);
+        MPCB_TS(2);
+        const bool leader = spin ? (chunk == g_first) : last;
+        const bool merger = spin && chunk < nm;
+        if (!leader && !merger) return;
+        if (leader) {
+            if (spin) await(g, g_rows);
+            MergeOut go = none;
+            go.out_row = group_rows + (long long)g * PL;
+            mppi_merge_rows<BLOCK>(ctrl_rows + (long long)g_first * PL, PL, g_rows, H, 0, 1, inv_lambda_m, FINAL_RANK_ROW, go,
+                                   scratch, part_d);
+            if (tid == 0 && PL > kPartialHdr + H) go.out_row[kPartialHdr + H] = 0.0;
+            MPCB_TS(3);
+            const bool last2 = arrive(p.groups, p.groups);
+            if (!spin && !last2) return;
+        }
+        if (spin) {
+            if (!merger) return;
+            mi = chunk;
+            await(p.groups, p.groups);
+        }
         MPCB_TS(4);
-        if (!s_last) return;
-        fence_acq_rel_gpu();
         final_rows = group_rows;
         final_n = p.groups;
     }
-    // ---- final merge of this controller ----
-    double* u_out_c = p.u_out + (long long)c * H;
-    double* u_host_c = p.u_out_host ? p.u_out_host + (long long)c * H : nullptr;
-    mpcb_mppi_info* info_host_c = p.info_host ? p.info_host + c : nullptr;
-    const int last_cnt = (p.groups > 1) ? p.groups : 0;
+    // ---- final merge of this controller (this block's column slice mi of nm) ----
+    MergeOut fo = none;
+    fo.u_out = p.u_out + (long long)c * H;
+    fo.u_out_host = p.u_out_host ? p.u_out_host + (long long)c * H : nullptr;
+    fo.info = p.info + c;
+    fo.info_host = p.info_host ? p.info_host + c : nullptr;
+    fo.done_host = p.done_host;
+    fo.epoch = p.epoch;
     if (p.final_mode != FINAL_PEER_EXCHANGE) {
-        double* rank_row = p.rank_partial ? p.rank_partial + (long long)c * PL : nullptr;
-        mppi_merge_rows<BLOCK>(final_rows, PL, final_n, H, Hp, lgHp, lambda, p.final_mode, u_out_c, u_host_c, p.info + c,
-                               info_host_c, rank_row, scratch, part_d, p.done_host, p.epoch, MPCB_OK,
-                               (p.debug_ts != nullptr && p.groups == 1) ? p.debug_ts + (size_t)blockIdx.x * 8 : nullptr);
-        if (tid == 0) cnt[last_cnt] = 0u;  // ready for the next launch
+        fo.out_row = p.rank_partial ? p.rank_partial + (long long)c * PL : nullptr;
+        fo.ts = (p.groups == 1 && mi == 0) ? dbg : nullptr;
+        mppi_merge_rows<BLOCK>(final_rows, PL, final_n, H, mi, nm, inv_lambda_m, p.final_mode, fo, scratch, part_d);
+        if (p.final_mode == FINAL_RANK_ROW && mi == 0 && tid == 0 && PL > kPartialHdr + H) fo.out_row[kPartialHdr + H] = 0.0;
         MPCB_TS(5);
         return;
     }
-    // ---- cross-GPU exchange inside the kernel: this rank's merged row goes into every rank's
-    // mailbox slot [parity][rank][c] (peer stores over NVLink), then one flag per peer is released; the block
-    // then acquires the G flags of its own mailbox and combines the G rows exactly like the rows of one GPU.
+    // ---- cross-GPU exchange inside the kernel: merger mi puts its column slice of this rank's merged
+    // row into every rank's mailbox slot [parity][rank][c] (peer stores over NVLink) and releases its flag
+    // [parity][rank][c][mi] on every peer; it then acquires, for every rank, that rank's flag mi (its own slice)
+    // and flag 0 (the slice holding m, argmax, sum_w, n) and combines the G rows exactly like the rows of one GPU.
     // Slots alternate with the exchange epoch: a peer can only be one step ahead, so two slots never collide. ----
     {
         const int G = p.G;
@@ -718,34 +845,41 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
         const long long slot_self = ((long long)(par * G + p.rank) * p.C + c);
         double* own_box = p.peer_mbox[p.rank];
         double* my_slot = own_box + slot_self * PL;
-        mppi_merge_rows<BLOCK>(final_rows, PL, final_n, H, Hp, lgHp, lambda, FINAL_RANK_ROW, nullptr, nullptr, nullptr,
-                               nullptr, my_slot, scratch, part_d);
-        if (tid == 0) cnt[last_cnt] = 0u;
-        __syncthreads();  // the slot (header by thread 0, columns by the others) is complete in this GPU's memory
+        MergeOut ro = none;
+        ro.out_row = my_slot;
+        mppi_merge_rows<BLOCK>(final_rows, PL, final_n, H, mi, nm, inv_lambda_m, FINAL_RANK_ROW, ro, scratch, part_d);
+        // the doubles of the row this merger produced: its pairs, plus the 4 header doubles for merger 0
+        const int ncol2 = (H + 3) >> 1;
+        const int cp = (ncol2 - 1 + nm - 1) / nm;
+        int d_lo = 2 + 2 * (1 + mi * cp), d_hi = d_lo + 2 * cp;
+        if (d_hi > PL) d_hi = PL;
+        if (mi == 0) d_lo = 0;
+        if (mi == nm - 1 && tid == 0 && PL > kPartialHdr + H) my_slot[kPartialHdr + H] = 0.0;
+        __syncthreads();  // the slice is complete in this GPU's memory
         for (int r = 0; r < G; ++r) {
             if (r == p.rank) continue;
             double* dst = p.peer_mbox[r] + slot_self * PL;
-            for (int i = tid; i < PL; i += BLOCK) dst[i] = __ldcg(my_slot + i);
+            for (int i = d_lo + tid; i < d_hi; i += BLOCK) dst[i] = __ldcg(my_slot + i);
         }
         __threadfence_system();
         __syncthreads();
-        for (int r = tid; r < G; r += BLOCK) st_release_sys_u32(p.peer_flags[r] + slot_self, p.xepoch);
-        // wait for every rank's row of this step (bounded: a missing peer becomes MPCB_PEER_TIMEOUT, not a hang)
+        for (int r = tid; r < G; r += BLOCK) st_release_sys_u32(p.peer_flags[r] + slot_self * kMaxMergers + mi, p.xepoch);
+        // wait for every rank's slices of this step (bounded: a missing peer becomes MPCB_PEER_TIMEOUT, not a hang)
         __shared__ int s_timeout;
         if (tid == 0) s_timeout = 0;
         __syncthreads();
-        for (int r = tid; r < G; r += BLOCK) {
-            const unsigned int* f = p.peer_flags[p.rank] + ((long long)(par * G + r) * p.C + c);
+        for (int r = tid; r < 2 * G; r += BLOCK) {
+            const int src = r >> 1, which = (r & 1) ? mi : 0;
+            const unsigned int* f = p.peer_flags[p.rank] + ((long long)(par * G + src) * p.C + c) * kMaxMergers + which;
             const unsigned long long t_start = globaltimer_ns();
             while (ld_acquire_sys_u32(f) != p.xepoch) {
                 if (globaltimer_ns() - t_start > 20000000000ull) { s_timeout = 1; break; }
             }
         }
         __syncthreads();
-        const int forced = s_timeout ? MPCB_PEER_TIMEOUT : MPCB_OK;
-        mppi_merge_rows<BLOCK>(own_box + (long long)(par * G) * p.C * PL + (long long)c * PL, (long long)p.C * PL, G, H, Hp,
-                               lgHp, lambda, FINAL_NORMALISE, u_out_c, u_host_c, p.info + c, info_host_c, nullptr, scratch,
-                               part_d, p.done_host, p.epoch, forced);
+        fo.forced_status = s_timeout ? MPCB_PEER_TIMEOUT : MPCB_OK;
+        mppi_merge_rows<BLOCK>(own_box + (long long)(par * G) * p.C * PL + (long long)c * PL, (long long)p.C * PL, G, H, mi, nm,
+                               inv_lambda_m, FINAL_NORMALISE, fo, scratch, part_d);
         MPCB_TS(5);
     }
 }
@@ -766,14 +900,21 @@ struct MppiCombineParams {
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) mppi_combine_kernel(const MppiCombineParams p) {
     __shared__ double scratch[kScratchDoubles];
-    __shared__ double part[kMaxHorizon > BLOCK ? kMaxHorizon : BLOCK];
+    __shared__ __align__(16) double part[2 * ((kMaxHorizon > BLOCK ? kMaxHorizon : BLOCK) + kMaxHorizon)];
     const int c = blockIdx.x;
-    const int PL = kPartialHdr + p.H;
-    int lg;
-    const int Hp = mppi_pow2_horizon(p.H, &lg);
-    mppi_merge_rows<BLOCK>(p.rows + (long long)c * PL, (long long)p.C * PL, p.G, p.H, Hp, lg, p.lambda, FINAL_NORMALISE,
-                           p.u_out + (long long)c * p.H, p.u_out_host ? p.u_out_host + (long long)c * p.H : nullptr,
-                           p.info + c, p.info_host ? p.info_host + c : nullptr, nullptr, scratch, part, p.done_host, p.epoch);
+    const int PL = mppi_partial_len(p.H);
+    MergeOut o;
+    o.u_out = p.u_out + (long long)c * p.H;
+    o.u_out_host = p.u_out_host ? p.u_out_host + (long long)c * p.H : nullptr;
+    o.info = p.info + c;
+    o.info_host = p.info_host ? p.info_host + c : nullptr;
+    o.out_row = nullptr;
+    o.done_host = p.done_host;
+    o.epoch = p.epoch;
+    o.forced_status = MPCB_OK;
+    o.ts = nullptr;
+    mppi_merge_rows<BLOCK>(p.rows + (long long)c * PL, (long long)p.C * PL, p.G, p.H, 0, 1, 1.0 / p.lambda, FINAL_NORMALISE, o,
+                           scratch, part);
 }
 
 // kernel entry table (defined in mppi_f32*.cu / mppi_f64.cu)

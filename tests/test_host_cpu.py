@@ -126,18 +126,18 @@ def _free_port():
 
 
 def _partial_row(oid, p, H, lam, sig, lim, x, u_n, eps_shard, k_offset):
-    """The row one rank contributes: [max, sum_w, argmax, n_finite, sum_w*v[0..H)] (csrc/mppi_kernel.cuh)."""
+    """The row one rank contributes: [max, argmax, sum_w, n_finite, sum_w*v[0..H)] (csrc/mppi_kernel.cuh)."""
     K = eps_shard.shape[0]
     st, _, info, c = O.mppi_compute(oid, p, K, H, lam, sig, lim[0], lim[1], x, u_n, eps_shard, want_costs=True)
     v = np.clip(u_n[None, :] + eps_shard, lim[0], lim[1])
     w = np.exp((c - info["max"]) / lam)
-    return np.concatenate([[info["max"], w.sum(), float(info["argmax"] + k_offset), float(info["n_finite"])], w @ v])
+    return np.concatenate([[info["max"], float(info["argmax"] + k_offset), w.sum(), float(info["n_finite"])], w @ v])
 
 
 def _merge_rows(rows, lam):
     M = rows[:, 0].max()
     s = np.exp((rows[:, 0] - M) / lam)
-    return (s[:, None] * rows[:, 4:]).sum(0) / (s * rows[:, 1]).sum(), int(rows[np.argmax(rows[:, 0]), 2])
+    return (s[:, None] * rows[:, 4:]).sum(0) / (s * rows[:, 2]).sum(), int(rows[np.argmax(rows[:, 0]), 1])
 
 
 def _worker(rank, world, port, q):
@@ -148,6 +148,9 @@ def _worker(rank, world, port, q):
     try:
         # (1) the id rendezvous: rank 0's 128 bytes reach everyone
         uid = D.exchange_unique_id(lambda: bytes(range(128)))
+        # (1b) the peer-handle rendezvous: everyone ends with every rank's 128 bytes, in rank order
+        hs = D.exchange_handles(bytes([rank]) * 128)
+        assert hs == [bytes([r]) * 128 for r in range(world)]
         # (2) one sharded control step: each rank reduces its sample shard to one row, one all_gather, same merge
         oid, H, dt, lam, sig, lim, K = O.MODEL_NL, 8, 0.1, 0.5, 3.0, (-20.0, 20.0), 5001
         p = O.model_defaults(oid, dt=dt)

@@ -23,14 +23,17 @@ L.mpcb_device_upload(0, p, xu.ctypes.data_as(C.c_void_p), xu.nbytes)
 for _ in range(5):
     m.compute_device(p.value, p.value + 32, p.value + 32 + 8 * H)
 m.sync()
-buf = np.zeros((4096, 8), dtype=np.uint64)
+buf = np.zeros((4096, 16), dtype=np.uint64)
 n = L.mpcb_mppi_debug_timeline(m._h, buf.ctypes.data_as(C.c_void_p), 4096)
 ts = buf[:n].astype(np.int64)
 t0 = ts[:, 0].min()
 rel = np.where(ts > 0, ts - t0, -1)
 print(f"K={K} H={H} blocks={n}")
 names = ["start", "rollouts done", "ticket1", "group merged | final: headers done", "ticket2 | final: columns done", "final done"]
+names += ["", "m: entry", "m: loads issued", "m: after barrier 1 (warp argmax)", "m: tid0 accumulated", "m: outputs stored"]
 for i, nm in enumerate(names):
+    if not nm:
+        continue
     col = rel[:, i][rel[:, i] >= 0]
     if len(col):
         print(f"  {nm:38s} n={len(col):4d}  min {col.min()/1e3:7.2f} us  median {np.median(col)/1e3:7.2f} us  max {col.max()/1e3:7.2f} us")
