@@ -54,12 +54,16 @@ UNIT = "rollout-steps/s"
 
 
 def workload(n_gpus: int) -> dict:
+    transport = os.environ.get("MPCB_BENCH_TRANSPORT", "peer")
+    exchange = (f"one ncclAllGather of {H + 4} doubles per rank per step" if transport == "nccl" else
+                f"in-kernel exchange: each rank's final blocks store its {H + 4}-double partial row into the peers' mailboxes "
+                "over NVLink and combine the rows they receive (no collective call)")
     return {
         "workload": "BASELINE configs[1]: examples/mppi4-non-liner.rs MPPI, model NL, "
                     f"K={K_PER_GPU} samples/GPU x H={H}, DT={DT}, lambda={LAMBDA}, sigma={SIGMA}, limit=+-20",
         "samples_per_gpu": K_PER_GPU, "samples_total": K_PER_GPU * n_gpus, "horizon": H, "controllers": 1,
         "noise": "philox4x32-10 in-register (generate mode)", "precision": "f32 rollout, f64 accumulation/softmax",
-        "sharding": f"samples x{n_gpus}, one ncclAllGather of {H + 4} doubles per rank per step" if n_gpus > 1 else "none",
+        "sharding": f"samples x{n_gpus}, {exchange}" if n_gpus > 1 else "none",
         "l2": "flushed between timed steps (256 MiB write); inputs are O(H) bytes",
     }
 
@@ -228,9 +232,13 @@ def run_gpu(args):
     # ---- controller: global K = K_PER_GPU * world, this rank's shard = K_PER_GPU samples ----
     mppi = Mppi(H, K_PER_GPU * world, model=models.NL, lam=LAMBDA, std_dev=SIGMA, limit=LIMIT, precision="f32", dt=DT,
                 device=dev, rank=rank, world_size=world, seed=20240001)
+    transport = os.environ.get("MPCB_BENCH_TRANSPORT", "peer")  # "peer": fused in-kernel exchange; "nccl": ncclAllGather
     if world > 1:
-        from mpc_rs_b200.distributed import attach_mppi
-        attach_mppi(mppi)  # rank 0's ncclUniqueId -> everyone (torch.distributed broadcast), then ncclCommInitRank
+        from mpc_rs_b200.distributed import attach_mppi, attach_mppi_peers
+        if transport == "nccl":
+            attach_mppi(mppi)  # rank 0's ncclUniqueId -> everyone (torch.distributed broadcast), then ncclCommInitRank
+        else:
+            attach_mppi_peers(mppi)  # every rank's mailbox handle -> everyone, then cudaIpcOpenMemHandle
 
     stream = torch.cuda.ExternalStream(mppi.stream, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2

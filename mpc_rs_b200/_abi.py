@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmpc_b200.so")
+LIB_PATH = os.environ.get("MPCB_LIB_PATH") or os.path.join(_HERE, "libmpc_b200.so")  # override: developer A/B builds
 
 # ---- enums (include/mpc_b200.h) ----
 OK, NO_FINITE_COST, SUM_ZERO, U_INVALID, INVERSE_FAIL, CHOLESKY_FAIL, BAD_ARG, CUDA_ERROR, NCCL_ERROR, NOT_PREDICTED, \

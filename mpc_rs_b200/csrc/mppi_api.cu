@@ -2,6 +2,7 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <stdlib.h>
+#include <time.h>
 #include <unistd.h>
 
 #include <new>
@@ -62,7 +63,17 @@ struct mpcb_mppi {
     unsigned int** d_peer_flags = nullptr;
     bool peers_attached = false;
     unsigned int xepoch = 0;
+    // host-side trace of the single-controller compute (MPCB_TRACE_HOST=1): accumulated microseconds
+    bool trace = false;
+    double tr_launch = 0, tr_wait = 0, tr_total = 0;
+    long tr_n = 0;
 };
+
+static inline double host_now_us() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
 
 // 128-byte blob exchanged between ranks by mpcb_mppi_peer_handle / mpcb_mppi_attach_peers
 struct PeerBlob {
@@ -203,6 +214,7 @@ void fill_params(const mpcb_mppi* h, MppiParams* p) {
     p->lgHp = h->lgHp;
     p->PL = h->PL;
     p->mergers = h->mergers;
+
     p->W = h->W;
     p->C = h->C;
     p->chunks = h->chunks;
@@ -313,6 +325,7 @@ void set_peer_params(mpcb_mppi* h, MppiParams& p) {
 mpcb_status compute_host(mpcb_mppi* h, const double* x, const double* u_in, const void* d_eps, int eps_dtype,
                          void* d_dump, double* u_out, mpcb_mppi_info* info) {
     MPCB_REQUIRE(h && x && u_in && u_out, "null pointer");
+    const double tr0 = h->trace ? host_now_us() : 0.0;
     MPCB_CUDA_TRY(cudaSetDevice(h->cfg.device));
     MppiParams p;
     fill_params(h, &p);
@@ -345,7 +358,21 @@ mpcb_status compute_host(mpcb_mppi* h, const double* x, const double* u_in, cons
         if (st != MPCB_OK) return st;
     }
     const int words = (sharded && !peer) ? 1 : (h->mergers > 0 ? h->mergers : 1);
-    return finish_host(h, u_out, info, spin, words);
+    const double tr1 = h->trace ? host_now_us() : 0.0;
+    st = finish_host(h, u_out, info, spin, words);
+    if (h->trace) {
+        const double tr2 = host_now_us();
+        h->tr_launch += tr1 - tr0;
+        h->tr_wait += tr2 - tr1;
+        h->tr_total += tr2 - tr0;
+        h->tr_n += 1;
+        if (h->tr_n % 1000 == 0) {
+            fprintf(stderr, "[mpcb trace] compute: enqueue %.2f us, wait+copy-out %.2f us, total %.2f us (mean of 1000)\n",
+                    h->tr_launch / 1000, h->tr_wait / 1000, h->tr_total / 1000);
+            h->tr_launch = h->tr_wait = h->tr_total = 0;
+        }
+    }
+    return st;
 }
 
 mpcb_status run_combine(mpcb_mppi* h, const double* rows, int G) {
@@ -478,6 +505,7 @@ mpcb_status mpcb_mppi_create(mpcb_mppi** out, const mpcb_mppi_cfg* cfg) {
     TRY_OR_FAIL(cudaMemset(h->d_counters, 0, C * (size_t)(h->groups + 1) * sizeof(unsigned int)));
     TRY_OR_FAIL(cudaMalloc(&h->d_info, C * sizeof(mpcb_mppi_info)));
     TRY_OR_FAIL(cudaMemset(h->d_info, 0, C * sizeof(mpcb_mppi_info)));
+    h->trace = getenv("MPCB_TRACE_HOST") != nullptr;
     if (getenv("MPCB_DEBUG_TS")) {
         TRY_OR_FAIL(cudaMalloc(&h->d_ts, C * (size_t)h->chunks * 16 * sizeof(unsigned long long)));
         TRY_OR_FAIL(cudaMemset(h->d_ts, 0, C * (size_t)h->chunks * 16 * sizeof(unsigned long long)));

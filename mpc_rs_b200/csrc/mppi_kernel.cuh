@@ -36,6 +36,10 @@ namespace mpcb {
 constexpr int kPartialHdr = 4;   // m, argmax (bits), sum_w, n_finite (as double)
 constexpr int kMergeFan = 256;   // max rows merged by one block
 constexpr int kMaxWarps = 16;    // warps per block (BLOCK <= 512)
+#ifndef MPCB_FLUSH_STEPS
+#define MPCB_FLUSH_STEPS 4
+#endif
+constexpr int kFlushSteps = MPCB_FLUSH_STEPS;  // FP32 cost partial sums -> FP64 accumulator period (power of two >= 4)
 // shared scratch (doubles): red_m[16] red_a[16] red_n[16] red_s[24] sc[kMergeFan]
 constexpr int kScratchDoubles = 16 + 16 + 16 + 24 + kMergeFan;
 
@@ -215,7 +219,7 @@ struct MergeOut {
 template <int BLOCK>
 __device__ __noinline__ void mppi_merge_rows(const double* rows, long long row_stride, int n_rows, int H, int mi, int nm,
                                              double inv_lambda, int final_mode, const MergeOut& o, double* scratch,
-                                             double* part) {
+                                             double* part, double* tot) {
     constexpr int NW = BLOCK / 32;
     constexpr int RPT = (kMergeFan + BLOCK - 1) / BLOCK;  // header rows per thread
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -335,7 +339,7 @@ __device__ __noinline__ void mppi_merge_rows(const double* rows, long long row_s
     __syncthreads();
     if (ts != nullptr && tid == 0) ts[4] = globaltimer_ns();
     // ---- the nq (<= 32) partition sums of a pair: one warp per pair, fixed xor tree over the lanes ----
-    double2* tot2 = part2 + nq * Hpm;  // [npl]
+    double2* tot2 = reinterpret_cast<double2*>(tot);  // [npl]
     for (int jl = wid; jl < npl; jl += NW) {
         double2 t0 = (lane < nq) ? part2[lane * Hpm + jl] : make_double2(0.0, 0.0);
 #pragma unroll
@@ -435,7 +439,7 @@ __host__ __device__ inline int mppi_partial_len(int H) { return (kPartialHdr + H
 __host__ __device__ inline size_t mppi_part_doubles(int H, int block) {
     const int Hp = mppi_pow2_horizon(H, nullptr), Hp2 = mppi_pow2_pairs(H, nullptr);
     size_t a = (size_t)(block > Hp ? block : Hp);
-    size_t b = 2 * ((size_t)(block > Hp2 ? block : Hp2) + Hp2);  // partition sums + totals, double2 each
+    size_t b = 2 * (size_t)(block > Hp2 ? block : Hp2);  // partition sums, double2 each
     return a > b ? a : b;
 }
 
@@ -614,11 +618,13 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
 #pragma unroll
                 for (int i = 0; i < 4; ++i) step(t0 + i, e[i], u4[i], ui4[i]);
                 if constexpr (!kExact) {
-                    // FP32 partial sums over 4 steps are flushed into the FP64 accumulators
-                    J += (double)cw;
-                    CT += (double)cu;
-                    cw = (real)0;
-                    cu = (real)0;
+                    // FP32 partial sums are flushed into the FP64 accumulators every kFlushSteps steps
+                    if ((t0 & (kFlushSteps - 1)) == kFlushSteps - 4) {
+                        J += (double)cw;
+                        CT += (double)cu;
+                        cw = (real)0;
+                        cu = (real)0;
+                    }
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) e[i] = en[i];
@@ -627,10 +633,10 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
 #pragma unroll
                 for (int i = 0; i < 3; ++i)
                     if (H4 + i < H) step(H4 + i, e[i], su[H4 + i], sui[H4 + i]);
-                if constexpr (!kExact) {
-                    J += (double)cw;
-                    CT += (double)cu;
-                }
+            }
+            if constexpr (!kExact) {
+                J += (double)cw;  // whatever is left since the last flush
+                CT += (double)cu;
             }
             ck = -J - CT;  // :61
             if (p.costs != nullptr && valid) p.costs[(long long)c * p.K_local + kl] = ck;
@@ -736,6 +742,7 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
     // last block to arrive merges alone.
     const int PL = p.PL;
     const double inv_lambda_m = 1.0 / lambda;
+    double* tot_d = reinterpret_cast<double*>(v_s);  // the v tile is dead after the rollouts: merge totals [<= (H+5)/2 double2]
     double* ctrl_rows = p.partial + (long long)c * (p.chunks + p.groups) * PL;
     double* my_row = ctrl_rows + (long long)chunk * PL;
     for (int t = tid; t < H; t += BLOCK) my_row[kPartialHdr + t] = U_run[t];
@@ -803,7 +810,7 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
             MergeOut go = none;
             go.out_row = group_rows + (long long)g * PL;
             mppi_merge_rows<BLOCK>(ctrl_rows + (long long)g_first * PL, PL, g_rows, H, 0, 1, inv_lambda_m, FINAL_RANK_ROW, go,
-                                   scratch, part_d);
+                                   scratch, part_d, tot_d);
             if (tid == 0 && PL > kPartialHdr + H) go.out_row[kPartialHdr + H] = 0.0;
             MPCB_TS(3);
             const bool last2 = arrive(p.groups, p.groups);
@@ -829,7 +836,7 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
     if (p.final_mode != FINAL_PEER_EXCHANGE) {
         fo.out_row = p.rank_partial ? p.rank_partial + (long long)c * PL : nullptr;
         fo.ts = (p.groups == 1 && mi == 0) ? dbg : nullptr;
-        mppi_merge_rows<BLOCK>(final_rows, PL, final_n, H, mi, nm, inv_lambda_m, p.final_mode, fo, scratch, part_d);
+        mppi_merge_rows<BLOCK>(final_rows, PL, final_n, H, mi, nm, inv_lambda_m, p.final_mode, fo, scratch, part_d, tot_d);
         if (p.final_mode == FINAL_RANK_ROW && mi == 0 && tid == 0 && PL > kPartialHdr + H) fo.out_row[kPartialHdr + H] = 0.0;
         MPCB_TS(5);
         return;
@@ -847,7 +854,7 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
         double* my_slot = own_box + slot_self * PL;
         MergeOut ro = none;
         ro.out_row = my_slot;
-        mppi_merge_rows<BLOCK>(final_rows, PL, final_n, H, mi, nm, inv_lambda_m, FINAL_RANK_ROW, ro, scratch, part_d);
+        mppi_merge_rows<BLOCK>(final_rows, PL, final_n, H, mi, nm, inv_lambda_m, FINAL_RANK_ROW, ro, scratch, part_d, tot_d);
         // the doubles of the row this merger produced: its pairs, plus the 4 header doubles for merger 0
         const int ncol2 = (H + 3) >> 1;
         const int cp = (ncol2 - 1 + nm - 1) / nm;
@@ -879,7 +886,7 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
         __syncthreads();
         fo.forced_status = s_timeout ? MPCB_PEER_TIMEOUT : MPCB_OK;
         mppi_merge_rows<BLOCK>(own_box + (long long)(par * G) * p.C * PL + (long long)c * PL, (long long)p.C * PL, G, H, mi, nm,
-                               inv_lambda_m, FINAL_NORMALISE, fo, scratch, part_d);
+                               inv_lambda_m, FINAL_NORMALISE, fo, scratch, part_d, tot_d);
         MPCB_TS(5);
     }
 }
@@ -900,7 +907,8 @@ struct MppiCombineParams {
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) mppi_combine_kernel(const MppiCombineParams p) {
     __shared__ double scratch[kScratchDoubles];
-    __shared__ __align__(16) double part[2 * ((kMaxHorizon > BLOCK ? kMaxHorizon : BLOCK) + kMaxHorizon)];
+    __shared__ __align__(16) double part[2 * (kMaxHorizon > BLOCK ? kMaxHorizon : BLOCK)];
+    __shared__ __align__(16) double tot[kMaxHorizon + 8];
     const int c = blockIdx.x;
     const int PL = mppi_partial_len(p.H);
     MergeOut o;
@@ -914,7 +922,7 @@ __global__ void __launch_bounds__(BLOCK) mppi_combine_kernel(const MppiCombinePa
     o.forced_status = MPCB_OK;
     o.ts = nullptr;
     mppi_merge_rows<BLOCK>(p.rows + (long long)c * PL, (long long)p.C * PL, p.G, p.H, 0, 1, 1.0 / p.lambda, FINAL_NORMALISE, o,
-                           scratch, part);
+                           scratch, part, tot);
 }
 
 // kernel entry table (defined in mppi_f32*.cu / mppi_f64.cu)

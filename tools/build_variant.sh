@@ -1,0 +1,13 @@
+#!/bin/bash
+# Developer A/B helper: builds mpc_rs_b200/libmpc_b200_<name>.so with extra -D flags applied to the MPPI kernels of
+# model NL (FP32), everything else linked from the regular objects.  Select it at run time with MPCB_LIB_PATH.
+#   tools/build_variant.sh <name> -DMPCB_SOMETHING=1 ...
+set -e
+name=$1; shift
+cd "$(dirname "$0")/../mpc_rs_b200/csrc"
+make -j8 >/dev/null
+mkdir -p /tmp/mpcb_var_$name
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -ccbin g++ -Xcompiler -fPIC "$@" -c mppi_f32_NL.cu -o /tmp/mpcb_var_$name/mppi_f32_NL.o
+objs=$(ls *.o | grep -v '^mppi_f32_NL.o$')
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../libmpc_b200_$name.so $objs /tmp/mpcb_var_$name/mppi_f32_NL.o -lcudart -ldl
+echo built ../libmpc_b200_$name.so
