@@ -165,6 +165,9 @@ mpcb_status mpcb_mppi_get_costs(mpcb_mppi* h, double* c_out);
  * (generate).  Status lands in the handle; read it with mpcb_mppi_last_info after mpcb_mppi_sync. */
 mpcb_status mpcb_mppi_compute_device(mpcb_mppi* h, const double* d_x, const double* d_u_in,
                                      const void* d_eps, int32_t eps_dtype, double* d_u_out);
+/* d_u0[c] = d_u_out[c][0] on the handle's stream: the control every controller applies next (u_n[0],
+ * examples/mppi4-non-liner-ukf.rs:231,270) — feeds mpcb_ukf_run_device's per-filter d_u without a host trip. */
+mpcb_status mpcb_mppi_first_control_device(mpcb_mppi* h, const double* d_u_out, double* d_u0);
 mpcb_status mpcb_mppi_sync(mpcb_mppi* h);
 mpcb_status mpcb_mppi_last_info(mpcb_mppi* h, mpcb_mppi_info* info /*[C]*/);
 void* mpcb_mppi_stream(mpcb_mppi* h);    /* cudaStream_t */
@@ -250,6 +253,16 @@ mpcb_status mpcb_ukf_get_state(mpcb_ukf* h, double* x, double* P);
 mpcb_status mpcb_ukf_get_state_range(mpcb_ukf* h, int64_t first, int64_t count, double* x, double* P);
 mpcb_status mpcb_ukf_set_q(mpcb_ukf* h, const double* Q); /* src/ukf2.rs:96 */
 mpcb_status mpcb_ukf_set_r(mpcb_ukf* h, const double* R); /* called by examples/mppi4-ukf-commu.rs:280, missing in the reference */
+/* Per-packet sensor gating of examples/mppi4-ukf-commu.rs:228-236,279-293: bit i of `enable` cleared means sensor i
+ * delivered nothing — the hx closure returns 0 for that row (mpcb_ukf_set_enable, applies to the following
+ * update/step calls; default all ones) and gen_r inflates its variance to 1e6 (mpcb_ukf_gen_r builds that R from
+ * the nominal R[o][o]; pass it to mpcb_ukf_set_r, as the example does). */
+mpcb_status mpcb_ukf_set_enable(mpcb_ukf* h, uint32_t enable);
+mpcb_status mpcb_ukf_gen_r(const mpcb_ukf* h, uint32_t enable, const double* R, double* R_out);
+/* d_out[B][n_idx] (device, row per filter) <- state components idx[0..n_idx) of every filter, on the handle's
+ * stream: e.g. idx = {0,1,3,4} turns the 6-state estimate into the 4-state MPPI input of
+ * examples/mppi4-non-liner-ukf.rs:78 for mpcb_mppi_compute_device. */
+mpcb_status mpcb_ukf_gather_state_device(mpcb_ukf* h, int32_t n_idx, const int32_t* idx, double* d_out);
 /* predict(u, fx) (src/ukf.rs:44): u[B] per-filter controls, or NULL with u_scalar broadcast; dt <= 0 uses
  * cfg.model.dt (NL6_UKF's fx is dynamics_short(.,.,dt,0), examples/mppi4-non-liner-ukf.rs:278). */
 mpcb_status mpcb_ukf_predict(mpcb_ukf* h, const double* u, double u_scalar, double dt);

@@ -105,6 +105,10 @@ SYMBOLS = {
     "mpcb_mppi_combine": (C.c_int, [_H, _vp, C.c_int32, _dp, C.POINTER(MppiInfo)]),
     "mpcb_comm_unique_id": (C.c_int, [C.c_char_p]),
     "mpcb_mppi_attach_comm": (C.c_int, [_H, C.c_char_p]),
+    "mpcb_mppi_first_control_device": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
+    "mpcb_ukf_set_enable": (C.c_int, [_H, C.c_uint32]),
+    "mpcb_ukf_gen_r": (C.c_int, [_H, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "mpcb_ukf_gather_state_device": (C.c_int, [_H, C.c_int32, C.POINTER(C.c_int32), C.c_void_p]),
     "mpcb_mppi_peer_handle": (C.c_int, [_H, C.c_char_p]),
     "mpcb_mppi_attach_peers": (C.c_int, [_H, C.c_char_p]),
     "mpcb_ukf_default_cfg": (C.c_int, [C.c_int32, C.POINTER(UkfCfg)]),

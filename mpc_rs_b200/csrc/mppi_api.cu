@@ -641,6 +641,21 @@ mpcb_status mpcb_mppi_compute_device(mpcb_mppi* h, const double* d_x, const doub
     return MPCB_OK;
 }
 
+// u0[c] = u_out[c][0]: the control each controller applies next (u_n[0], examples/mppi4-non-liner-ukf.rs:231,270)
+__global__ void mppi_first_control_kernel(const double* u_out, double* u0, int C, int H) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) u0[c] = u_out[(long long)c * H];
+}
+
+mpcb_status mpcb_mppi_first_control_device(mpcb_mppi* h, const double* d_u_out, double* d_u0) {
+    MPCB_REQUIRE(h && d_u_out && d_u0, "null pointer");
+    MPCB_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    mppi_first_control_kernel<<<(h->C + 255) / 256, 256, 0, h->stream>>>(d_u_out, d_u0, h->C, h->H);
+    MPCB_CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    return MPCB_OK;
+}
+
 mpcb_status mpcb_mppi_sync(mpcb_mppi* h) {
     MPCB_REQUIRE(h, "null handle");
     MPCB_CUDA_TRY(cudaSetDevice(h->cfg.device));

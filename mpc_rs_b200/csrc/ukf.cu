@@ -50,8 +50,23 @@ struct mpcb_ukf {
     double* d_z = nullptr;
     int* d_status = nullptr;
     bool predicted = false;
+    unsigned int enable = 0xffffffffu;  // sensor mask of the next update (examples/mppi4-ukf-commu.rs:279-293)
     int64_t launches = 0;
 };
+
+// x[B][n_idx] (AoS rows) <- the state components idx[] of every filter (SoA [n][B])
+struct GatherParams {
+    const double* x;
+    double* out;
+    long long B;
+    int n_idx;
+    int idx[8];
+};
+__global__ void ukf_gather_state_kernel(const GatherParams p) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    for (int j = 0; j < p.n_idx; ++j) p.out[b * p.n_idx + j] = p.x[(long long)p.idx[j] * p.B + b];
+}
 
 namespace {
 
@@ -98,6 +113,7 @@ void fill_params(const mpcb_ukf* h, UkfParams* p) {
     memcpy(p->Q, h->Q, sizeof(p->Q));
     memcpy(p->R, h->R, sizeof(p->R));
     p->mc = h->mc;
+    p->enable = h->enable;
 }
 
 mpcb_status launch(mpcb_ukf* h, UkfKernelFn fn, const UkfParams& p) {
@@ -393,6 +409,40 @@ mpcb_status mpcb_ukf_set_q(mpcb_ukf* h, const double* Q) {
 mpcb_status mpcb_ukf_set_r(mpcb_ukf* h, const double* R) {
     MPCB_REQUIRE(h && R, "null pointer");
     memcpy(h->R, R, sizeof(double) * h->o * h->o);
+    return MPCB_OK;
+}
+
+mpcb_status mpcb_ukf_set_enable(mpcb_ukf* h, uint32_t enable) {
+    MPCB_REQUIRE(h, "null handle");
+    h->enable = enable;
+    return MPCB_OK;
+}
+
+mpcb_status mpcb_ukf_gen_r(const mpcb_ukf* h, uint32_t enable, const double* R, double* R_out) {
+    MPCB_REQUIRE(h && R && R_out, "null pointer");
+    // gen_r, examples/mppi4-ukf-commu.rs:228-236: a disabled sensor's variance becomes 1e6
+    for (int i = 0; i < h->o * h->o; ++i) R_out[i] = R[i];
+    for (int i = 0; i < h->o; ++i)
+        if ((enable & (1u << i)) == 0) R_out[i * h->o + i] = 1e6;
+    return MPCB_OK;
+}
+
+mpcb_status mpcb_ukf_gather_state_device(mpcb_ukf* h, int32_t n_idx, const int32_t* idx, double* d_out) {
+    MPCB_REQUIRE(h && idx && d_out, "null pointer");
+    MPCB_REQUIRE(n_idx >= 1 && n_idx <= 8, "1..8 components");
+    GatherParams g;
+    g.x = h->d_x;
+    g.out = d_out;
+    g.B = h->B;
+    g.n_idx = n_idx;
+    for (int j = 0; j < n_idx; ++j) {
+        MPCB_REQUIRE(idx[j] >= 0 && idx[j] < h->n, "component index outside the state");
+        g.idx[j] = idx[j];
+    }
+    MPCB_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    ukf_gather_state_kernel<<<(unsigned)((h->B + 255) / 256), 256, 0, h->stream>>>(g);
+    MPCB_CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
     return MPCB_OK;
 }
 

@@ -35,6 +35,8 @@ struct UkfParams {
     int* status;      // [B], sticky
     double u_scalar;
     double dt;
+    unsigned int enable;  // sensor bit mask: hx rows of cleared bits read 0 (examples/mppi4-ukf-commu.rs:279-293)
+    unsigned int pad0;
     double wm0, wc0, wi, cC;  // sigma_weight (src/ukf.rs:112-118), C = alpha^2 (n + kappa)
     double Q[36];
     double R[25];
@@ -483,7 +485,7 @@ __global__ void __launch_bounds__(128) ukf_kernel(const __grid_constant__ UkfPar
                 for (int r = 0; r < N; ++r) col[r] = sig[r][i];
                 ukf_hx<MODEL, N, O>(p.mc, col, zz);
 #pragma unroll
-                for (int r = 0; r < O; ++r) zs[r][i] = zz[r];
+                for (int r = 0; r < O; ++r) zs[r][i] = ((p.enable >> r) & 1u) ? zz[r] : 0.0;
             }
             double zp[O], pz[O][O];
             unscented_transform<O, M, FAST>(zs, p.wm0, p.wc0, p.wi, p.R, zp, pz);

@@ -182,6 +182,10 @@ class Mppi:
     def compute_device(self, d_x: int, d_u_in: int, d_u_out: int, d_eps: int = 0, eps_dtype: int = A.DT_F32):
         A.check(A.lib().mpcb_mppi_compute_device(self._h, d_x, d_u_in, d_eps or None, eps_dtype, d_u_out))
 
+    def first_control_device(self, d_u_out: int, d_u0: int):
+        """Asynchronous: d_u0[c] = d_u_out[c][0] (the control every controller applies next)."""
+        A.check(A.lib().mpcb_mppi_first_control_device(self._h, d_u_out, d_u0))
+
     def sync(self):
         A.check(A.lib().mpcb_mppi_sync(self._h))
 

@@ -115,6 +115,23 @@ class BatchedUkf:
         R = np.ascontiguousarray(R, dtype=np.float64).reshape(self.o, self.o)
         A.check(A.lib().mpcb_ukf_set_r(self._h, _dp(R)))
 
+    def set_enable(self, enable: int):
+        """Sensor bit mask of the following updates: a cleared bit zeroes that row of hx, like the closure of
+        examples/mppi4-ukf-commu.rs:279-293.  Pair it with set_r(gen_r(enable, R))."""
+        A.check(A.lib().mpcb_ukf_set_enable(self._h, int(enable) & 0xFFFFFFFF))
+
+    def gen_r(self, enable: int, R):
+        """gen_r of examples/mppi4-ukf-commu.rs:228-236: R with the variance of every disabled sensor set to 1e6."""
+        R = np.ascontiguousarray(R, dtype=np.float64).reshape(self.o, self.o)
+        out = np.empty_like(R)
+        A.check(A.lib().mpcb_ukf_gen_r(self._h, int(enable) & 0xFFFFFFFF, _dp(R), _dp(out)))
+        return out
+
+    def gather_state_device(self, idx, d_out: int):
+        """Asynchronous: d_out[B][len(idx)] <- the state components idx of every filter (for Mppi.compute_device)."""
+        arr = (C.c_int32 * len(idx))(*[int(i) for i in idx])
+        A.check(A.lib().mpcb_ukf_gather_state_device(self._h, len(idx), arr, d_out))
+
     # -- filtering --
     def _u(self, u):
         if np.ndim(u) == 0:

@@ -762,8 +762,22 @@ int orc_ukf_predict(int model_id, const mpcb_model_params* p, int n, int sqrt_mo
     return MPCB_OK;
 }
 
+/* gen_r of examples/mppi4-ukf-commu.rs:228-236: the variance of every disabled sensor becomes 1e6 */
+void orc_gen_r(int o, const double* R, uint32_t enable, double* R_out) {
+    for (int i = 0; i < o * o; ++i) R_out[i] = R[i];
+    for (int i = 0; i < o; ++i)
+        if ((enable & (1u << i)) == 0) R_out[i * o + i] = 1e6;
+}
+
 int orc_ukf_update(int model_id, const mpcb_model_params* p, int n, int o, double* x, double* P, const double* R,
                    const double* z, const double* sigma_f) {
+    return orc_ukf_update_masked(model_id, p, n, o, x, P, R, z, sigma_f, 0xffffffffu);
+}
+
+/* update with the per-packet sensor mask of examples/mppi4-ukf-commu.rs:279-293: the hx closure zeroes the
+ * rows of disabled sensors (the caller pairs it with orc_gen_r) */
+int orc_ukf_update_masked(int model_id, const mpcb_model_params* p, int n, int o, double* x, double* P, const double* R,
+                          const double* z, const double* sigma_f, uint32_t enable) {
     const int M = 2 * n + 1;
     double wm[ORC_MAX_M], wc[ORC_MAX_M];
     orc_ukf_weights(n, wm, wc);
@@ -772,7 +786,7 @@ int orc_ukf_update(int model_id, const mpcb_model_params* p, int n, int o, doubl
         double col[ORC_MAX_N], zz[ORC_MAX_N];
         for (int r = 0; r < n; ++r) col[r] = sigma_f[r * M + i];
         orc_hx(model_id, p, col, zz);
-        for (int r = 0; r < o; ++r) sh[r * M + i] = zz[r];
+        for (int r = 0; r < o; ++r) sh[r * M + i] = (enable & (1u << r)) ? zz[r] : 0.0;
     }
     double zp[ORC_MAX_N], pz[ORC_MAX_N * ORC_MAX_N];
     unscented_transform(o, M, sh, wm, wc, R, zp, pz); /* :62 */
@@ -829,13 +843,20 @@ int orc_ukf_update(int model_id, const mpcb_model_params* p, int n, int o, doubl
 int orc_ukf_step_batch(int model_id, const mpcb_model_params* p, int n, int o, int sqrt_mode, int order, int64_t B,
                        double* x, double* P, const double* Q, const double* R, const double* u, double u_scalar,
                        double dt, const double* z, int32_t* status, int threads) {
+    return orc_ukf_step_batch_masked(model_id, p, n, o, sqrt_mode, order, B, x, P, Q, R, u, u_scalar, dt, z, status, threads,
+                                     0xffffffffu);
+}
+
+int orc_ukf_step_batch_masked(int model_id, const mpcb_model_params* p, int n, int o, int sqrt_mode, int order, int64_t B,
+                              double* x, double* P, const double* Q, const double* R, const double* u, double u_scalar,
+                              double dt, const double* z, int32_t* status, int threads, uint32_t enable) {
     if (threads <= 0) threads = orc_max_threads();
     int any = MPCB_OK;
 #pragma omp parallel for schedule(static) num_threads(threads)
     for (int64_t b = 0; b < B; ++b) {
         double sf[ORC_MAX_N * ORC_MAX_M];
         int st = orc_ukf_predict(model_id, p, n, sqrt_mode, order, x + b * n, P + b * n * n, Q, u ? u[b] : u_scalar, dt, sf);
-        if (st == MPCB_OK) st = orc_ukf_update(model_id, p, n, o, x + b * n, P + b * n * n, R, z + b * o, sf);
+        if (st == MPCB_OK) st = orc_ukf_update_masked(model_id, p, n, o, x + b * n, P + b * n * n, R, z + b * o, sf, enable);
         if (status) status[b] = st;
         if (st != MPCB_OK) {
 #pragma omp critical

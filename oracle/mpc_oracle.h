@@ -81,6 +81,12 @@ int orc_ukf_predict(int model_id, const mpcb_model_params* p, int n, int sqrt_mo
 /* update (src/ukf.rs:54-74) */
 int orc_ukf_update(int model_id, const mpcb_model_params* p, int n, int o, double* x, double* P, const double* R,
                    const double* z, const double* sigma_f);
+int orc_ukf_update_masked(int model_id, const mpcb_model_params* p, int n, int o, double* x, double* P, const double* R,
+                          const double* z, const double* sigma_f, uint32_t enable); /* examples/mppi4-ukf-commu.rs:279-293 */
+void orc_gen_r(int o, const double* R, uint32_t enable, double* R_out);            /* examples/mppi4-ukf-commu.rs:228-236 */
+int orc_ukf_step_batch_masked(int model_id, const mpcb_model_params* p, int n, int o, int sqrt_mode, int order, int64_t B,
+                              double* x, double* P, const double* Q, const double* R, const double* u, double u_scalar,
+                              double dt, const double* z, int32_t* status, int threads, uint32_t enable);
 /* batched predict+update over B filters, AoS x[B][n], P[B][n][n], z[B][o], u[B] or NULL; `threads` workers */
 int orc_ukf_step_batch(int model_id, const mpcb_model_params* p, int n, int o, int sqrt_mode, int order, int64_t B,
                        double* x, double* P, const double* Q, const double* R, const double* u, double u_scalar,

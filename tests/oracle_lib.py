@@ -87,6 +87,9 @@ def lib():
     L.orc_ukf_update.argtypes = [C.c_int, PP, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
     L.orc_ukf_step_batch.argtypes = [C.c_int, PP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, _dp, _dp, _dp, _dp,
                                      _dp, C.c_double, C.c_double, _dp, C.POINTER(C.c_int32), C.c_int]
+    L.orc_ukf_step_batch_masked.argtypes = L.orc_ukf_step_batch.argtypes + [C.c_uint32]
+    L.orc_gen_r.argtypes = [C.c_int, _dp, C.c_uint32, _dp]
+    L.orc_gen_r.restype = None
     for f in ("add", "sub", "mul"):
         fn = getattr(L, "orc_gaussian_" + f)
         fn.argtypes = [Gaussian, Gaussian]
@@ -253,8 +256,19 @@ def ukf_update(model_id, p, x, P, R, z, sigma_f):
     return st, x, P
 
 
-def ukf_step_batch(model_id, p, x, P, Q, R, u, z, dt=0.0, sqrt_mode=SQRT_CHOLESKY, order=ORDER_LIBRARY, threads=0):
-    """x[B][n], P[B][n][n] AoS (copied), u scalar or [B], z[B][o]. Returns (x', P', status[B])."""
+def gen_r(R, enable):
+    """gen_r of examples/mppi4-ukf-commu.rs:228-236."""
+    R = _f64(R)
+    o = R.shape[0]
+    out = np.empty_like(R)
+    lib().orc_gen_r(o, _ptr(R), enable, _ptr(out))
+    return out
+
+
+def ukf_step_batch(model_id, p, x, P, Q, R, u, z, dt=0.0, sqrt_mode=SQRT_CHOLESKY, order=ORDER_LIBRARY, threads=0,
+                   enable=0xFFFFFFFF):
+    """x[B][n], P[B][n][n] AoS (copied), u scalar or [B], z[B][o]. Returns (x', P', status[B]).
+    enable: sensor bit mask of examples/mppi4-ukf-commu.rs:279-293 (hx rows of cleared bits are zeroed)."""
     x, P = _f64(x).copy(), _f64(P).copy()
     B, n = x.shape
     z = _f64(z)
@@ -266,6 +280,6 @@ def ukf_step_batch(model_id, p, x, P, Q, R, u, z, dt=0.0, sqrt_mode=SQRT_CHOLESK
         ua = _f64(u)
         up, us = _ptr(ua), 0.0
     Q, R = _f64(Q), _f64(R)
-    lib().orc_ukf_step_batch(model_id, C.byref(p), n, o, sqrt_mode, order, B, _ptr(x), _ptr(P), _ptr(Q), _ptr(R), up,
-                             us, float(dt), _ptr(z), status.ctypes.data_as(C.POINTER(C.c_int32)), threads)
+    lib().orc_ukf_step_batch_masked(model_id, C.byref(p), n, o, sqrt_mode, order, B, _ptr(x), _ptr(P), _ptr(Q), _ptr(R), up,
+                                    us, float(dt), _ptr(z), status.ctypes.data_as(C.POINTER(C.c_int32)), threads, enable)
     return x, P, status

@@ -1,0 +1,125 @@
+"""BASELINE config #4 and SURVEY.md 8(f): sensor gating, the batched MPPI+UKF closed loop against the oracle running
+the same schedule, and the example drivers (examples/*.py) end to end."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from mpc_rs_b200 import BatchedUkf, models, ukf
+from mpc_rs_b200.closed_loop import ClosedLoopBatch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "examples"))
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.mark.parametrize("name,oid", [("NL6_UKF", O.MODEL_NL6_UKF), ("PEN6", O.MODEL_PEN6)])
+def test_sensor_gating_parity(gpu_required, name, oid):
+    """set_enable + gen_r (examples/mppi4-ukf-commu.rs:228-236,279-293) against the masked oracle update."""
+    model = getattr(models, name)
+    p = O.model_defaults(oid)
+    Q, R, P0 = O.ukf_default_noise(oid, 0.01)
+    rng = np.random.default_rng(7)
+    B = 96
+    x0, z = rng.normal(0, 0.02, (B, 6)), rng.normal(0, 1.0, (B, 5))
+    for enable in (0b11111, 0b10101, 0b00001, 0b11110):
+        with BatchedUkf(model, B, exact=True) as f:
+            f.init(np.zeros(6), P0 * 0.01, Q, R)
+            f.set_state(x0, None)
+            Rg = f.gen_r(enable, R)
+            assert np.array_equal(Rg, O.gen_r(R, enable))
+            f.set_r(Rg)
+            f.set_enable(enable)
+            f.step(0.4, z, dt=0.01)
+            xg, Pg = f.get_state()
+        xo, Po, st = O.ukf_step_batch(oid, p, x0, np.tile(P0 * 0.01, (B, 1, 1)), Q, Rg, 0.4, z, 0.01, O.SQRT_EIG,
+                                      O.ORDER_LIBRARY, enable=enable)
+        assert not st.any()
+        assert rel(xg, xo) < 1e-8 and rel(Pg, Po) < 1e-8, (name, bin(enable), rel(xg, xo), rel(Pg, Po))
+
+
+def test_closed_loop_matches_the_oracle_schedule(gpu_required):
+    """C robots, MPPI noise replayed: every tick the GPU loop and an oracle loop (same plant, same sensor readings,
+    same noise) must agree on the applied control, the control sequence and the estimate."""
+    C, K, ticks = 3, 2048, 5
+    rng = np.random.default_rng(99)
+    x0 = np.zeros((C, 6))
+    x0[:, 3] = [0.05, -0.08, 0.02]
+    pm, pu = O.model_defaults(O.MODEL_NL6), O.model_defaults(O.MODEL_NL6_UKF)
+    with ClosedLoopBatch(C, K, precision="f64", exact_ukf=True, x0=x0, seed=5) as loop:
+        H, DT, dt = loop.H, loop.DT, loop.tick_dt
+        Q, R, P0 = O.ukf_default_noise(O.MODEL_NL6_UKF, dt)
+        x_true, x_est, P_est = x0.copy(), x0.copy(), np.tile(P0, (C, 1, 1))
+        u_seq, u0 = np.zeros((C, H)), np.zeros(C)
+        for k in range(ticks):
+            eps = loop.R_U * rng.standard_normal((C, K, H))
+            # oracle side of the tick (same order as ClosedLoopBatch.tick)
+            f = loop.plant.push(k * dt)
+            x_true = np.stack([O.dynamics_short(pu, x_true[c], u0[c], dt, f) for c in range(C)])
+            z = np.stack([O.hx(O.MODEL_NL6_UKF, pu, x_true[c]) for c in range(C)]) + rng.normal(0, 1, (C, 5)) * PlantR
+            x_est, P_est, st = O.ukf_step_batch(O.MODEL_NL6_UKF, pu, x_est, P_est, Q, R, u0, z, dt, O.SQRT_EIG, O.ORDER_LIBRARY)
+            assert not st.any()
+            for c in range(C):
+                s, u_new, info, _ = O.mppi_compute(O.MODEL_NL6, pm, K, H, loop.LAMBDA, loop.R_U, loop.LIMIT[0], loop.LIMIT[1],
+                                                   x_est[c][[0, 1, 3, 4]], u_seq[c], eps[c])
+                u_seq[c] = u_new if s == 0 else 0.0
+            u0 = u_seq[:, 0].copy()
+            # GPU side, fed the same sensor readings and noise
+            u0_g = loop.tick(eps=eps, z=z)
+            xg, Pg = loop.estimate()
+            assert np.allclose(loop.x, x_true, rtol=1e-12, atol=1e-14)  # numpy plant == oracle plant
+            # per-tick parity of the coupled parts: UKF 1e-6 on this ill-conditioned n = 6 filter (the sigma weights
+            # amplify rounding 1.7e5 x per step), MPPI 1e-6 on the estimate it was given
+            assert rel(xg, x_est) < 1e-7 and rel(Pg, P_est) < 1e-6, (k, rel(xg, x_est), rel(Pg, P_est))
+            assert rel(loop.controls(), u_seq) < 1e-6, (k, rel(loop.controls(), u_seq))
+            assert rel(u0_g, u0) < 1e-6
+            # the filter multiplies any difference ~200 x per tick, so both sides continue from the oracle's state:
+            # every tick is then a fresh per-step comparison of the whole coupled tick
+            loop.x = x_true.copy()
+            loop.ukf.set_state(x_est, P_est)
+            from mpc_rs_b200.closed_loop import _upload
+            _upload(loop.dev, loop.d_u[loop.cur], u_seq)
+            _upload(loop.dev, loop.d_u0, u0)
+            loop.u0 = u0.copy()
+            assert not loop.mppi_status().any()
+
+
+PlantR = np.array([200.0, 200.0, 10.0, 0.05, 0.05])
+
+
+def test_closed_loop_keeps_the_robots_upright(gpu_required):
+    """Trajectory-level sanity for the batch: with the estimate in the loop, robots started within +-0.1 rad stay
+    inside the reference's abort bound |theta| <= pi/2 through the 2 N push window start."""
+    import mppi4_non_liner_ukf as ex
+    up = ex.run(controllers=64, samples=4096, seconds=1.2, quiet=True, csv=os.path.join(ROOT, "gpurun_out", "cl_test.csv"))
+    assert up.sum() >= 60, f"only {int(up.sum())} of 64 robots upright"
+    data = np.loadtxt(os.path.join(ROOT, "gpurun_out", "cl_test.csv"), delimiter=",")
+    assert data.ndim == 2 and data.shape[1] == 20 and np.all(np.diff(data[:, 0]) > 0)
+
+
+def test_example_mppi4_balances_and_logs(gpu_required, tmp_path):
+    """examples/mppi4.rs / mppi4-non-liner.rs drivers: 3 s of closed loop, pendulum stays inside 60 degrees, CSV loads
+    the way scripts/plot-mppi.py loads it."""
+    import mppi4 as ex
+    for nonlinear in (False, True):
+        path = str(tmp_path / f"mppi_{int(nonlinear)}.csv")
+        rows = ex.run(nonlinear=nonlinear, samples=200_000, seconds=3.0, csv=path, quiet=True, seed=11)
+        assert len(rows) == 30 and np.all(np.abs(rows[:, 4]) < np.radians(60.0))
+        assert abs(rows[-1, 4]) < abs(rows[0, 4]) + 0.05  # theta is being driven back
+        data = np.loadtxt(path, dtype="float", delimiter=",")
+        assert data.shape == (30, 6) and np.allclose(data, rows, rtol=0, atol=0)
+
+
+def test_example_ukf_pen_converges(gpu_required):
+    import ukf_pen as ex
+    x_act, x_est, p = ex.run(batch=256, steps=100, quiet=True, seed=4)
+    assert np.all(np.isfinite(x_est)) and np.all(np.isfinite(p))
+    # observed components (x1, x3) are tracked to within the sensor noise; P has contracted from 10 I
+    assert np.sqrt(np.mean((x_est[:, 1] - x_act[:, 1]) ** 2)) < 0.5
+    assert np.all(p[:, 1, 1] < 5.0) and np.all(p[:, 3, 3] < 5.0)
