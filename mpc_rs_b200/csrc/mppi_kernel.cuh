@@ -210,6 +210,9 @@ struct MergeOut {
     mpcb_mppi_info* info;
     mpcb_mppi_info* info_host;
     double* out_row;
+    double* const* copy_rows;  // FINAL_RANK_ROW: device table of further destinations of the row (peer mailboxes) ...
+    long long copy_offset;     // ... written at copy_rows[r] + copy_offset for r < n_copies, r != copy_skip
+    int n_copies, copy_skip;
     unsigned int* done_host;  // [nm] completion words (mapped host memory) or nullptr
     unsigned int epoch;
     int forced_status;
@@ -361,16 +364,19 @@ __device__ __noinline__ void mppi_merge_rows(const double* rows, long long row_s
         const double ax = tot2[jl].x, ay = tot2[jl].y;
         const int pair = (jl == 0) ? 0 : p_lo + jl - 1;
         if (final_mode == FINAL_RANK_ROW) {
-            if (pair == 0) {
-                if (mi == 0) {
-                    o.out_row[0] = any ? m : -CUDART_INF;
-                    o.out_row[1] = ll_as_double(any ? a : -1ll);
-                    o.out_row[2] = ax;
-                    o.out_row[3] = ay;
+            // the row goes to out_row and, for the cross-GPU exchange, straight into the peers' mailboxes (NVLink stores)
+            for (int r = -1; r < o.n_copies; ++r) {
+                if (r == o.copy_skip) continue;
+                double* dst = (r < 0) ? o.out_row : o.copy_rows[r] + o.copy_offset;
+                if (pair == 0) {
+                    if (mi == 0) {
+                        *reinterpret_cast<double2*>(dst) = make_double2(any ? m : -CUDART_INF, ll_as_double(any ? a : -1ll));
+                        *reinterpret_cast<double2*>(dst + 2) = make_double2(ax, ay);
+                    }
+                } else {
+                    // for odd H the last pair's second slot is the row's zero pad
+                    *reinterpret_cast<double2*>(dst + 2 + 2 * pair) = make_double2(ax, ay);
                 }
-            } else {
-                o.out_row[2 + 2 * pair] = ax;
-                o.out_row[3 + 2 * pair] = ay;  // for odd H the last pair's second slot is the row's zero pad
             }
         } else if (pair > 0) {
             const int t0 = 2 * pair - 2;
@@ -404,6 +410,98 @@ __device__ __noinline__ void mppi_merge_rows(const double* rows, long long row_s
         }
         if (o.done_host) {
             // results first, then this merger's completion word the host spins on (system-scope release)
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned int*>(o.done_host + mi) = o.epoch;
+        }
+    }
+}
+
+// Combines the G (<= 32) rank rows of the cross-GPU exchange: same result as mppi_merge_rows, done by ONE warp with no
+// block barrier — lane r holds row r's header and (sum_w, n_finite), the scales are shuffled around, and lane jl sums
+// its column pair over the G rows.  Called by warp 0 of a merger block; mi/nm select the merger's column slice.
+static __device__ __noinline__ void mppi_combine_ranks_warp(const double* rows, long long row_stride, int G, int H, int mi, int nm,
+                                                     double inv_lambda, const MergeOut& o) {
+    const unsigned int full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int ncol2 = (H + 3) >> 1;
+    const int cp = (ncol2 - 1 + nm - 1) / nm;
+    const int p_lo = 1 + mi * cp;
+    int p_hi = p_lo + cp;
+    if (p_hi > ncol2) p_hi = ncol2;
+    const bool has = lane < G;
+    double2 hd = make_double2(-CUDART_INF, ll_as_double(-1ll)), p0 = make_double2(0.0, 0.0);
+    if (has) {
+        hd = __ldcg(reinterpret_cast<const double2*>(rows + (long long)lane * row_stride));
+        p0 = __ldcg(reinterpret_cast<const double2*>(rows + (long long)lane * row_stride + 2));
+    }
+    // max over the ranks, lowest sample index among equal maxima
+    double m = hd.x, wm;
+    long long a = double_as_ll(hd.y), wa;
+    if (a < 0) a = kNoArg;
+    int dummy;
+    warp_argmax(m, a, has && a != kNoArg, &wm, &wa, &dummy);
+    const bool holds = has && a != kNoArg && m == wm;
+    const unsigned int ahi = holds ? (unsigned int)((unsigned long long)a >> 32) : 0xffffffffu;
+    const unsigned int mh = __reduce_min_sync(full, ahi);
+    const unsigned int alo = (holds && ahi == mh) ? (unsigned int)a : 0xffffffffu;
+    const unsigned int ml = __reduce_min_sync(full, alo);
+    const bool any = (wa != kNoArg);
+    const long long arg = any ? (long long)(((unsigned long long)mh << 32) | ml) : -1ll;
+    const double sc = (!has || hd.x == -CUDART_INF) ? 0.0 : exp((hd.x - wm) * inv_lambda);
+    // sum_w and n_finite in rank order (a serial chain over <= 32 shuffles keeps the order fixed)
+    double s = 0.0, nf = 0.0;
+    for (int r = 0; r < G; ++r) {
+        const double fr = __hiloint2double(__shfl_sync(full, __double2hiint(sc), r), __shfl_sync(full, __double2loint(sc), r));
+        const double sr = __hiloint2double(__shfl_sync(full, __double2hiint(p0.x), r), __shfl_sync(full, __double2loint(p0.x), r));
+        const double nr = __hiloint2double(__shfl_sync(full, __double2hiint(p0.y), r), __shfl_sync(full, __double2loint(p0.y), r));
+        s += fr * sr;  // scale 0 * NaN = NaN keeps the reference's poisoning
+        nf += nr;
+    }
+    int status = (o.forced_status != MPCB_OK) ? o.forced_status : (!any ? MPCB_NO_FINITE_COST : (s == 0.0 ? MPCB_SUM_ZERO : MPCB_OK));
+    const int npairs = p_hi > p_lo ? p_hi - p_lo : 0;
+    for (int j0 = 0; j0 < npairs || j0 == 0; j0 += 32) {  // at least one pass so that the shuffles below are uniform
+        const int j = j0 + lane;
+        const bool live = j < npairs;
+        const int pair = p_lo + j;
+        double ax = 0.0, ay = 0.0;
+        for (int r = 0; r < G; ++r) {
+            const double fr = __hiloint2double(__shfl_sync(full, __double2hiint(sc), r), __shfl_sync(full, __double2loint(sc), r));
+            if (live) {
+                const double2 v = __ldcg(reinterpret_cast<const double2*>(rows + (long long)r * row_stride + 2 + 2 * pair));
+                ax += fr * v.x;
+                ay += fr * v.y;
+            }
+        }
+        if (live) {
+            const int t0 = 2 * pair - 2;
+            const double u0 = any ? ax / s : 0.0;
+            const double u1 = any ? ay / s : 0.0;
+            o.u_out[t0] = u0;
+            if (o.u_out_host) o.u_out_host[t0] = u0;
+            if (t0 + 1 < H) {
+                o.u_out[t0 + 1] = u1;
+                if (o.u_out_host) o.u_out_host[t0 + 1] = u1;
+            }
+            if (t0 == 0 && status == MPCB_OK && !finite_f64(u0)) status = MPCB_U_INVALID;  // src/mppi.rs:87-89
+        }
+        if (j0 + 32 >= npairs) break;
+    }
+    // u[0] lives in pair 1 = the first pair of merger 0, lane 0
+    if (o.done_host) __threadfence_system();
+    __syncwarp();
+    if (lane == 0) {
+        if (mi == 0) {
+            mpcb_mppi_info out;
+            out.status = status;
+            out.reserved = 0;
+            out.argmax = arg;
+            out.max = any ? wm : 0.0;
+            out.sum = s;
+            out.n_finite = (long long)nf;
+            *o.info = out;
+            if (o.info_host) *o.info_host = out;
+        }
+        if (o.done_host) {
             __threadfence_system();
             *reinterpret_cast<volatile unsigned int*>(o.done_host + mi) = o.epoch;
         }
@@ -787,6 +885,7 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
     int final_n = p.chunks;
     MergeOut none;
     none.u_out = nullptr; none.u_out_host = nullptr; none.info = nullptr; none.info_host = nullptr; none.out_row = nullptr;
+    none.copy_rows = nullptr; none.copy_offset = 0; none.n_copies = 0; none.copy_skip = -2;
     none.done_host = nullptr; none.epoch = 0u; none.forced_status = MPCB_OK; none.ts = nullptr;
     if (p.groups == 1) {
         const bool last = arrive(0, p.chunks);
@@ -851,24 +950,14 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
         const unsigned int par = p.xepoch & 1u;
         const long long slot_self = ((long long)(par * G + p.rank) * p.C + c);
         double* own_box = p.peer_mbox[p.rank];
-        double* my_slot = own_box + slot_self * PL;
         MergeOut ro = none;
-        ro.out_row = my_slot;
+        ro.out_row = own_box + slot_self * PL;
+        ro.copy_rows = p.peer_mbox;
+        ro.copy_offset = slot_self * PL;
+        ro.n_copies = G;
+        ro.copy_skip = p.rank;
         mppi_merge_rows<BLOCK>(final_rows, PL, final_n, H, mi, nm, inv_lambda_m, FINAL_RANK_ROW, ro, scratch, part_d, tot_d);
-        // the doubles of the row this merger produced: its pairs, plus the 4 header doubles for merger 0
-        const int ncol2 = (H + 3) >> 1;
-        const int cp = (ncol2 - 1 + nm - 1) / nm;
-        int d_lo = 2 + 2 * (1 + mi * cp), d_hi = d_lo + 2 * cp;
-        if (d_hi > PL) d_hi = PL;
-        if (mi == 0) d_lo = 0;
-        if (mi == nm - 1 && tid == 0 && PL > kPartialHdr + H) my_slot[kPartialHdr + H] = 0.0;
-        __syncthreads();  // the slice is complete in this GPU's memory
-        for (int r = 0; r < G; ++r) {
-            if (r == p.rank) continue;
-            double* dst = p.peer_mbox[r] + slot_self * PL;
-            for (int i = d_lo + tid; i < d_hi; i += BLOCK) dst[i] = __ldcg(my_slot + i);
-        }
-        __threadfence_system();
+        // the stores of the whole block come before the barrier, thread r's system-scope release after it (cumulative)
         __syncthreads();
         for (int r = tid; r < G; r += BLOCK) st_release_sys_u32(p.peer_flags[r] + slot_self * kMaxMergers + mi, p.xepoch);
         // wait for every rank's slices of this step (bounded: a missing peer becomes MPCB_PEER_TIMEOUT, not a hang)
@@ -885,8 +974,13 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
         }
         __syncthreads();
         fo.forced_status = s_timeout ? MPCB_PEER_TIMEOUT : MPCB_OK;
-        mppi_merge_rows<BLOCK>(own_box + (long long)(par * G) * p.C * PL + (long long)c * PL, (long long)p.C * PL, G, H, mi, nm,
-                               inv_lambda_m, FINAL_NORMALISE, fo, scratch, part_d, tot_d);
+        const double* rank_rows = own_box + (long long)(par * G) * p.C * PL + (long long)c * PL;
+        if (G <= 32) {
+            if (wid == 0) mppi_combine_ranks_warp(rank_rows, (long long)p.C * PL, G, H, mi, nm, inv_lambda_m, fo);
+        } else {
+            mppi_merge_rows<BLOCK>(rank_rows, (long long)p.C * PL, G, H, mi, nm, inv_lambda_m, FINAL_NORMALISE, fo, scratch,
+                                   part_d, tot_d);
+        }
         MPCB_TS(5);
     }
 }
@@ -917,12 +1011,17 @@ __global__ void __launch_bounds__(BLOCK) mppi_combine_kernel(const MppiCombinePa
     o.info = p.info + c;
     o.info_host = p.info_host ? p.info_host + c : nullptr;
     o.out_row = nullptr;
+    o.copy_rows = nullptr; o.copy_offset = 0; o.n_copies = 0; o.copy_skip = -2;
     o.done_host = p.done_host;
     o.epoch = p.epoch;
     o.forced_status = MPCB_OK;
     o.ts = nullptr;
-    mppi_merge_rows<BLOCK>(p.rows + (long long)c * PL, (long long)p.C * PL, p.G, p.H, 0, 1, 1.0 / p.lambda, FINAL_NORMALISE, o,
-                           scratch, part, tot);
+    if (p.G <= 32) {
+        if (threadIdx.x < 32) mppi_combine_ranks_warp(p.rows + (long long)c * PL, (long long)p.C * PL, p.G, p.H, 0, 1, 1.0 / p.lambda, o);
+    } else {
+        mppi_merge_rows<BLOCK>(p.rows + (long long)c * PL, (long long)p.C * PL, p.G, p.H, 0, 1, 1.0 / p.lambda, FINAL_NORMALISE, o,
+                               scratch, part, tot);
+    }
 }
 
 // kernel entry table (defined in mppi_f32*.cu / mppi_f64.cu)
