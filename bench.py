@@ -47,6 +47,10 @@ FLOPS_PER_STEP = 60.0  # model NL 58 + 2 epilogue flops per roll
 UKF_B = 1 << 20
 UKF_T = 50
 UKF_BYTES = 336.0  # 8*(2n + 2n^2 + o), n=4, o=2
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures of these kernels
+# (profiles/mppi_r1_final_ncu_full_summary.txt, profiles/ukf_r1_final_ncu_full_summary.txt)
+MPPI_DRAM_TRAFFIC_BYTES = 83_968 + 0
+UKF_DRAM_TRAFFIC_BYTES = 188_768_000 + 112_360_448
 FP32_FALLBACK_TFLOPS = 69.5  # tools/peak_bench on this pool's B200 (profiles/peaks_r1.json)
 FP64_FALLBACK_TFLOPS = 33.9
 METRIC = "mppi_rollout_steps_per_sec"
@@ -356,16 +360,18 @@ def run_gpu(args):
     peaks = measured_peaks()
     ach_tflops = K_PER_GPU * H * FLOPS_PER_STEP / (kern_ms * 1e-3) / 1e12
     roof = {
-        "bound": "fp32", "kernel": "mppi_rollout_kernel<ModelNL,float,128,generate>",
+        "bound": "fp32", "kernel": "mppi_rollout_kernel<ModelNL,float,512,generate>",
         "achieved": ach_tflops, "peak": peaks["fp32_tflops"], "unit": "TFLOP/s", "frac": ach_tflops / peaks["fp32_tflops"],
-        "traffic": None, "kernel_ms": kern_ms,
+        "traffic": MPPI_DRAM_TRAFFIC_BYTES, "kernel_ms": kern_ms,
         "note": f"{FLOPS_PER_STEP:.0f} algorithmic FP32 flops per rollout-step (SURVEY.md 8d) x {K_PER_GPU * H} steps per launch; "
-                f"peak = {peaks['fp32_source']}; HBM traffic is O(blocks*H) partial rows, not a bound",
+                f"peak = {peaks['fp32_source']}; neither 'hbm' nor 'tensor' bounds this kernel: it issues FP32/MUFU "
+                "instructions and moves 84 KB of DRAM per launch (traffic, bytes, ncu); kernel_ms = back-to-back launches "
+                "without the L2 flush" + ("; at N > 1 it includes the in-kernel cross-GPU exchange" if world > 1 else ""),
     }
     if ukf_out and "value" in ukf_out:
         gbs = ukf_out["value"] / world * UKF_BYTES / 1e9
         ukf_out["roofline"] = {"bound": "hbm", "kernel": "ukf_kernel<4,2,PEN_LIN,cholesky,interleaved,fused>", "achieved": gbs,
-                               "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+                               "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": UKF_DRAM_TRAFFIC_BYTES,
                                "note": f"{UKF_BYTES:.0f} algorithmic bytes per filter-update; peak = {peaks['hbm_source']}; "
                                        f"FP64 pipe peak {peaks['fp64_tflops']:.1f} TFLOP/s ({peaks['fp32_source']})"}
     cpu_val, cpu_info = cpu_baseline(3, 1, budget_s=15.0) if world == 1 else (None, None)
