@@ -20,6 +20,8 @@ struct mpcb_mppi {
     int H = 0, C = 0, PL = 0;
     int block = 0, chunks = 0, group_size = 0, groups = 0;
     int Hp = 8, lgHp = 3;
+    int spt = 1;            // samples per thread (2: packed f32x2 kernels)
+    int block_samples = 0;  // samples per block and batch = block * spt
     int mergers = 0;        // blocks sharing the final merge (0: last arriver merges alone)
     unsigned int seq = 0;   // launches so far (arrival counters are monotonic)
     long long W = 0;  // warps of 32 samples in K_local
@@ -109,65 +111,101 @@ mpcb_status pick_kernels(mpcb_mppi* h) {
     const size_t smem_max = prop.sharedMemPerBlockOptin;
     h->Hp = mppi_pow2_horizon(h->H, &h->lgHp);
     h->W = (h->K_local + 31) / 32;
-    auto smem_of = [&](int b) { return f64 ? mppi_smem_bytes<double>(h->H, b) : mppi_smem_bytes<float>(h->H, b); };
-    auto kernel_of = [&](int b, int noise) {
-        return f64 ? mppi_kernel_f64(h->cfg.model_id, b, noise) : mppi_kernel_f32(h->cfg.model_id, b, noise);
-    };
-    auto fits = [&](int b) { return kernel_of(b, NOISE_GENERATE) != nullptr && smem_of(b) + 1024 <= smem_max; };
 
-    long long chunks1 = h->num_sms / h->C;
-    if (chunks1 < 1) chunks1 = 1;
-    if (chunks1 > h->W) chunks1 = h->W;
-    const long long wpc = (h->W + chunks1 - 1) / chunks1;  // warps per range if there is about one block per SM
-    int block = 0;
-    bool single_batch = false;
-    const char* force = getenv("MPCB_MPPI_BLOCK");  // developer override
-    if (force && fits(atoi(force))) {
-        block = atoi(force);
-    } else {
-        for (int b : {128, 256, 512}) {
-            if (wpc * 32 <= b && fits(b)) {
-                block = b;
-                single_batch = true;
-                break;
-            }
-        }
-        if (block == 0) {
-            for (int b : {128, 64, 32}) {
-                if (fits(b)) {
-                    block = b;
+    struct Plan {
+        int spt = 1, sb = 0, block = 0, occ = 0;
+        size_t smem = 0;
+        bool single_batch = false;
+        long long chunks = 0;
+        double warps_per_sm = 0.0;  // resident thread-warps per SM while the rollouts run
+        MppiKernelFn k[3] = {nullptr, nullptr, nullptr};
+    };
+    // Everything is in SAMPLES per block (sb); the block has sb / spt threads.
+    auto make_plan = [&](int spt, Plan* out) -> mpcb_status {
+        Plan pl;
+        pl.spt = spt;
+        auto smem_of = [&](int sb) { return f64 ? mppi_smem_bytes<double>(h->H, sb) : mppi_smem_bytes<float>(h->H, sb); };
+        auto kernel_of = [&](int sb, int noise) -> MppiKernelFn {
+            if (sb % spt) return nullptr;
+            if (f64) return mppi_kernel_f64(h->cfg.model_id, sb, noise);
+            return spt == 2 ? mppi_kernel_f32x2(h->cfg.model_id, sb / 2, noise) : mppi_kernel_f32(h->cfg.model_id, sb, noise);
+        };
+        auto fits = [&](int sb) { return kernel_of(sb, NOISE_GENERATE) != nullptr && smem_of(sb) + 1024 <= smem_max; };
+        long long chunks1 = h->num_sms / h->C;
+        if (chunks1 < 1) chunks1 = 1;
+        if (chunks1 > h->W) chunks1 = h->W;
+        const long long wpc = (h->W + chunks1 - 1) / chunks1;  // warps per range if there is about one block per SM
+        const char* force = getenv("MPCB_MPPI_BLOCK");  // developer override (samples per block)
+        if (force && fits(atoi(force))) {
+            pl.sb = atoi(force);
+        } else {
+            for (int b : {128, 256, 512}) {
+                if (wpc * 32 <= b && fits(b)) {
+                    pl.sb = b;
+                    pl.single_batch = true;
                     break;
                 }
             }
+            if (pl.sb == 0) {
+                for (int b : {128, 64, 32}) {
+                    if (fits(b)) {
+                        pl.sb = b;
+                        break;
+                    }
+                }
+            }
         }
-    }
-    if (block == 0) {
-        set_error("horizon %d needs more shared memory than one SM has", h->H);
-        return MPCB_BAD_ARG;
-    }
-    h->block = block;
-    h->smem = smem_of(block);
-    for (int noise = 0; noise < 3; ++noise) {
-        h->k_noise[noise] = kernel_of(block, noise);
-        if (!h->k_noise[noise]) {
-            set_error("no MPPI kernel for model %d", h->cfg.model_id);
+        if (pl.sb == 0) {
+            set_error("horizon %d needs more shared memory than one SM has", h->H);
             return MPCB_BAD_ARG;
         }
-        MPCB_CUDA_TRY(cudaFuncSetAttribute((const void*)h->k_noise[noise], cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)h->smem));
+        pl.block = pl.sb / spt;
+        pl.smem = smem_of(pl.sb);
+        for (int noise = 0; noise < 3; ++noise) {
+            pl.k[noise] = kernel_of(pl.sb, noise);
+            if (!pl.k[noise]) {
+                set_error("no MPPI kernel for model %d", h->cfg.model_id);
+                return MPCB_BAD_ARG;
+            }
+            MPCB_CUDA_TRY(cudaFuncSetAttribute((const void*)pl.k[noise], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        }
+        MPCB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pl.occ, (const void*)pl.k[NOISE_GENERATE], pl.block, pl.smem));
+        if (pl.occ < 1) pl.occ = 1;
+        if (pl.single_batch) {
+            pl.chunks = (h->W + wpc - 1) / wpc;  // ranges of wpc or wpc-1 warps, none empty
+            pl.warps_per_sm = (double)((wpc + spt - 1) / spt) * h->C * pl.chunks / h->num_sms;
+        } else {
+            pl.chunks = (long long)pl.occ * h->num_sms / h->C;
+            const long long nbatches = (h->W * 32 + pl.sb - 1) / pl.sb;
+            if (pl.chunks > nbatches) pl.chunks = nbatches;
+            if (pl.chunks < 1) pl.chunks = 1;
+            double blocks_per_sm = (double)h->C * pl.chunks / h->num_sms;
+            if (blocks_per_sm > pl.occ) blocks_per_sm = pl.occ;
+            pl.warps_per_sm = blocks_per_sm * (pl.block / 32.0);
+        }
+        *out = pl;
+        return MPCB_OK;
+    };
+    // FP32: two samples per thread with packed f32x2 arithmetic take ~30 % fewer issue slots per sample, but halve
+    // the warps.  They win when the SM still holds >= 8 warps (short horizons, many controllers: +35 % on the
+    // config-#4 shape) and lose when the rollout is starved for warps (K = 65536 x H = 100 on 148 SMs has 14
+    // sample-warps per SM; H = 200 fits 9) — there the scalar kernels run.  MPCB_MPPI_SPT=1/2 forces one.
+    Plan plan;
+    mpcb_status st = make_plan(1, &plan);
+    if (st != MPCB_OK) return st;
+    if (!f64) {
+        const char* spt_env = getenv("MPCB_MPPI_SPT");
+        const int forced = spt_env ? atoi(spt_env) : 0;
+        Plan p2;
+        if (forced != 1 && make_plan(2, &p2) == MPCB_OK && (forced == 2 || p2.warps_per_sm >= 8.0)) plan = p2;
     }
-    long long chunks;
-    if (single_batch) {
-        chunks = (h->W + wpc - 1) / wpc;  // ranges of wpc or wpc-1 warps, none empty
-    } else {
-        int occ = 0;
-        MPCB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)h->k_noise[NOISE_GENERATE], block, h->smem));
-        if (occ < 1) occ = 1;
-        chunks = (long long)occ * h->num_sms / h->C;
-        const long long nbatches = (h->W * 32 + block - 1) / block;
-        if (chunks > nbatches) chunks = nbatches;
-        if (chunks < 1) chunks = 1;
-    }
+    h->spt = plan.spt;
+    const int block = plan.block;  // threads
+    h->block = block;
+    h->block_samples = plan.sb;
+    h->smem = plan.smem;
+    for (int noise = 0; noise < 3; ++noise) h->k_noise[noise] = plan.k[noise];
+    long long chunks = plan.chunks;
     if (chunks > (long long)kMergeFan * kMergeFan) chunks = (long long)kMergeFan * kMergeFan;
     h->chunks = (int)chunks;
     // designated mergers (first blocks of a controller wait for the arrival counters) only when the whole launch

@@ -1,0 +1,6 @@
+// mppi_f32x2_NL.cu — FP32 fast path with two samples per thread and packed f32x2 arithmetic (f32x2.cuh), model NL.
+#define MPCB_INST_MODEL ModelNL
+#define MPCB_INST_REAL float
+#define MPCB_INST_FN mppi_kernel_f32x2_NL
+#define MPCB_INST_SPT 2
+#include "mppi_inst.cuh"

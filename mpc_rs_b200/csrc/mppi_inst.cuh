@@ -5,16 +5,21 @@
 
 namespace mpcb {
 
+#ifndef MPCB_INST_SPT
+#define MPCB_INST_SPT 1
+#endif
+
 template <int BLOCK>
 static MppiKernelFn inst_pick_noise(int noise) {
     switch (noise) {
-        case NOISE_GENERATE: return mppi_rollout_kernel<MPCB_INST_MODEL, MPCB_INST_REAL, BLOCK, NOISE_GENERATE>;
-        case NOISE_GENERATE_DUMP: return mppi_rollout_kernel<MPCB_INST_MODEL, MPCB_INST_REAL, BLOCK, NOISE_GENERATE_DUMP>;
-        case NOISE_REPLAY: return mppi_rollout_kernel<MPCB_INST_MODEL, MPCB_INST_REAL, BLOCK, NOISE_REPLAY>;
+        case NOISE_GENERATE: return mppi_rollout_kernel<MPCB_INST_MODEL, MPCB_INST_REAL, BLOCK, NOISE_GENERATE, MPCB_INST_SPT>;
+        case NOISE_GENERATE_DUMP: return mppi_rollout_kernel<MPCB_INST_MODEL, MPCB_INST_REAL, BLOCK, NOISE_GENERATE_DUMP, MPCB_INST_SPT>;
+        case NOISE_REPLAY: return mppi_rollout_kernel<MPCB_INST_MODEL, MPCB_INST_REAL, BLOCK, NOISE_REPLAY, MPCB_INST_SPT>;
         default: return nullptr;
     }
 }
 
+// `block` = threads per block; a block covers block * MPCB_INST_SPT samples per batch
 MppiKernelFn MPCB_INST_FN(int block, int noise) {
     switch (block) {
 #ifdef MPCB_INST_BLOCK512

@@ -519,6 +519,32 @@ struct RealTraits<double> {
     static constexpr bool kExact = true;
 };
 
+// arithmetic type of the rollout: the storage type, or two packed FP32 samples per thread (SPT = 2)
+template <typename real, int SPT>
+struct ArithT {
+    using type = real;
+};
+template <>
+struct ArithT<float, 2> {
+    using type = f2;
+};
+
+// Warp max of v over the lanes with `has`, and the smallest idx among the lanes holding that max.
+__device__ __forceinline__ void warp_max_minidx(double v, long long idx, bool has, double* vmax, long long* imin) {
+    const unsigned int full = 0xffffffffu;
+    double wm;
+    long long wa;
+    int dummy;
+    warp_argmax(v, idx, has, &wm, &wa, &dummy);
+    const bool holds = has && v == wm;
+    const unsigned int ahi = holds ? (unsigned int)((unsigned long long)idx >> 32) : 0xffffffffu;
+    const unsigned int mh = __reduce_min_sync(full, ahi);
+    const unsigned int alo = (holds && ahi == mh) ? (unsigned int)idx : 0xffffffffu;
+    const unsigned int ml = __reduce_min_sync(full, alo);
+    *vmax = wm;
+    *imin = (wa == kNoArg) ? kNoArg : (long long)(((unsigned long long)mh << 32) | ml);
+}
+
 __host__ __device__ inline int mppi_pow2_horizon(int H, int* lg) {
     int hp = 8, l = 3;
     while (hp < H) { hp <<= 1; ++l; }
@@ -561,24 +587,29 @@ __device__ __forceinline__ float fast_exp_neg(double a) {
     return r;
 }
 
-template <template <typename> class ModelT, typename real, int BLOCK, int NOISE>
+// SPT = samples per thread.  SPT = 2 (FP32 only) packs the two samples' FP32 arithmetic into f32x2 instructions
+// (f32x2.cuh): thread tid of a batch owns samples tid and BLOCK + tid of the batch's SB = 2*BLOCK samples.
+template <template <typename> class ModelT, typename real, int BLOCK, int NOISE, int SPT>
 __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_constant__ MppiParams p) {
+    static_assert(SPT == 1 || (SPT == 2 && sizeof(real) == 4), "two samples per thread is an FP32 layout");
     constexpr int NW = BLOCK / 32;
-    constexpr int LD = BLOCK + 4;
+    constexpr int SB = BLOCK * SPT;  // samples per batch
+    constexpr int LD = SB + 4;
     constexpr bool kExact = RealTraits<real>::kExact;
     constexpr bool kReplay = (NOISE == NOISE_REPLAY);
+    using areal = typename ArithT<real, SPT>::type;
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int H = p.H, Hp = p.Hp, lgHp = p.lgHp;
     const int H4a = (H + 3) & ~3;
     double* scratch = reinterpret_cast<double*>(smem_raw);           // [kScratchDoubles] (even)
     double* part_d = scratch + kScratchDoubles;                      // [mppi_part_doubles] (even): 16-byte aligned
     real* part_r = reinterpret_cast<real*>(part_d);
-    double* U_run = part_d + mppi_part_doubles(H, BLOCK);            // [H]
-    const int ndbl = (H + kScratchDoubles + (int)mppi_part_doubles(H, BLOCK) + 3) & ~3;
+    double* U_run = part_d + mppi_part_doubles(H, SB);               // [H]
+    const int ndbl = (H + kScratchDoubles + (int)mppi_part_doubles(H, SB) + 3) & ~3;
     real* su = reinterpret_cast<real*>(scratch + ndbl);              // [H4a]  u_n (16-byte aligned rows from here on)
     real* sui = su + H4a;                                            // [H4a]  u_n * sigma^-2
-    real* w_s = sui + H4a;                                           // [BLOCK]
-    real* v_s = w_s + BLOCK;                                         // [H][LD]
+    real* w_s = sui + H4a;                                           // [SB]
+    real* v_s = w_s + SB;                                            // [H][LD]
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int c = blockIdx.x / p.chunks;      // controller
@@ -591,7 +622,7 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
         p.debug_ts[(size_t)blockIdx.x * 16 + 6] = smid + 1;
     }
     // ---- prologue: model constants, x0, u_n ----
-    ModelT<real> model;
+    ModelT<areal> model;
     model.load(p.mc);
     real x0[4];
     if (p.use_inline) {
@@ -625,27 +656,33 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
     int* red_n = (int*)(scratch + 32);              // [16]
     double* red_s = scratch + 48;                   // [24]: [0..15] warp sums, [16] rescale
 
-    // this block's range of whole warps, walked in batches of NW warps
+    // this block's range of whole warps (of 32 samples), walked in batches of NW*SPT warps
     const long long w_begin = p.W * chunk / p.chunks;
     const long long w_end = p.W * (chunk + 1) / p.chunks;
     __syncthreads();
 
-    for (long long wb = w_begin; wb < w_end; wb += NW) {
-        const long long gw = wb + wid;         // this warp's index in the controller's sample range
-        const bool warp_live = gw < w_end;     // whole warps beyond the range skip the rollout
-        const long long kl = gw * 32 + lane;   // local sample index
-        const bool valid = warp_live && kl < p.K_local;
-        const long long kg = p.k_offset + kl;  // global sample index (Philox counter / replay row / argmax)
+    for (long long wb = w_begin; wb < w_end; wb += NW * SPT) {
+        // sample s of this thread lives in sample-warp wb + s*NW + wid (column s*BLOCK + tid of the batch)
+        long long kl[SPT], kg[SPT];  // local / global sample index (global: Philox counter, replay row, argmax)
+        bool live[SPT], valid[SPT];  // whole warps beyond the range skip the rollout
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) {
+            const long long gw = wb + (long long)s * NW + wid;
+            live[s] = gw < w_end;
+            kl[s] = gw * 32 + lane;
+            valid[s] = live[s] && kl[s] < p.K_local;
+            kg[s] = p.k_offset + kl[s];
+        }
 
         if constexpr (kReplay) {
             // coalesced tile load: the batch's consecutive sample rows of H values -> v_s[t][k]
             const long long k_first = wb * 32;
             long long nrows = (w_end - wb) * 32;
-            if (nrows > BLOCK) nrows = BLOCK;
+            if (nrows > SB) nrows = SB;
             if (nrows > p.K_local - k_first) nrows = p.K_local - k_first;
             const long long base = ((long long)c * p.K_global + p.k_offset + k_first) * H;
-            const int live = (int)nrows * H;
-            for (int i = tid; i < live; i += BLOCK) {
+            const int n_live = (int)nrows * H;
+            for (int i = tid; i < n_live; i += BLOCK) {
                 const real e = p.eps_f64 ? (real) reinterpret_cast<const double*>(p.eps)[base + i]
                                          : (real) reinterpret_cast<const float*>(p.eps)[base + i];
                 const int kr = i / H, t = i - kr * H;
@@ -654,22 +691,20 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
             __syncthreads();
         }
 
-        double ck = -CUDART_INF;
-        if (warp_live) {
+        double ck[SPT];
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) ck[s] = -CUDART_INF;
+        if (live[0]) {  // live[1] implies live[0]
             // ---- PASS 1+2: noise, clamp, rollout, cost ----
-            real x[4] = {x0[0], x0[1], x0[2], x0[3]};
-            double J = 0.0, CT = 0.0;
-            real cw = (real)0, cu = (real)0;
-            const unsigned int c0 = (unsigned int)(kg & 0xffffffffll);
-            const unsigned int khi = (unsigned int)((kg >> 32) & 0xffff) << 16;
             real* vcol = v_s + tid;
-
-            // four N(0, sigma^2) draws for steps t0..t0+3
-            auto noise4 = [&](int t0, real(&e)[4]) {
+            // four N(0, sigma^2) draws of sample s for steps t0..t0+3
+            auto draw4 = [&](int s, int t0, real(&e)[4]) {
                 if constexpr (kReplay) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) e[i] = (valid && t0 + i < H) ? vcol[(t0 + i) * LD] : (real)0;
+                    for (int i = 0; i < 4; ++i) e[i] = (valid[s] && t0 + i < H) ? vcol[(t0 + i) * LD + s * BLOCK] : (real)0;
                 } else {
+                    const unsigned int c0 = (unsigned int)(kg[s] & 0xffffffffll);
+                    const unsigned int khi = (unsigned int)((kg[s] >> 32) & 0xffff) << 16;
                     const Philox4 r = philox4x32_10(c0, p.call_idx, (unsigned int)c, (unsigned int)(t0 >> 2) | khi,
                                                     p.seed_lo, p.seed_hi);
                     float z[4];
@@ -677,8 +712,8 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
 #pragma unroll
                     for (int i = 0; i < 4; ++i) e[i] = (real)z[i];
                     if constexpr (NOISE == NOISE_GENERATE_DUMP) {
-                        if (valid) {
-                            real* dump = reinterpret_cast<real*>(p.eps_dump) + ((long long)c * p.K_local + kl) * H;
+                        if (valid[s]) {
+                            real* dump = reinterpret_cast<real*>(p.eps_dump) + ((long long)c * p.K_local + kl[s]) * H;
 #pragma unroll
                             for (int i = 0; i < 4; ++i)
                                 if (t0 + i < H) dump[t0 + i] = e[i];
@@ -686,76 +721,147 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
                     }
                 }
             };
-            // one rollout step: v = clamp(u_n[t] + eps), x <- dynamics(x, v), cost, control term
-            auto step = [&](int t, real eps, real ut, real uit) {
-                real v = ut + eps;
-                if constexpr (kExact) v = clampr(v, lo, hi);  // f64::clamp, NaN stays NaN
-                else v = fminf(fmaxf(v, lo), hi);
-                vcol[t * LD] = v;
-                model.step(x, v);
-                if constexpr (kExact) {
-                    const real ct = model.cost(x);
-                    J = J + ct;      // :57 c + cost(x_n)
-                    CT += uit * v;   // :60 (u*inv)*v, summed in order
-                } else {
-                    cw = model.cost.acc(x, cw);
-                    cu = fmaf(uit, v, cu);
-                }
-            };
-
-            // Software pipeline: the noise of group g+1 (independent of the state) is drawn while group g rolls
-            // out, so the scheduler has Philox/Box-Muller work to fill the dependency stalls of the serial chain.
             const int H4 = H & ~3;
-            real e[4];
-            noise4(0, e);
-            for (int t0 = 0; t0 < H4; t0 += 4) {
-                real en[4], u4[4], ui4[4];
-                lds4(su + t0, u4);
-                lds4(sui + t0, ui4);
-                noise4(t0 + 4, en);  // the last prefetch (t0 + 4 >= H4) feeds the tail below or is discarded
+            double J[SPT], CT[SPT];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) step(t0 + i, e[i], u4[i], ui4[i]);
-                if constexpr (!kExact) {
-                    // FP32 partial sums are flushed into the FP64 accumulators every kFlushSteps steps
-                    if ((t0 & (kFlushSteps - 1)) == kFlushSteps - 4) {
-                        J += (double)cw;
-                        CT += (double)cu;
-                        cw = (real)0;
-                        cu = (real)0;
+            for (int s = 0; s < SPT; ++s) { J[s] = 0.0; CT[s] = 0.0; }
+
+            if constexpr (SPT == 1) {
+                real x[4] = {x0[0], x0[1], x0[2], x0[3]};
+                real cw = (real)0, cu = (real)0;
+                // one rollout step: v = clamp(u_n[t] + eps), x <- dynamics(x, v), cost, control term
+                auto step = [&](int t, real eps, real ut, real uit) {
+                    real v = ut + eps;
+                    if constexpr (kExact) v = clampr(v, lo, hi);  // f64::clamp, NaN stays NaN
+                    else v = fminf(fmaxf(v, lo), hi);
+                    vcol[t * LD] = v;
+                    model.step(x, v);
+                    if constexpr (kExact) {
+                        const real ct = model.cost(x);
+                        J[0] = J[0] + ct;   // :57 c + cost(x_n)
+                        CT[0] += uit * v;   // :60 (u*inv)*v, summed in order
+                    } else {
+                        cw = model.cost.acc(x, cw);
+                        cu = fmaf(uit, v, cu);
                     }
+                };
+                // Software pipeline: the noise of group g+1 (independent of the state) is drawn while group g rolls
+                // out, so the scheduler has Philox/Box-Muller work to fill the dependency stalls of the serial chain.
+                real e[4];
+                draw4(0, 0, e);
+                for (int t0 = 0; t0 < H4; t0 += 4) {
+                    real en[4], u4[4], ui4[4];
+                    lds4(su + t0, u4);
+                    lds4(sui + t0, ui4);
+                    draw4(0, t0 + 4, en);  // the last prefetch (t0 + 4 >= H4) feeds the tail below or is discarded
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) step(t0 + i, e[i], u4[i], ui4[i]);
+                    if constexpr (!kExact) {
+                        // FP32 partial sums are flushed into the FP64 accumulators every kFlushSteps steps
+                        if ((t0 & (kFlushSteps - 1)) == kFlushSteps - 4) {
+                            J[0] += (double)cw;
+                            CT[0] += (double)cu;
+                            cw = (real)0;
+                            cu = (real)0;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) e[i] = en[i];
                 }
+                if (H4 < H) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) e[i] = en[i];
-            }
-            if (H4 < H) {
+                    for (int i = 0; i < 3; ++i)
+                        if (H4 + i < H) step(H4 + i, e[i], su[H4 + i], sui[H4 + i]);
+                }
+                if constexpr (!kExact) {
+                    J[0] += (double)cw;  // whatever is left since the last flush
+                    CT[0] += (double)cu;
+                }
+            } else {
+                // two samples per thread, FP32 arithmetic packed (the second sample of a thread whose second warp is
+                // beyond the range rolls out harmlessly and gets weight 0)
+                f2 x[4] = {splat2(x0[0]), splat2(x0[1]), splat2(x0[2]), splat2(x0[3])};
+                f2 cw = splat2(0.0f), cu = splat2(0.0f);
+                auto step2 = [&](int t, f2 eps, float ut, float uit) {
+                    const f2 v = clamp2(add2(splat2(ut), eps), lo, hi);
+                    float vl, vh;
+                    un2(v, vl, vh);
+                    vcol[t * LD] = vl;
+                    vcol[t * LD + BLOCK] = vh;
+                    model.step(x, v);
+                    cw = model.cost.acc(x, cw);
+                    cu = fma2(splat2(uit), v, cu);
+                };
+                auto draw4x2 = [&](int t0, f2(&e)[4]) {
+                    float ea[4], eb[4];
+                    draw4(0, t0, ea);
+                    draw4(1, t0, eb);
 #pragma unroll
-                for (int i = 0; i < 3; ++i)
-                    if (H4 + i < H) step(H4 + i, e[i], su[H4 + i], sui[H4 + i]);
+                    for (int i = 0; i < 4; ++i) e[i] = mk2(ea[i], eb[i]);
+                };
+                auto flush = [&]() {
+                    float a, b;
+                    un2(cw, a, b);
+                    J[0] += (double)a;
+                    J[1] += (double)b;
+                    un2(cu, a, b);
+                    CT[0] += (double)a;
+                    CT[1] += (double)b;
+                    cw = splat2(0.0f);
+                    cu = splat2(0.0f);
+                };
+                f2 e[4];
+                draw4x2(0, e);
+                for (int t0 = 0; t0 < H4; t0 += 4) {
+                    f2 en[4];
+                    float u4[4], ui4[4];
+                    lds4(su + t0, u4);
+                    lds4(sui + t0, ui4);
+                    draw4x2(t0 + 4, en);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) step2(t0 + i, e[i], u4[i], ui4[i]);
+                    if ((t0 & (kFlushSteps - 1)) == kFlushSteps - 4) flush();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) e[i] = en[i];
+                }
+                if (H4 < H) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+                        if (H4 + i < H) step2(H4 + i, e[i], su[H4 + i], sui[H4 + i]);
+                }
+                flush();
             }
-            if constexpr (!kExact) {
-                J += (double)cw;  // whatever is left since the last flush
-                CT += (double)cu;
+#pragma unroll
+            for (int s = 0; s < SPT; ++s) {
+                ck[s] = -J[s] - CT[s];  // :61
+                if (p.costs != nullptr && valid[s]) p.costs[(long long)c * p.K_local + kl[s]] = ck[s];
             }
-            ck = -J - CT;  // :61
-            if (p.costs != nullptr && valid) p.costs[(long long)c * p.K_local + kl] = ck;
         }
 
         // ---- PASS 3: block max over finite c_k, lowest index on ties ----
-        const bool fin = valid && finite_f64(ck);
+        bool fin[SPT];
+        int nf_thread = 0;
+        double tm = -CUDART_INF;  // this thread's best finite sample (the lower index wins a tie)
+        long long ta = kNoArg;
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) {
+            fin[s] = valid[s] && finite_f64(ck[s]);
+            nf_thread += fin[s] ? 1 : 0;
+            if (fin[s] && (ta == kNoArg || ck[s] > tm)) { tm = ck[s]; ta = kg[s]; }
+        }
         double bm;
         long long ba;
-        int bn;
-        warp_argmax(ck, kg, fin, &bm, &ba, &bn);
+        warp_max_minidx(tm, ta, ta != kNoArg, &bm, &ba);
+        int bn = __reduce_add_sync(0xffffffffu, nf_thread);
         if (lane == 0) { red_m[wid] = bm; red_a[wid] = ba; red_n[wid] = bn; }
         __syncthreads();
         {
-            // every warp reduces the NW warp results again (lane l holds warp l's entry; warps are in index order)
+            // every warp reduces the NW warp results again (lane l holds warp l's entry)
             const bool has = lane < NW;
             const double wm = has ? red_m[lane] : -CUDART_INF;
             const long long wa = has ? red_a[lane] : kNoArg;
             const int wn = has ? red_n[lane] : 0;
-            int dummy;
-            warp_argmax(wm, wa, has && wa != kNoArg, &bm, &ba, &dummy);
+            warp_max_minidx(wm, wa, has && wa != kNoArg, &bm, &ba);
             bn = __reduce_add_sync(0xffffffffu, wn);
         }
         const double m_old = m_run;
@@ -763,27 +869,31 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
         nfin_run += bn;
 
         // ---- PASS 4-5: weights against the running max, rescale of what was accumulated so far ----
-        real w;
-        if constexpr (kExact) {
-            // reference semantics: exp((c - max)/lambda) for every sample, NaN/+inf poison the sums (:71-74);
-            // exp(a) is exactly 0 in f64 for a < -745.14, so skipping the call there is bit-identical
-            const double arg = (ck - m_run) / lambda;
-            if (!valid || ck == -CUDART_INF) w = 0.0;
-            else w = (arg < -746.0) ? 0.0 : exp(arg);
-        } else {
-            // FP32 rollouts can overflow where the f64 reference yields a huge finite cost whose weight
-            // underflows to exactly 0: non-finite costs get weight 0 here.
-            w = fin ? fast_exp_neg((ck - m_run) * inv_lambda) : 0.0f;
+        real wsum = (real)0;
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) {
+            real w;
+            if constexpr (kExact) {
+                // reference semantics: exp((c - max)/lambda) for every sample, NaN/+inf poison the sums (:71-74);
+                // exp(a) is exactly 0 in f64 for a < -745.14, so skipping the call there is bit-identical
+                const double arg = (ck[s] - m_run) / lambda;
+                if (!valid[s] || ck[s] == -CUDART_INF) w = 0.0;
+                else w = (arg < -746.0) ? 0.0 : exp(arg);
+            } else {
+                // FP32 rollouts can overflow where the f64 reference yields a huge finite cost whose weight
+                // underflows to exactly 0: non-finite costs get weight 0 here.
+                w = fin[s] ? fast_exp_neg((ck[s] - m_run) * inv_lambda) : 0.0f;
+            }
+            w_s[s * BLOCK + tid] = w;
+            wsum += w;
         }
-        w_s[tid] = w;
         {
-            real ws = w;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
-                if constexpr (kExact) ws += shfl_down_f64(ws, off);
-                else ws += __shfl_down_sync(0xffffffffu, ws, off);
+                if constexpr (kExact) wsum += shfl_down_f64(wsum, off);
+                else wsum += __shfl_down_sync(0xffffffffu, wsum, off);
             }
-            if (lane == 0) red_s[wid] = (double)ws;
+            if (lane == 0) red_s[wid] = (double)wsum;
         }
         if (tid == 0) red_s[16] = (m_old == -CUDART_INF) ? 0.0 : exp((m_old - m_run) / lambda);  // block-uniform rescale
         __syncthreads();
@@ -799,8 +909,8 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
         {
             int nq = BLOCK >> lgHp;
             if (nq < 1) nq = 1;
-            if (nq > BLOCK / 8) nq = BLOCK / 8;
-            const int kper = BLOCK / nq;
+            if (nq > SB / 8) nq = SB / 8;
+            const int kper = SB / nq;
             const int items = Hp * nq;
             for (int item = tid; item < items; item += BLOCK) {
                 const int t = item & (Hp - 1), q = item >> lgHp;
@@ -1027,6 +1137,7 @@ __global__ void __launch_bounds__(BLOCK) mppi_combine_kernel(const MppiCombinePa
 // kernel entry table (defined in mppi_f32*.cu / mppi_f64.cu)
 using MppiKernelFn = void (*)(const MppiParams);
 MppiKernelFn mppi_kernel_f32(int model_id, int block, int noise);
+MppiKernelFn mppi_kernel_f32x2(int model_id, int block, int noise);  // two samples per thread (block threads = 2*block samples)
 MppiKernelFn mppi_kernel_f64(int model_id, int block, int noise);
 
 }  // namespace mpcb
