@@ -464,12 +464,23 @@ static __device__ __noinline__ void mppi_combine_ranks_warp(const double* rows, 
         const bool live = j < npairs;
         const int pair = p_lo + j;
         double ax = 0.0, ay = 0.0;
-        for (int r = 0; r < G; ++r) {
-            const double fr = __hiloint2double(__shfl_sync(full, __double2hiint(sc), r), __shfl_sync(full, __double2loint(sc), r));
-            if (live) {
-                const double2 v = __ldcg(reinterpret_cast<const double2*>(rows + (long long)r * row_stride + 2 + 2 * pair));
-                ax += fr * v.x;
-                ay += fr * v.y;
+        for (int rb = 0; rb < G; rb += 8) {  // 8 rank rows at a time: all loads in flight before the first use
+            double2 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                v[i] = (live && rb + i < G)
+                           ? __ldcg(reinterpret_cast<const double2*>(rows + (long long)(rb + i) * row_stride + 2 + 2 * pair))
+                           : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (rb + i < G) {  // uniform
+                    const int r = rb + i;
+                    const double fr = __hiloint2double(__shfl_sync(full, __double2hiint(sc), r), __shfl_sync(full, __double2loint(sc), r));
+                    if (live) {
+                        ax += fr * v[i].x;
+                        ay += fr * v[i].y;
+                    }
+                }
             }
         }
         if (live) {

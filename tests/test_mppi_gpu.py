@@ -240,6 +240,46 @@ def test_peer_exchange_on_one_gpu(gpu_required):
         A.lib().mpcb_device_free(0, q)
 
 
+def test_peer_exchange_batched_controllers_odd_horizon(gpu_required):
+    """The same exchange with C = 3 controllers per handle (one mailbox slot and flag set per controller) and an odd
+    horizon (rows padded to a whole number of 16-byte column pairs), model L, G = 2 handles on one device."""
+    import ctypes as C
+    model, oid, _, dt, lam, sig, lim = CASES["L_shipped"]
+    H, K, G, NC = 7, 3001, 2, 3
+    rng = np.random.default_rng(32)
+    xs = rng.normal(0, 0.2, (NC, 4))
+    us = rng.uniform(-2, 2, (NC, H))
+    d = [C.c_void_p() for _ in range(2 + G)]
+    for q, n in zip(d, [32 * NC, 8 * H * NC] + [8 * H * NC] * G):
+        A.check(A.lib().mpcb_device_alloc(0, n, C.byref(q)))
+    A.check(A.lib().mpcb_device_upload(0, d[0], xs.ctypes.data_as(C.c_void_p), xs.nbytes))
+    A.check(A.lib().mpcb_device_upload(0, d[1], us.ctypes.data_as(C.c_void_p), us.nbytes))
+    for prec, tol in (("f64", 1e-12), ("f32", 2e-6)):
+        hs = [Mppi(H, K, model=model, lam=lam, std_dev=sig, limit=lim, precision=prec, dt=dt, rank=r, world_size=G, seed=9,
+                   controllers=NC) for r in range(G)]
+        handles = [h.peer_handle() for h in hs]
+        for h in hs:
+            h.attach_peers(handles)
+        with Mppi(H, K, model=model, lam=lam, std_dev=sig, limit=lim, precision=prec, dt=dt, seed=9, controllers=NC) as one:
+            for step in range(3):
+                u_one = one.compute(xs, us)
+                for r, h in enumerate(hs):
+                    h.compute_device(d[0].value, d[1].value, d[2 + r].value)
+                for r, h in enumerate(hs):
+                    h.sync()
+                    infos = h.last_info()
+                    out = np.empty((NC, H))
+                    A.check(A.lib().mpcb_device_download(0, out.ctypes.data_as(C.c_void_p), d[2 + r], out.nbytes))
+                    for c in range(NC):
+                        assert infos[c]["status"] == 0 and infos[c]["n_finite"] == K
+                        assert infos[c]["argmax"] == one.last_call_info()[c]["argmax"]
+                        assert rel_err(out[c], u_one[c]) < tol, (prec, step, r, c)
+        for h in hs:
+            h.close()
+    for q in d:
+        A.lib().mpcb_device_free(0, q)
+
+
 def test_launch_shapes(gpu_required):
     """Work split (mppi_kernel.cuh header): sample counts around the one-block-per-SM boundary, block sizes 128/256/512,
     ragged last warps, multi-batch ranges, many controllers — replay parity against the oracle for each."""
