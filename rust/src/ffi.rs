@@ -32,6 +32,14 @@ extern "C" {
     pub fn mpcb_ukf_predict(h: *mut MpcbUkf, u: *const f64, u_scalar: f64, dt: f64) -> i32;
     pub fn mpcb_ukf_update(h: *mut MpcbUkf, z: *const f64) -> i32;
     pub fn mpcb_ukf_get_status(h: *mut MpcbUkf, s: *mut i32) -> i32;
+    // per-packet sensor gating (examples/mppi4-ukf-commu.rs:228-236,279-293)
+    pub fn mpcb_ukf_set_enable(h: *mut MpcbUkf, enable: u32) -> i32;
+    pub fn mpcb_ukf_gen_r(h: *const MpcbUkf, enable: u32, r: *const f64, r_out: *mut f64) -> i32;
+    // multi-GPU: fused exchange over peer memory (128-byte handles gathered by the application) or NCCL
+    pub fn mpcb_mppi_peer_handle(h: *mut MpcbMppi, out: *mut std::os::raw::c_char) -> i32;
+    pub fn mpcb_mppi_attach_peers(h: *mut MpcbMppi, handles: *const std::os::raw::c_char) -> i32;
+    pub fn mpcb_comm_unique_id(id: *mut std::os::raw::c_char) -> i32;
+    pub fn mpcb_mppi_attach_comm(h: *mut MpcbMppi, id: *const std::os::raw::c_char) -> i32;
 }
 pub fn last_error() -> String {
     unsafe { std::ffi::CStr::from_ptr(mpcb_last_error_string()).to_string_lossy().into_owned() }

@@ -53,6 +53,9 @@ impl UnscentedKalmanFilter {
     pub fn set_q(&mut self, q: Cov<N>) { unsafe { ffi::mpcb_ukf_set_q(self.h, q.as_ptr()) }; }
     /// Called by examples/mppi4-ukf-commu.rs:280 and examples/mpc-ukf-commu.rs:334 but missing in the reference.
     pub fn set_r(&mut self, r: Cov<O>) { unsafe { ffi::mpcb_ukf_set_r(self.h, r.as_ptr()) }; }
+    /// The `hx` closure of examples/mppi4-ukf-commu.rs:279-293 zeroes the rows of sensors whose enable bit is 0; a
+    /// kernel cannot run that closure, so the mask is handed over instead (applies to the following `update`s).
+    pub fn set_enable(&mut self, enable: u8) { unsafe { ffi::mpcb_ukf_set_enable(self.h, enable as u32) }; }
 
     fn check(&self) {
         let mut s = 0i32;
