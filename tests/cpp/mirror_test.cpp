@@ -1,0 +1,125 @@
+// Parity of the C++ host mirror (include/mpc_b200.hpp) against the CPU oracle (oracle/, test infrastructure): written
+// the way a test of the reference crate would read — construct with the reference's constants, call compute /
+// predict / update, compare.  Built and run by tests/test_cpp_mirror.py (-m gpu); exits 0 and prints "mirror ok".
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <vector>
+
+#include "mpc_b200.hpp"
+#include "mpc_oracle.h"
+
+static int fails = 0;
+#define EXPECT(cond, ...)                          \
+    do {                                           \
+        if (!(cond)) {                             \
+            std::printf("FAIL %s:%d: ", __FILE__, __LINE__); \
+            std::printf(__VA_ARGS__);              \
+            std::printf("\n");                     \
+            ++fails;                               \
+        }                                          \
+    } while (0)
+
+template <std::size_t N>
+static double rel_err(const std::array<double, N>& a, const double* b) {
+    double num = 0, den = 0;
+    for (std::size_t i = 0; i < N; ++i) { num += (a[i] - b[i]) * (a[i] - b[i]); den += b[i] * b[i]; }
+    return std::sqrt(num) / std::sqrt(den > 0 ? den : 1e-300);
+}
+
+int main() {
+    using namespace mpc;
+    // ---- Mppi<8, 20000, 4>, model L, shipped constants (examples/mppi4.rs:8-18), 3 closed-loop steps on replayed noise
+    {
+        constexpr std::size_t N = 8, K = 20000;
+        auto m64 = mppi::Mppi<N, K, 4>::create(DeviceModel::L, DeviceModel::L, 0.5, 3.0, {-20.0, 20.0}, 0.0, MPCB_F64);
+        auto m32 = mppi::Mppi<N, K, 4>::create(DeviceModel::L, DeviceModel::L, 0.5, 3.0, {-20.0, 20.0});
+        mpcb_model_params p;
+        orc_model_defaults(MPCB_MODEL_L, &p);
+        std::mt19937_64 rng(7);
+        std::normal_distribution<double> nd(0.0, 3.0);
+        std::array<double, 4> x{0.5, 0.0, 0.1, 0.0};
+        std::array<double, N> u{};
+        std::vector<double> eps(K * N);
+        for (int step = 0; step < 3; ++step) {
+            for (auto& e : eps) e = nd(rng);
+            double u_ref[N];
+            orc_mppi_out info;
+            const int st = orc_mppi_compute(MPCB_MODEL_L, &p, K, N, 0.5, 3.0, -20.0, 20.0, x.data(), u.data(), eps.data(), u_ref, nullptr, &info);
+            EXPECT(st == 0, "oracle status %d", st);
+            const auto r64 = m64.compute_replay(x, u, eps.data());
+            const auto r32 = m32.compute_replay(x, u, eps.data());
+            EXPECT(r64.ok && r32.ok, "compute failed: %s", r64.ok ? r32.err : r64.err);
+            EXPECT(rel_err(r64.value, u_ref) < 1e-9, "f64 controls %.3e", rel_err(r64.value, u_ref));
+            EXPECT(rel_err(r32.value, u_ref) < 1e-5, "f32 controls %.3e", rel_err(r32.value, u_ref));
+            EXPECT(m64.info().argmax == info.argmax && m32.info().argmax == info.argmax, "argmin");
+            double xn[4];
+            orc_dynamics(MPCB_MODEL_L, &p, x.data(), u_ref[0], xn);
+            std::memcpy(x.data(), xn, sizeof(xn));
+            std::memcpy(u.data(), u_ref, sizeof(u_ref));
+        }
+        // generate mode returns a usable control (what examples/mppi4.rs:42 does with .unwrap())
+        const auto g = m32.compute(x, u).unwrap();
+        EXPECT(std::isfinite(g[0]) && std::fabs(g[0]) <= 20.0, "generate-mode control %f", g[0]);
+        // Err(&'static str): NaN state -> no finite cost -> "Cannot calculate max" (src/mppi.rs:69)
+        const auto bad = m64.compute({NAN, 0, 0, 0}, u);
+        EXPECT(!bad.ok && std::strcmp(bad.err, "Cannot calculate max") == 0, "error path: %s", bad.err ? bad.err : "(ok)");
+        bool threw = false;
+        try { bad.unwrap(); } catch (const std::runtime_error& e) { threw = std::strcmp(e.what(), "Cannot calculate max") == 0; }
+        EXPECT(threw, "unwrap() must throw the reference's message");
+    }
+    // ---- mpc::ukf::UnscentedKalmanFilter (n=4, o=3), examples/ukf-pen2.rs constants, 5 predict/update pairs vs the oracle
+    {
+        const std::array<double, 16> Q{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0.25};
+        const std::array<double, 9> R{100, 0, 0, 0, 100, 0, 0, 0, 0.5};
+        const std::array<double, 16> P0{10, 0, 0, 0, 0, 10, 0, 0, 0, 0, 10, 0, 0, 0, 0, 10};
+        auto f = ukf::UnscentedKalmanFilter::create({0, 0, 0, 0}, P0, Q, R, DeviceModel::PEN_NL);
+        mpcb_model_params p;
+        orc_model_defaults(MPCB_MODEL_PEN_NL, &p);
+        double xo[4] = {0, 0, 0, 0}, Po[16], sf[4 * 9];
+        std::memcpy(Po, P0.data(), sizeof(Po));
+        std::mt19937_64 rng(3);
+        std::normal_distribution<double> nd(0.0, 1.0);
+        for (int i = 0; i < 5; ++i) {
+            const std::array<double, 3> z{30 * nd(rng), 30 * nd(rng), 0.5 * nd(rng)};
+            EXPECT(orc_ukf_predict(MPCB_MODEL_PEN_NL, &p, 4, MPCB_SQRT_EIG, MPCB_ORDER_LIBRARY, xo, Po, Q.data(), 0.1, 0.0, sf) == 0, "oracle predict");
+            EXPECT(orc_ukf_update(MPCB_MODEL_PEN_NL, &p, 4, 3, xo, Po, R.data(), z.data(), sf) == 0, "oracle update");
+            f.predict(0.1, DeviceModel::PEN_NL);
+            f.update(z, DeviceModel::PEN_NL);
+            // the filters are re-synchronised every step: the sigma weights amplify rounding 1.7e5 x per step
+            EXPECT(rel_err(f.state(), xo) < 1e-6, "ukf state step %d: %.3e", i, rel_err(f.state(), xo));
+            EXPECT(rel_err(f.covariance(), Po) < 1e-6, "ukf covariance step %d: %.3e", i, rel_err(f.covariance(), Po));
+        }
+        bool threw = false;
+        try { f.predict(0.1, DeviceModel::PEN6); } catch (const std::invalid_argument&) { threw = true; }
+        EXPECT(threw, "a foreign fx model must be rejected");
+    }
+    // ---- mpc::ukf2 (n=6, o=5): set_q / set_r / set_enable / gen_r exist and a gated step runs
+    {
+        std::array<double, 36> Q{}, P0{};
+        std::array<double, 25> R{};
+        mpcb_ukf_default_noise(MPCB_MODEL_NL6_UKF, 0.01, Q.data(), R.data(), P0.data());
+        auto f = ukf2::UnscentedKalmanFilter::create({0, 0, 0, 0.05, 0, 0}, P0, Q, R);
+        f.set_q(Q);
+        const auto Rg = f.gen_r(0b10101, R);
+        EXPECT(Rg[6] == 1e6 && Rg[18] == 1e6 && Rg[0] == R[0], "gen_r");
+        f.set_r(Rg);
+        f.set_enable(0b10101);
+        f.predict(0.3, DeviceModel::NL6_UKF, 0.01);
+        f.update({10.0, 999.0, 1.0, 999.0, 0.0}, DeviceModel::NL6_UKF);
+        const auto x = f.state();
+        EXPECT(std::isfinite(x[0]) && std::isfinite(x[3]), "gated ukf2 step");
+    }
+    // ---- Gaussian (src/gaussian.rs)
+    {
+        using gaussian::Gaussian;
+        const Gaussian a = Gaussian::create(1.0, 4.0), b = Gaussian::create(3.0, 1.0);
+        const Gaussian s = a + b, d = a - b, m = a * b, k = a * 2.0, z{};
+        EXPECT(s.mean == 4.0 && s.var == 5.0 && d.mean == -2.0 && d.var == 3.0, "add/sub");
+        EXPECT(std::fabs(m.mean - (4.0 * 3.0 + 1.0 * 1.0) / 5.0) < 1e-15 && std::fabs(m.var - 0.8) < 1e-15, "product");
+        EXPECT(k.mean == 2.0 && k.var == 8.0 && z.mean == 0.0 && z.var == 0.0, "scale/default");
+    }
+    if (fails == 0) std::printf("mirror ok\n");
+    return fails == 0 ? 0 : 1;
+}
