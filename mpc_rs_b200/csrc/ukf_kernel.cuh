@@ -180,7 +180,7 @@ __device__ __forceinline__ bool chol_lower(double (&m)[N][N]) {
 
 // U*sqrt(S) of the SVD of a symmetric PSD matrix by cyclic Jacobi (src/ukf.rs:121-124); at most 10
 // row-cyclic sweeps, stops when every off-diagonal element is exactly zero.
-template <int N>
+template <int N, bool FAST = false>
 __device__ __forceinline__ void sym_eig_sqrt(double (&A)[N][N], double (&Lo)[N][N]) {
     double V[N][N];
 #pragma unroll
@@ -203,30 +203,71 @@ __device__ __forceinline__ void sym_eig_sqrt(double (&A)[N][N], double (&Lo)[N][
             for (int q = p + 1; q < N; ++q) {
                 const double apq = A[p][q];
                 if (apq != 0.0) {
-                    const double tau = (A[q][q] - A[p][p]) / (2.0 * apq);
-                    const double rt = sqrt(1.0 + tau * tau);
-                    const double t = (tau >= 0.0) ? 1.0 / (tau + rt) : -1.0 / (-tau + rt);
-                    const double c = 1.0 / sqrt(1.0 + t * t);
-                    const double s = t * c;
+                    if constexpr (!FAST) {
+                        // the oracle's operation order (two divisions, two square roots, full two-sided update)
+                        const double tau = (A[q][q] - A[p][p]) / (2.0 * apq);
+                        const double rt = sqrt(1.0 + tau * tau);
+                        const double t = (tau >= 0.0) ? 1.0 / (tau + rt) : -1.0 / (-tau + rt);
+                        const double c = 1.0 / sqrt(1.0 + t * t);
+                        const double s = t * c;
 #pragma unroll
-                    for (int k = 0; k < N; ++k) {
-                        const double akp = A[k][p], akq = A[k][q];
-                        A[k][p] = c * akp - s * akq;
-                        A[k][q] = s * akp + c * akq;
-                    }
+                        for (int k = 0; k < N; ++k) {
+                            const double akp = A[k][p], akq = A[k][q];
+                            A[k][p] = c * akp - s * akq;
+                            A[k][q] = s * akp + c * akq;
+                        }
 #pragma unroll
-                    for (int k = 0; k < N; ++k) {
-                        const double apk = A[p][k], aqk = A[q][k];
-                        A[p][k] = c * apk - s * aqk;
-                        A[q][k] = s * apk + c * aqk;
-                    }
-                    A[p][q] = 0.0;
-                    A[q][p] = 0.0;
+                        for (int k = 0; k < N; ++k) {
+                            const double apk = A[p][k], aqk = A[q][k];
+                            A[p][k] = c * apk - s * aqk;
+                            A[q][k] = s * apk + c * aqk;
+                        }
+                        A[p][q] = 0.0;
+                        A[q][p] = 0.0;
 #pragma unroll
-                    for (int k = 0; k < N; ++k) {
-                        const double vkp = V[k][p], vkq = V[k][q];
-                        V[k][p] = c * vkp - s * vkq;
-                        V[k][q] = s * vkp + c * vkq;
+                        for (int k = 0; k < N; ++k) {
+                            const double vkp = V[k][p], vkq = V[k][q];
+                            V[k][p] = c * vkp - s * vkq;
+                            V[k][q] = s * vkp + c * vkq;
+                        }
+                    } else {
+                        // same rotation with reciprocals / reciprocal square roots (MUFU seed + Newton instead of the
+                        // IEEE division and sqrt sequences) and the symmetric update: only rows/columns p and q of the
+                        // other indices change, the 2x2 block in closed form (a_pp -= t a_pq, a_qq += t a_pq, a_pq = 0)
+                        const double diff = A[q][q] - A[p][p];
+                        // equal diagonal entries rotate by 45 degrees (tau = 0) whatever the size of a_pq, like the
+                        // division does; a_pq so small that tau overflows means t = 1/(2 tau) (and 0 * inf never forms)
+                        const double tau = (diff == 0.0) ? 0.0 : diff * (0.5 * __drcp_rn(apq));
+                        const double at = fabs(tau);
+                        double t;
+                        if (at < 1e150) {
+                            const double w = fma(tau, tau, 1.0);
+                            const double rt = w * rsqrt(w);  // sqrt(1 + tau^2)
+                            t = copysign(__drcp_rn(at + rt), tau);
+                        } else {
+                            t = 0.5 * __drcp_rn(tau);
+                        }
+                        const double c = rsqrt(fma(t, t, 1.0));
+                        const double s = t * c;
+#pragma unroll
+                        for (int k = 0; k < N; ++k) {
+                            if (k != p && k != q) {
+                                const double akp = A[k][p], akq = A[k][q];
+                                const double np_ = c * akp - s * akq, nq_ = s * akp + c * akq;
+                                A[k][p] = np_; A[p][k] = np_;
+                                A[k][q] = nq_; A[q][k] = nq_;
+                            }
+                        }
+                        A[p][p] -= t * apq;
+                        A[q][q] += t * apq;
+                        A[p][q] = 0.0;
+                        A[q][p] = 0.0;
+#pragma unroll
+                        for (int k = 0; k < N; ++k) {
+                            const double vkp = V[k][p], vkq = V[k][q];
+                            V[k][p] = c * vkp - s * vkq;
+                            V[k][q] = s * vkp + c * vkq;
+                        }
                     }
                 }
             }
@@ -452,7 +493,7 @@ __global__ void __launch_bounds__(128) ukf_kernel(const __grid_constant__ UkfPar
                 for (int r = 0; r < N; ++r)
 #pragma unroll
                     for (int c = 0; c < N; ++c) cp[r][c] = p.cC * P[r][c];
-                sym_eig_sqrt<N>(cp, Lm);
+                sym_eig_sqrt<N, FAST>(cp, Lm);
             }
             if (!ok) { st = MPCB_CHOLESKY_FAIL; break; }
 #pragma unroll
