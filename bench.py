@@ -73,8 +73,10 @@ def workload(n_gpus: int) -> dict:
 
 
 # ---- reference arm / cpu baseline ---------------------------------------------------------------------------
-def cpu_baseline(steps: int, warmup: int, budget_s: float = 20.0):
-    """Times the CPU restatement (oracle/) of src/mppi.rs:38-91 on all host cores.  Returns (steps/s, info)."""
+def cpu_baseline(steps, warmup: int, budget_s: float = 12.0):
+    """Times the CPU restatement (oracle/) of src/mppi.rs:38-91 on all host cores: full-size control steps of the bench
+    workload (K = 65536, H = 100), closed loop.  steps=None runs as many as fit in about budget_s seconds of CPU work
+    (the bounded sample); an explicit step count is capped by the same budget.  Returns (rollout-steps/s, info)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
     threads = O.max_threads()
@@ -84,8 +86,8 @@ def cpu_baseline(steps: int, warmup: int, budget_s: float = 20.0):
     t0 = time.perf_counter()
     O.mppi_compute_cpu(O.MODEL_NL, p, K, H, LAMBDA, SIGMA, LIMIT[0], LIMIT[1], X0, u, seed=1, threads=threads)
     one = time.perf_counter() - t0
-    if steps * one > budget_s:  # keep the run bounded: fewer samples per step, same H
-        K = max(4096, int(K * budget_s / (steps * one)) // 1024 * 1024)
+    fit = max(3, int(budget_s / max(one, 1e-6)))
+    steps = fit if steps is None else max(1, min(int(steps), fit))
     for i in range(warmup):
         O.mppi_compute_cpu(O.MODEL_NL, p, K, H, LAMBDA, SIGMA, LIMIT[0], LIMIT[1], X0, u, seed=2 + i, threads=threads)
     x, t0 = X0.copy(), time.perf_counter()
@@ -94,10 +96,10 @@ def cpu_baseline(steps: int, warmup: int, budget_s: float = 20.0):
                                       threads=threads)
     el = time.perf_counter() - t0
     return K * H * steps / el, {
-        "kind": "port", "cores": threads,
-        "sample": f"{steps} control steps of K={K} x H={H} (model NL) through oracle/ orc_mppi_compute_cpu: "
-                  "materialised v[K][H], six passes, xoshiro256+/ziggurat per worker, f64, -O3 -march=native "
-                  "-ffp-contract=off; C restatement of the nalgebra/rayon path, not the Rust binary",
+        "kind": "port", "cores": threads, "steps": steps,
+        "sample": f"{steps} control steps ({el:.1f} s of wall time on {threads} threads) of K={K} x H={H} (model NL) through "
+                  "oracle/ orc_mppi_compute_cpu: materialised v[K][H], six passes, xoshiro256+/ziggurat per worker, f64, "
+                  "-O3 -march=native -ffp-contract=off; C restatement of the nalgebra/rayon path, not the Rust binary",
         "ms_per_step": el / steps * 1e3,
     }
 
@@ -106,8 +108,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    steps = min(args.steps, 50)
-    val, info = cpu_baseline(steps, min(args.warmup, 3), budget_s=90.0)
+    val, info = cpu_baseline(args.steps, min(args.warmup, 3), budget_s=120.0)  # every step is a full-size control step
+    steps = info["steps"]
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": min(args.warmup, 3), "ms_per_step": info["ms_per_step"], "higher_is_better": True,
@@ -374,7 +376,7 @@ def run_gpu(args):
                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": UKF_DRAM_TRAFFIC_BYTES,
                                "note": f"{UKF_BYTES:.0f} algorithmic bytes per filter-update; peak = {peaks['hbm_source']}; "
                                        f"FP64 pipe peak {peaks['fp64_tflops']:.1f} TFLOP/s ({peaks['fp32_source']})"}
-    cpu_val, cpu_info = cpu_baseline(3, 1, budget_s=15.0) if world == 1 else (None, None)
+    cpu_val, cpu_info = cpu_baseline(None, 2, budget_s=12.0) if world == 1 else (None, None)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -16,13 +16,15 @@ from mpc_rs_b200.closed_loop import ClosedLoopBatch  # noqa: E402
 from mpc_rs_b200.csvlog import MppiUkfLog  # noqa: E402
 
 
-def run(controllers=4096, samples=8192, seconds=3.0, truth=False, csv="logs/mppi/mppi.csv", quiet=False, seed=20240004):
+def run(controllers=4096, samples=8192, seconds=3.0, truth=False, csv="logs/mppi/mppi.csv", quiet=False, seed=20240004,
+        precision=None):
     rng = np.random.default_rng(seed)
     x0 = np.zeros((controllers, 6))
     x0[:, 3] = rng.uniform(-0.1, 0.1, controllers)  # theta0 ~ U(-0.1, 0.1); the example starts at 0
     x0[0, 3] = 0.0
     t0 = time.perf_counter()
-    with ClosedLoopBatch(controllers, samples, use_estimate=not truth, seed=seed, x0=x0) as loop, MppiUkfLog(csv) as log:
+    with ClosedLoopBatch(controllers, samples, use_estimate=not truth, seed=seed, x0=x0, precision=precision) as loop, \
+            MppiUkfLog(csv) as log:
         next_log = 0.0
         while loop.t < seconds:
             loop.tick()
@@ -54,5 +56,7 @@ if __name__ == "__main__":
     ap.add_argument("--seconds", type=float, default=3.0)
     ap.add_argument("--truth", action="store_true", help="DEBUG_UKF = true: feed the controller the true state")
     ap.add_argument("--csv", default="logs/mppi/mppi.csv")
+    ap.add_argument("--precision", choices=["f32", "f64"], default=None,
+                    help="MPPI arithmetic; default f64 for this model (DESIGN.md 4.1 precision policy), f32 is ~20x faster")
     a = ap.parse_args()
-    run(a.controllers, a.samples, a.seconds, a.truth, a.csv)
+    run(a.controllers, a.samples, a.seconds, a.truth, a.csv, precision=a.precision)
