@@ -149,6 +149,18 @@ __device__ __forceinline__ void ukf_hx(const ModelConsts& mc, const double (&x)[
     }
 }
 
+// Out-of-line calls for the six-state models: their fx/hx carry FP64 sin/cos expansions, and inlining them at all
+// 2n+1 = 13 sigma points made the fused kernel 220 KB of straight-line code — ncu: "no_instruction" was the top
+// stall (2.8 cycles per issue), the FP64 pipe 23 % busy.  The four-state kernels stay inlined (their code fits).
+template <int MODEL, int N>
+__device__ __noinline__ void ukf_fx_call(const ModelConsts& mc, double (&x)[N], double u, double dt) {
+    ukf_fx<MODEL, N>(mc, x, u, dt);
+}
+template <int MODEL, int N, int O>
+__device__ __noinline__ void ukf_hx_call(const ModelConsts& mc, const double (&x)[N], double (&z)[O]) {
+    ukf_hx<MODEL, N, O>(mc, x, z);
+}
+
 // ------------------------------------------------------------------------------------------------
 // small dense kernels, fully unrolled
 // ------------------------------------------------------------------------------------------------
@@ -510,7 +522,8 @@ __global__ void __launch_bounds__(128) ukf_kernel(const __grid_constant__ UkfPar
                 double col[N];
 #pragma unroll
                 for (int r = 0; r < N; ++r) col[r] = sig[r][i];
-                ukf_fx<MODEL, N>(p.mc, col, u, p.dt);
+                if constexpr (N >= 6) ukf_fx_call<MODEL, N>(p.mc, col, u, p.dt);
+                else ukf_fx<MODEL, N>(p.mc, col, u, p.dt);
 #pragma unroll
                 for (int r = 0; r < N; ++r) sig[r][i] = col[r];
             }
@@ -524,7 +537,8 @@ __global__ void __launch_bounds__(128) ukf_kernel(const __grid_constant__ UkfPar
                 double col[N], zz[O];
 #pragma unroll
                 for (int r = 0; r < N; ++r) col[r] = sig[r][i];
-                ukf_hx<MODEL, N, O>(p.mc, col, zz);
+                if constexpr (N >= 6) ukf_hx_call<MODEL, N, O>(p.mc, col, zz);
+                else ukf_hx<MODEL, N, O>(p.mc, col, zz);
 #pragma unroll
                 for (int r = 0; r < O; ++r) zs[r][i] = ((p.enable >> r) & 1u) ? zz[r] : 0.0;
             }
