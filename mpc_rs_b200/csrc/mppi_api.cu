@@ -113,7 +113,7 @@ mpcb_status pick_kernels(mpcb_mppi* h) {
     h->W = (h->K_local + 31) / 32;
 
     struct Plan {
-        int spt = 1, sb = 0, block = 0, occ = 0;
+        int spt = 1, sb = 0, block = 0, occ = 0, vt = 1;
         size_t smem = 0;
         bool single_batch = false;
         long long chunks = 0;
@@ -121,48 +121,67 @@ mpcb_status pick_kernels(mpcb_mppi* h) {
         MppiKernelFn k[3] = {nullptr, nullptr, nullptr};
     };
     // Everything is in SAMPLES per block (sb); the block has sb / spt threads.
+    //   single batch  : one block per SM sized to its range, v tile in shared memory (VT kernels)
+    //   several batches: 128 samples per block; horizons >= 32 without the v tile — the weighted sums regenerate the
+    //                    controls of the samples with non-zero weight (NOVT kernels)
+    const char* vt_env = getenv("MPCB_MPPI_VT");  // developer override: 1 = keep the tile in multi-batch plans too
     auto make_plan = [&](int spt, Plan* out) -> mpcb_status {
         Plan pl;
         pl.spt = spt;
-        auto smem_of = [&](int sb) { return f64 ? mppi_smem_bytes<double>(h->H, sb) : mppi_smem_bytes<float>(h->H, sb); };
-        auto kernel_of = [&](int sb, int noise) -> MppiKernelFn {
+        auto smem_of = [&](int sb, int vt) { return f64 ? mppi_smem_bytes<double>(h->H, sb, vt != 0) : mppi_smem_bytes<float>(h->H, sb, vt != 0); };
+        auto kernel_of = [&](int sb, int noise, int vt) -> MppiKernelFn {
             if (sb % spt) return nullptr;
-            if (f64) return mppi_kernel_f64(h->cfg.model_id, sb, noise);
-            return spt == 2 ? mppi_kernel_f32x2(h->cfg.model_id, sb / 2, noise) : mppi_kernel_f32(h->cfg.model_id, sb, noise);
+            if (f64) return mppi_kernel_f64(h->cfg.model_id, sb, noise, vt);
+            return spt == 2 ? mppi_kernel_f32x2(h->cfg.model_id, sb / 2, noise, vt) : mppi_kernel_f32(h->cfg.model_id, sb, noise, vt);
         };
-        auto fits = [&](int sb) { return kernel_of(sb, NOISE_GENERATE) != nullptr && smem_of(sb) + 1024 <= smem_max; };
+        auto fits = [&](int sb, int vt) { return kernel_of(sb, NOISE_GENERATE, vt) != nullptr && smem_of(sb, vt) + 1024 <= smem_max; };
         long long chunks1 = h->num_sms / h->C;
         if (chunks1 < 1) chunks1 = 1;
         if (chunks1 > h->W) chunks1 = h->W;
         const long long wpc = (h->W + chunks1 - 1) / chunks1;  // warps per range if there is about one block per SM
-        const char* force = getenv("MPCB_MPPI_BLOCK");  // developer override (samples per block)
-        if (force && fits(atoi(force))) {
+        const char* force = getenv("MPCB_MPPI_BLOCK");  // developer override (samples per block, tile kept)
+        if (force && fits(atoi(force), 1)) {
             pl.sb = atoi(force);
         } else {
             for (int b : {128, 256, 512}) {
-                if (wpc * 32 <= b && fits(b)) {
+                if (wpc * 32 <= b && fits(b, 1)) {
                     pl.sb = b;
                     pl.single_batch = true;
                     break;
                 }
             }
             if (pl.sb == 0) {
-                for (int b : {128, 64, 32}) {
-                    if (fits(b)) {
-                        pl.sb = b;
-                        break;
+                // several batches per block.  Measured (K = 2^20, model NL): without the tile the scalar kernels gain
+                // 4-6 % at H = 100 / 200 (no store per step, weighted sums only over the few non-zero weights, 16 warps
+                // per SM at any horizon); at H = 8 regenerating costs more than the tile (62 vs 47 us), and the packed
+                // kernels never gain from it.  So: long horizons drop the tile, short ones keep it.
+                bool want_vt = h->H < 32 || spt == 2;
+                if (vt_env) want_vt = atoi(vt_env) == 1;
+                if (want_vt && fits(128, 1)) {
+                    pl.sb = 128;
+                } else {
+                    pl.vt = 0;
+                    for (int b : {128, 64}) {
+                        if (fits(b, 0)) {
+                            pl.sb = b;
+                            break;
+                        }
+                    }
+                    if (pl.sb == 0 && fits(128, 1)) {  // no tile-less kernel of this flavour: keep the tile
+                        pl.vt = 1;
+                        pl.sb = 128;
                     }
                 }
             }
         }
         if (pl.sb == 0) {
-            set_error("horizon %d needs more shared memory than one SM has", h->H);
+            set_error("no MPPI kernel configuration fits horizon %d", h->H);
             return MPCB_BAD_ARG;
         }
         pl.block = pl.sb / spt;
-        pl.smem = smem_of(pl.sb);
+        pl.smem = smem_of(pl.sb, pl.vt);
         for (int noise = 0; noise < 3; ++noise) {
-            pl.k[noise] = kernel_of(pl.sb, noise);
+            pl.k[noise] = kernel_of(pl.sb, noise, pl.vt);
             if (!pl.k[noise]) {
                 set_error("no MPPI kernel for model %d", h->cfg.model_id);
                 return MPCB_BAD_ARG;

@@ -2,5 +2,5 @@
 #define MPCB_INST_MODEL ModelNL
 #define MPCB_INST_REAL float
 #define MPCB_INST_FN mppi_kernel_f32_NL
-#define MPCB_INST_BLOCK512 1
+#define MPCB_INST_SAMPLES512 1
 #include "mppi_inst.cuh"

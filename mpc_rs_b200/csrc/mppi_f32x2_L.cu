@@ -3,4 +3,5 @@
 #define MPCB_INST_REAL float
 #define MPCB_INST_FN mppi_kernel_f32x2_L
 #define MPCB_INST_SPT 2
+#define MPCB_INST_SAMPLES512 1
 #include "mppi_inst.cuh"

@@ -3,4 +3,5 @@
 #define MPCB_INST_REAL float
 #define MPCB_INST_FN mppi_kernel_f32x2_NL6
 #define MPCB_INST_SPT 2
+#define MPCB_INST_SAMPLES512 1
 #include "mppi_inst.cuh"

@@ -579,11 +579,12 @@ __host__ __device__ inline size_t mppi_part_doubles(int H, int block) {
 }
 
 // Shared-memory bytes of one block.
+// `block` = samples per batch; vt = the kernel keeps the v tile [H][block + 4] (see the VT template parameter)
 template <typename real>
-__host__ __device__ inline size_t mppi_smem_bytes(int H, int block) {
+__host__ __device__ inline size_t mppi_smem_bytes(int H, int block, bool vt = true) {
     const size_t npart = mppi_part_doubles(H, block);
-    size_t dbl = ((size_t)H + kScratchDoubles + npart + 3) & ~(size_t)3;  // U_run + scratch + partition sums (32 B)
-    size_t rl = (size_t)2 * ((H + 3) & ~3) + block + (size_t)H * (block + 4);  // su, sui, w_s, v_s
+    size_t dbl = ((size_t)H + 8 + kScratchDoubles + npart + 3) & ~(size_t)3;  // U_run (+ merge totals) + scratch + partition sums
+    size_t rl = (size_t)2 * ((H + 3) & ~3) + block + (vt ? (size_t)H * (block + 4) : 0);  // su, sui, w_s, v_s
     size_t bytes = dbl * sizeof(double) + rl * sizeof(real);
     return (bytes + 15) & ~(size_t)15;
 }
@@ -600,7 +601,12 @@ __device__ __forceinline__ float fast_exp_neg(double a) {
 
 // SPT = samples per thread.  SPT = 2 (FP32 only) packs the two samples' FP32 arithmetic into f32x2 instructions
 // (f32x2.cuh): thread tid of a batch owns samples tid and BLOCK + tid of the batch's SB = 2*BLOCK samples.
-template <template <typename> class ModelT, typename real, int BLOCK, int NOISE, int SPT>
+// VT = keep the batch's control samples v[k][t] in shared memory for the weighted sums.  With VT = false nothing of
+// size K x H exists anywhere: the weighted sums REGENERATE v[k][t] = clamp(u_n[t] + eps[k][t]) from the same Philox
+// counters (or re-read the replay noise), for the samples whose weight is not zero only.  That frees the ~H*4 bytes
+// of shared memory per resident sample, which is what limits the occupancy of long horizons (H = 200: 2 blocks of
+// 128 per SM) — the multi-batch shapes use it, so that the packed kernels keep >= 8 warps per SM at any horizon.
+template <template <typename> class ModelT, typename real, int BLOCK, int NOISE, int SPT, bool VT>
 __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_constant__ MppiParams p) {
     static_assert(SPT == 1 || (SPT == 2 && sizeof(real) == 4), "two samples per thread is an FP32 layout");
     constexpr int NW = BLOCK / 32;
@@ -615,12 +621,12 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
     double* scratch = reinterpret_cast<double*>(smem_raw);           // [kScratchDoubles] (even)
     double* part_d = scratch + kScratchDoubles;                      // [mppi_part_doubles] (even): 16-byte aligned
     real* part_r = reinterpret_cast<real*>(part_d);
-    double* U_run = part_d + mppi_part_doubles(H, SB);               // [H]
-    const int ndbl = (H + kScratchDoubles + (int)mppi_part_doubles(H, SB) + 3) & ~3;
+    double* U_run = part_d + mppi_part_doubles(H, SB);               // [H + 8] (the merge totals reuse it)
+    const int ndbl = (H + 8 + kScratchDoubles + (int)mppi_part_doubles(H, SB) + 3) & ~3;
     real* su = reinterpret_cast<real*>(scratch + ndbl);              // [H4a]  u_n (16-byte aligned rows from here on)
     real* sui = su + H4a;                                            // [H4a]  u_n * sigma^-2
     real* w_s = sui + H4a;                                           // [SB]
-    real* v_s = w_s + SB;                                            // [H][LD]
+    real* v_s = w_s + SB;                                            // [H][LD] (VT only)
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int c = blockIdx.x / p.chunks;      // controller
@@ -685,7 +691,7 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
             kg[s] = p.k_offset + kl[s];
         }
 
-        if constexpr (kReplay) {
+        if constexpr (kReplay && VT) {
             // coalesced tile load: the batch's consecutive sample rows of H values -> v_s[t][k]
             const long long k_first = wb * 32;
             long long nrows = (w_end - wb) * 32;
@@ -710,9 +716,19 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
             real* vcol = v_s + tid;
             // four N(0, sigma^2) draws of sample s for steps t0..t0+3
             auto draw4 = [&](int s, int t0, real(&e)[4]) {
-                if constexpr (kReplay) {
+                if constexpr (kReplay && VT) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) e[i] = (valid[s] && t0 + i < H) ? vcol[(t0 + i) * LD + s * BLOCK] : (real)0;
+                } else if constexpr (kReplay) {
+                    // no tile: the thread reads its own row of the caller's noise (verification mode)
+                    const long long row = ((long long)c * p.K_global + kg[s]) * H;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        e[i] = (real)0;
+                        if (valid[s] && t0 + i < H)
+                            e[i] = p.eps_f64 ? (real) reinterpret_cast<const double*>(p.eps)[row + t0 + i]
+                                             : (real) reinterpret_cast<const float*>(p.eps)[row + t0 + i];
+                    }
                 } else {
                     const unsigned int c0 = (unsigned int)(kg[s] & 0xffffffffll);
                     const unsigned int khi = (unsigned int)((kg[s] >> 32) & 0xffff) << 16;
@@ -745,7 +761,7 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
                     real v = ut + eps;
                     if constexpr (kExact) v = clampr(v, lo, hi);  // f64::clamp, NaN stays NaN
                     else v = fminf(fmaxf(v, lo), hi);
-                    vcol[t * LD] = v;
+                    if constexpr (VT) vcol[t * LD] = v;
                     model.step(x, v);
                     if constexpr (kExact) {
                         const real ct = model.cost(x);
@@ -795,10 +811,12 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
                 f2 cw = splat2(0.0f), cu = splat2(0.0f);
                 auto step2 = [&](int t, f2 eps, float ut, float uit) {
                     const f2 v = clamp2(add2(splat2(ut), eps), lo, hi);
-                    float vl, vh;
-                    un2(v, vl, vh);
-                    vcol[t * LD] = vl;
-                    vcol[t * LD + BLOCK] = vh;
+                    if constexpr (VT) {
+                        float vl, vh;
+                        un2(v, vl, vh);
+                        vcol[t * LD] = vl;
+                        vcol[t * LD + BLOCK] = vh;
+                    }
                     model.step(x, v);
                     cw = model.cost.acc(x, cw);
                     cu = fma2(splat2(uit), v, cu);
@@ -917,7 +935,7 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
         // ---- PASS 6: sum_k w_k * v[k][t].  Item (t, q): column t, sample partition q; 128-bit shared loads of
         // four weights (broadcast) and four samples (conflict-free); groups whose weights are all zero —
         // samples far from the best, and warps beyond the range — are skipped, which leaves the sums unchanged. ----
-        {
+        if constexpr (VT) {
             int nq = BLOCK >> lgHp;
             if (nq < 1) nq = 1;
             if (nq > SB / 8) nq = SB / 8;
@@ -949,6 +967,64 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
                 U_run[t] = U_run[t] * resc + (double)acc;
             }
             __syncthreads();
+        } else {
+            // ---- PASS 6 without a v tile: thread item (g, j) takes the four steps t0 = 4j .. 4j+3 of every G-th sample
+            // of the batch (k = g, g+G, ...), skips the samples whose weight is zero, and rebuilds the others' controls
+            // from the Philox block (global sample index, t0/4) the rollout used — or re-reads the replay noise.  The
+            // G groups' sums are then added in order, so the result does not depend on timing. ----
+            const int Hq = (H + 3) >> 2;
+            int G = BLOCK / Hq;
+            const int cap = (int)(mppi_part_doubles(H, SB) * sizeof(double) / sizeof(real)) / H4a;  // part_r rows available
+            if (G > cap) G = cap;
+            if (G > 8) G = 8;
+            if (G < 1) G = 1;
+            for (int item = tid; item < G * Hq; item += BLOCK) {
+                const int g = item / Hq, j = item - g * Hq, t0 = 4 * j;
+                real acc[4] = {(real)0, (real)0, (real)0, (real)0};
+                real u4[4];
+                lds4(su + t0, u4);
+                for (int k = g; k < SB; k += G) {
+                    const real wk = w_s[k];
+                    real w1[4] = {wk, (real)0, (real)0, (real)0};
+                    if (all_zero_bits(w1)) continue;
+                    const long long kgk = p.k_offset + wb * 32 + k;  // column k of the batch is local sample wb*32 + k
+                    real e[4];
+                    if constexpr (kReplay) {
+                        const long long row = ((long long)c * p.K_global + kgk) * H;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            e[i] = (real)0;
+                            if (t0 + i < H)
+                                e[i] = p.eps_f64 ? (real) reinterpret_cast<const double*>(p.eps)[row + t0 + i]
+                                                 : (real) reinterpret_cast<const float*>(p.eps)[row + t0 + i];
+                        }
+                    } else {
+                        const unsigned int c0 = (unsigned int)(kgk & 0xffffffffll);
+                        const unsigned int khi = (unsigned int)((kgk >> 32) & 0xffff) << 16;
+                        const Philox4 r = philox4x32_10(c0, p.call_idx, (unsigned int)c, (unsigned int)j | khi, p.seed_lo, p.seed_hi);
+                        float z[4];
+                        philox_normal4(r, neg2s2ln2, z);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) e[i] = (real)z[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        real v = u4[i] + e[i];
+                        if constexpr (kExact) v = clampr(v, lo, hi);
+                        else v = fminf(fmaxf(v, lo), hi);
+                        acc[i] += wk * v;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) part_r[g * H4a + t0 + i] = acc[i];
+            }
+            __syncthreads();
+            for (int t = tid; t < H; t += BLOCK) {
+                real acc = part_r[t];
+                for (int g = 1; g < G; ++g) acc += part_r[g * H4a + t];
+                U_run[t] = U_run[t] * resc + (double)acc;
+            }
+            __syncthreads();
         }
     }
 
@@ -961,7 +1037,7 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
     // last block to arrive merges alone.
     const int PL = p.PL;
     const double inv_lambda_m = 1.0 / lambda;
-    double* tot_d = reinterpret_cast<double*>(v_s);  // the v tile is dead after the rollouts: merge totals [<= (H+5)/2 double2]
+    double* tot_d = U_run;  // dead once the row is stored (the arrival barrier comes first): merge totals [<= (H+5)/2 double2]
     double* ctrl_rows = p.partial + (long long)c * (p.chunks + p.groups) * PL;
     double* my_row = ctrl_rows + (long long)chunk * PL;
     for (int t = tid; t < H; t += BLOCK) my_row[kPartialHdr + t] = U_run[t];
@@ -1147,8 +1223,8 @@ __global__ void __launch_bounds__(BLOCK) mppi_combine_kernel(const MppiCombinePa
 
 // kernel entry table (defined in mppi_f32*.cu / mppi_f64.cu)
 using MppiKernelFn = void (*)(const MppiParams);
-MppiKernelFn mppi_kernel_f32(int model_id, int block, int noise);
-MppiKernelFn mppi_kernel_f32x2(int model_id, int block, int noise);  // two samples per thread (block threads = 2*block samples)
-MppiKernelFn mppi_kernel_f64(int model_id, int block, int noise);
+MppiKernelFn mppi_kernel_f32(int model_id, int block, int noise, int vt);
+MppiKernelFn mppi_kernel_f32x2(int model_id, int block, int noise, int vt);  // two samples per thread (block threads = 2*block samples)
+MppiKernelFn mppi_kernel_f64(int model_id, int block, int noise, int vt);
 
 }  // namespace mpcb

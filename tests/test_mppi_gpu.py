@@ -301,6 +301,29 @@ def test_launch_shapes(gpu_required):
                 assert abs(m.info[0]["sum"] - io["sum"]) <= (1e-9 if prec == "f64" else 1e-4) * io["sum"]
 
 
+def test_long_horizon_multi_batch_regenerates_controls(gpu_required):
+    """Several batches per block at H >= 32 run the kernels WITHOUT the v tile: the weighted sums rebuild v[k][t] from the
+    Philox counters (generate) or re-read the noise (replay).  Replay parity against the oracle, and generate mode
+    against a replay of its own dump, for both precisions; odd sizes so that ragged warps and tails are exercised."""
+    model, oid, _, _, lam, sig, lim = CASES["NL_h100"]
+    H, K, dt = 41, 100003, 0.02
+    p = O.model_defaults(oid, dt=dt)
+    rng = np.random.default_rng(51)
+    u_n = rng.uniform(-1, 1, H)
+    eps = sig * rng.standard_normal((K, H))
+    st, u_o, io, _ = O.mppi_compute(oid, p, K, H, lam, sig, lim[0], lim[1], X0, u_n, eps)
+    assert st == 0
+    for prec, tol in (("f64", 1e-9), ("f32", 1e-5)):
+        with Mppi(H, K, model=model, lam=lam, std_dev=sig, limit=lim, precision=prec, dt=dt, seed=3) as m:
+            u_g = m.compute_replay(X0, u_n, eps)
+            assert m.info[0]["argmax"] == io["argmax"] and m.info[0]["n_finite"] == K
+            assert rel_err(u_g, u_o) < tol, (prec, rel_err(u_g, u_o))
+            u_gen, eps_gen = m.compute_dump(X0, u_n)
+            st2, u_o2, io2, _ = O.mppi_compute(oid, p, K, H, lam, sig, lim[0], lim[1], X0, u_n, eps_gen.astype(np.float64))
+            assert st2 == 0 and m.info[0]["argmax"] == io2["argmax"]
+            assert rel_err(u_gen, u_o2) < tol, (prec, rel_err(u_gen, u_o2))
+
+
 def test_golden_fixtures_gpu(gpu_required):
     """The CUDA path against the committed golden vectors (tests/golden, made from the oracle by make_golden.py)."""
     import os
