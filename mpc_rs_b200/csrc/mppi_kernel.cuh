@@ -36,10 +36,7 @@ namespace mpcb {
 constexpr int kPartialHdr = 4;   // m, argmax (bits), sum_w, n_finite (as double)
 constexpr int kMergeFan = 256;   // max rows merged by one block
 constexpr int kMaxWarps = 16;    // warps per block (BLOCK <= 512)
-#ifndef MPCB_FLUSH_STEPS
-#define MPCB_FLUSH_STEPS 4
-#endif
-constexpr int kFlushSteps = MPCB_FLUSH_STEPS;  // FP32 cost partial sums -> FP64 accumulator period (power of two >= 4)
+constexpr int kFlushSteps = 4;   // FP32 cost partial sums -> FP64 accumulators every 4 steps (16 measured no faster)
 // shared scratch (doubles): red_m[16] red_a[16] red_n[16] red_s[24] sc[kMergeFan]
 constexpr int kScratchDoubles = 16 + 16 + 16 + 24 + kMergeFan;
 
@@ -107,9 +104,6 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
         if (p.debug_ts != nullptr && threadIdx.x == 0) p.debug_ts[(size_t)blockIdx.x * 16 + (slot)] = globaltimer_ns(); \
     } while (0)
 
-// gpu-scope release/acquire fence around the ticket atomics (cheaper than the sequentially consistent
-// __threadfence(); the ticket pattern only needs release on the producer and acquire on the consumer side)
-__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_release_sys_u32(unsigned int* p, unsigned int v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -167,7 +161,6 @@ __device__ __forceinline__ void warp_argmax(double v, long long tag, bool fin, d
 }
 
 // 4 consecutive elements of shared memory (16-byte aligned for float, 32-byte for double)
-struct Vec4f { float a, b, c, d; };
 __device__ __forceinline__ void lds4(const float* p, float (&o)[4]) {
     const float4 v = *reinterpret_cast<const float4*>(p);
     o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
