@@ -79,7 +79,8 @@ def cpu_baseline(steps, warmup: int, budget_s: float = 12.0):
     (the bounded sample); an explicit step count is capped by the same budget.  Returns (rollout-steps/s, info)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
-    threads = O.max_threads()
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every core this process may run on
+    threads = max(O.max_threads(), len(os.sched_getaffinity(0)))
     p = O.model_defaults(O.MODEL_NL, dt=DT)
     K = K_PER_GPU
     u = np.zeros(H)
