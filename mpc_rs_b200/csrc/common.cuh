@@ -35,6 +35,8 @@ const char* last_error();
 constexpr int kModelConsts = 24;
 struct ModelConsts {
     double k[kModelConsts];
+    float kf[kModelConsts];  // the same constants rounded to FP32 on the host: the packed kernels read them straight
+                             // from the constant bank, so that they stay in UNIFORM registers (see f32x2.cuh)
 };
 // Fills the constants for `model_id` from the physical parameter block, in the reference's association order.
 mpcb_status build_model_consts(int model_id, const mpcb_model_params& p, double dt, ModelConsts* out);

@@ -114,6 +114,7 @@ mpcb_status pick_kernels(mpcb_mppi* h) {
 
     struct Plan {
         int spt = 1, sb = 0, block = 0, occ = 0, vt = 1;
+        long long wpc = 0;  // sample-warps per block range when there is about one block per SM
         size_t smem = 0;
         bool single_batch = false;
         long long chunks = 0;
@@ -139,6 +140,7 @@ mpcb_status pick_kernels(mpcb_mppi* h) {
         if (chunks1 < 1) chunks1 = 1;
         if (chunks1 > h->W) chunks1 = h->W;
         const long long wpc = (h->W + chunks1 - 1) / chunks1;  // warps per range if there is about one block per SM
+        pl.wpc = wpc;
         const char* force = getenv("MPCB_MPPI_BLOCK");  // developer override (samples per block, tile kept)
         if (force && fits(atoi(force), 1)) {
             pl.sb = atoi(force);
@@ -205,10 +207,12 @@ mpcb_status pick_kernels(mpcb_mppi* h) {
         *out = pl;
         return MPCB_OK;
     };
-    // FP32: two samples per thread with packed f32x2 arithmetic take ~30 % fewer issue slots per sample, but halve
-    // the warps.  They win when the SM still holds >= 8 warps (short horizons, many controllers: +35 % on the
-    // config-#4 shape) and lose when the rollout is starved for warps (K = 65536 x H = 100 on 148 SMs has 14
-    // sample-warps per SM; H = 200 fits 9) — there the scalar kernels run.  MPCB_MPPI_SPT=1/2 forces one.
+    // FP32: two samples per thread with packed f32x2 arithmetic take ~30 % fewer issue slots per sample but halve the
+    // warps.  Measured (model NL, tools/dev_spt_crossover.py): a single-batch plan is quantised by warps per scheduler —
+    // scalar 19 / 25 / 31 / 37 us for 1..4 warps (H = 100), packed 27 / 35 us for 1..2 — so the packed kernels win
+    // exactly when the scalar plan would put 4 warps on a scheduler (13-16 sample-warps per SM: K = 65536 on 148 SMs)
+    // and lose below; multi-batch plans with a short horizon take them when >= 8 warps stay resident per SM (+35 % on
+    // the config-#4 shape); long multi-batch horizons run the scalar tile-less kernels.  MPCB_MPPI_SPT=1/2 forces one.
     Plan plan;
     mpcb_status st = make_plan(1, &plan);
     if (st != MPCB_OK) return st;
@@ -216,7 +220,11 @@ mpcb_status pick_kernels(mpcb_mppi* h) {
         const char* spt_env = getenv("MPCB_MPPI_SPT");
         const int forced = spt_env ? atoi(spt_env) : 0;
         Plan p2;
-        if (forced != 1 && make_plan(2, &p2) == MPCB_OK && (forced == 2 || p2.warps_per_sm >= 8.0)) plan = p2;
+        if (forced != 1 && make_plan(2, &p2) == MPCB_OK) {
+            const bool single_both = plan.single_batch && p2.single_batch;
+            const bool take = single_both ? plan.wpc > 12 : (!p2.single_batch && p2.vt && p2.warps_per_sm >= 8.0 && plan.vt);
+            if (forced == 2 || take) plan = p2;
+        }
     }
     h->spt = plan.spt;
     const int block = plan.block;  // threads
@@ -294,6 +302,7 @@ void fill_params(const mpcb_mppi* h, MppiParams* p) {
     p->info = h->d_info;
     p->rank_partial = h->d_rank_partial;
     p->mc = h->mc;
+    for (int i = 0; i < kModelConsts; ++i) p->mc.kf[i] = (float)h->mc.k[i];
     p->costs = h->cfg.keep_costs ? h->d_costs : nullptr;
     p->debug_ts = h->d_ts;
 }
