@@ -242,10 +242,25 @@ def run_gpu(args):
     transport = os.environ.get("MPCB_BENCH_TRANSPORT", "peer")  # "peer": fused in-kernel exchange; "nccl": ncclAllGather
     if world > 1:
         from mpc_rs_b200.distributed import attach_mppi, attach_mppi_peers
+        if transport != "nccl":
+            # every rank's mailbox handle -> everyone, then cudaIpcOpenMemHandle; if any rank cannot map its peers
+            # (e.g. devices hidden from each other) all ranks fall back to the NCCL transport together
+            ok = 1
+            try:
+                attach_mppi_peers(mppi)
+            except Exception as e:  # noqa: BLE001 - reported below
+                ok = 0
+                print(f"[bench] rank {rank}: peer exchange unavailable ({e}); falling back to NCCL", file=sys.stderr)
+            t_ok = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+            if int(t_ok.item()) == 0:
+                transport = "nccl"
+                os.environ["MPCB_BENCH_TRANSPORT"] = "nccl"
+                mppi.close()
+                mppi = Mppi(H, K_PER_GPU * world, model=models.NL, lam=LAMBDA, std_dev=SIGMA, limit=LIMIT, precision="f32", dt=DT,
+                            device=dev, rank=rank, world_size=world, seed=20240001)
         if transport == "nccl":
             attach_mppi(mppi)  # rank 0's ncclUniqueId -> everyone (torch.distributed broadcast), then ncclCommInitRank
-        else:
-            attach_mppi_peers(mppi)  # every rank's mailbox handle -> everyone, then cudaIpcOpenMemHandle
 
     stream = torch.cuda.ExternalStream(mppi.stream, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
