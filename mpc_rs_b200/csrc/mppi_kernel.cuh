@@ -1146,7 +1146,9 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
         ro.copy_offset = slot_self * PL;
         ro.n_copies = G;
         ro.copy_skip = p.rank;
+        MPCB_TS(12);
         mppi_merge_rows<BLOCK>(final_rows, PL, final_n, H, mi, nm, inv_lambda_m, FINAL_RANK_ROW, ro, scratch, part_d, tot_d);
+        MPCB_TS(13);
         // the stores of the whole block come before the barrier, thread r's system-scope release after it (cumulative)
         __syncthreads();
         for (int r = tid; r < G; r += BLOCK) st_release_sys_u32(p.peer_flags[r] + slot_self * kMaxMergers + mi, p.xepoch);
@@ -1154,6 +1156,7 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
         __shared__ int s_timeout;
         if (tid == 0) s_timeout = 0;
         __syncthreads();
+        MPCB_TS(14);
         for (int r = tid; r < 2 * G; r += BLOCK) {
             const int src = r >> 1, which = (r & 1) ? mi : 0;
             const unsigned int* f = p.peer_flags[p.rank] + ((long long)(par * G + src) * p.C + c) * kMaxMergers + which;
@@ -1163,6 +1166,7 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
             }
         }
         __syncthreads();
+        MPCB_TS(15);
         fo.forced_status = s_timeout ? MPCB_PEER_TIMEOUT : MPCB_OK;
         const double* rank_rows = own_box + (long long)(par * G) * p.C * PL + (long long)c * PL;
         if (G <= 32) {
