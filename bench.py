@@ -11,8 +11,8 @@ per control step inside the library.
 
     value     device-resident closed loop (u_out of step i is u_in of step i+1), CUDA events per step on the
               handle's stream, L2 flushed between timed steps, max over ranks
-    e2e       the same step through mpcb_mppi_compute with HOST buffers (inputs in the kernel parameters,
-              u_out/info written to mapped pinned memory, one stream sync per call), host wall clock
+    e2e       the same step through the C-ABI call mpcb_mppi_compute with HOST buffers (inputs travel in the kernel
+              parameters, u_out/info come back through mapped pinned memory and a completion word), host wall clock
     roofline  algorithmic FP32 flops (60 per rollout-step) / kernel time vs the FFMA peak measured
               live by tools/peak_bench (MEASURED_PEAKS.json has no FP32 vector number)
     ukf       BASELINE configs[2] on the side: 2^20 independent examples/ukf-pen.rs filters per GPU, FP64,
@@ -310,14 +310,25 @@ def run_gpu(args):
     mppi.sync()
     kern_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
 
-    # ---- e2e: host buffers through mpcb_mppi_compute ----
-    x_h, u_h = X0.copy(), np.zeros(H)
+    # ---- e2e: host buffers through the C-ABI entry point mpcb_mppi_compute itself (what a Rust/C++/ctypes caller of
+    # include/mpc_b200.h calls): x[4], u_in[H] -> u_out[H] + info, closed loop (u_out is the next u_in) ----
+    x_h, u_h, out_h = X0.copy(), np.zeros(H), np.zeros(H)
+    info_h = (A.MppiInfo * 1)()
+    px, pu, po = (a.ctypes.data_as(C.POINTER(C.c_double)) for a in (x_h, u_h, out_h))
+    compute = A.lib().mpcb_mppi_compute
+
+    def e2e_step():
+        st = compute(mppi._h, px, pu, po, info_h)
+        if st != 0:
+            raise SystemExit(f"mpcb_mppi_compute returned {st} in the e2e loop")
+        np.copyto(u_h, out_h)
+
     for _ in range(args.warmup):
-        u_h = mppi.compute(x_h, u_h)
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        u_h = mppi.compute(x_h, u_h)
+        e2e_step()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = steps_total / e2e_s
     clocks = sampler.stop() if rank == 0 else None
