@@ -240,6 +240,48 @@ def test_peer_exchange_on_one_gpu(gpu_required):
         A.lib().mpcb_device_free(0, q)
 
 
+def test_peer_exchange_large_shards(gpu_required):
+    """Peer exchange with shards large enough for the 256/512-thread one-block-per-SM plan (the other peer tests use
+    small K and so the 128-thread plan).  G = 2 handles of one process on device 0 against a single handle with the
+    same seed, several steps (flag parity and slot reuse), both precisions."""
+    import ctypes as C
+    model, oid, _, _, lam, sig, lim = CASES["NL_h100"]
+    H, K, G, dt = 16, 80000, 2, 0.05
+    rng = np.random.default_rng(33)
+    u_n = rng.uniform(-2, 2, H)
+    d = [C.c_void_p() for _ in range(2 + G)]
+    for q, n in zip(d, [32, 8 * H] + [8 * H] * G):
+        A.check(A.lib().mpcb_device_alloc(0, n, C.byref(q)))
+    A.check(A.lib().mpcb_device_upload(0, d[0], X0.ctypes.data_as(C.c_void_p), 32))
+    A.check(A.lib().mpcb_device_upload(0, d[1], u_n.ctypes.data_as(C.c_void_p), 8 * H))
+    for prec, tol in (("f64", 1e-12), ("f32", 2e-6)):
+        hs = [Mppi(H, K, model=model, lam=lam, std_dev=sig, limit=lim, precision=prec, dt=dt, rank=r, world_size=G, seed=6)
+              for r in range(G)]
+        handles = [h.peer_handle() for h in hs]
+        for h in hs:
+            h.attach_peers(handles)
+        with Mppi(H, K, model=model, lam=lam, std_dev=sig, limit=lim, precision=prec, dt=dt, seed=6) as one:
+            for step in range(5):
+                u_one = one.compute(X0, u_n)
+                for r, h in enumerate(hs):
+                    h.compute_device(d[0].value, d[1].value, d[2 + r].value)
+                for r, h in enumerate(hs):
+                    h.sync()
+                    info = h.last_info()[0]
+                    assert info["status"] == 0 and info["n_finite"] == K
+                    assert info["argmax"] == one.last_call_info()[0]["argmax"]
+                    out = np.empty(H)
+                    A.check(A.lib().mpcb_device_download(0, out.ctypes.data_as(C.c_void_p), d[2 + r], 8 * H))
+                    assert rel_err(out, u_one) < tol, (prec, step, r, rel_err(out, u_one))
+                    if r:
+                        assert np.array_equal(out, first), "ranks must agree bitwise"
+                    first = out
+        for h in hs:
+            h.close()
+    for q in d:
+        A.lib().mpcb_device_free(0, q)
+
+
 def test_peer_exchange_batched_controllers_odd_horizon(gpu_required):
     """The same exchange with C = 3 controllers per handle (one mailbox slot and flag set per controller) and an odd
     horizon (rows padded to a whole number of 16-byte column pairs), model L, G = 2 handles on one device."""
