@@ -187,6 +187,17 @@ class BatchedUkf:
         return A.lib().mpcb_ukf_stream(self._h) or 0
 
 
+    @property
+    def device_x(self) -> int:
+        """Raw device pointer of the state, structure of arrays x[n][B] (mpcb_ukf_device_x)."""
+        return A.lib().mpcb_ukf_device_x(self._h) or 0
+
+    @property
+    def device_p(self) -> int:
+        """Raw device pointer of the covariance, P[n*n][B] (mpcb_ukf_device_p)."""
+        return A.lib().mpcb_ukf_device_p(self._h) or 0
+
+
 class UnscentedKalmanFilter(BatchedUkf):
     """Single filter with the reference's method names and shapes (src/ukf.rs:30-94)."""
 

@@ -202,6 +202,24 @@ def test_multi_step_device_run(gpu_required):
     A.lib().mpcb_device_free(0, d_z)
 
 
+def test_raw_device_pointers_are_soa(gpu_required):
+    """mpcb_ukf_device_x / device_p expose x[n][B] and P[n*n][B] (component-major), the layout the kernels coalesce on."""
+    import ctypes as C
+    B, T = 700, 3
+    model, oid, p, n, o, Q, R, P0, u, zs = make_problem("PEN_LIN", B, T, 15)
+    with BatchedUkf(model, B) as f:
+        f.init(np.zeros(n), P0, Q, R)
+        for t in range(T):
+            f.step(u, zs[t])
+        x, P = f.get_state()
+        xs, Ps = np.empty((n, B)), np.empty((n * n, B))
+        assert f.device_x and f.device_p
+        A.check(A.lib().mpcb_device_download(0, xs.ctypes.data_as(C.c_void_p), C.c_void_p(f.device_x), xs.nbytes))
+        A.check(A.lib().mpcb_device_download(0, Ps.ctypes.data_as(C.c_void_p), C.c_void_p(f.device_p), Ps.nbytes))
+        np.testing.assert_array_equal(xs.T, x)
+        np.testing.assert_array_equal(Ps.T.reshape(B, n, n), P)
+
+
 def test_golden_fixtures_gpu(gpu_required):
     """The CUDA path against the committed golden vectors (tests/golden, made from the oracle by make_golden.py)."""
     import os
