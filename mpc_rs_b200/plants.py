@@ -97,6 +97,80 @@ class PlantPenLin:
         return z + np.asarray(self.R_DIAG) * rng.standard_normal(z.shape)
 
 
+class PlantPenNL:
+    """Truth model + sensor of examples/ukf-pen2.rs:31-66 (nonlinear pendulum, DT = 0.01; o = 3: rpm, rpm, deg/s)."""
+
+    NOISE = (100.0, 100.0, 0.5)  # :58-64
+
+    def __init__(self):
+        self.p = _params(A.MODEL_PEN_NL)
+        self.dt = self.p.dt
+
+    def fx(self, x, u):
+        p = self.p
+        M1, R_W, M2, L, J1, J2, G, KT = p.m1, p.r_w, p.m2, p.l, p.j1, p.j2, p.g, p.kt
+        x = np.asarray(x, dtype=np.float64)
+        th, om = x[..., 2], x[..., 3]
+        D = (M1 + M2 + J1 / (R_W * R_W)) * (M2 * L * L + J2)
+        d = D - M2 * M2 * L * L * np.cos(th) * np.cos(th)
+        drive = KT * u / R_W + M2 * L * om ** 2 * np.sin(th)
+        r = np.array(x, copy=True)
+        r[..., 3] += ((M1 + M2 + J1 / (R_W * R_W)) * M2 * G * L * np.sin(th) - drive * M2 * L * np.cos(th)) / d * self.dt
+        r[..., 2] += om * self.dt
+        r[..., 1] += ((J2 + M2 * L * L) * drive + M2 * G * L * L * np.sin(th) * np.cos(th)) / d * self.dt
+        r[..., 0] += x[..., 1] * self.dt
+        return r
+
+    def hx(self, x):
+        rpm = 60.0 / (2.0 * np.pi * self.p.r_w) * x[..., 1]
+        return np.stack([rpm, rpm, np.degrees(x[..., 3])], axis=-1)
+
+    def sensor(self, x, rng):
+        z = self.hx(np.asarray(x, dtype=np.float64))
+        return z + np.asarray(self.NOISE) * rng.standard_normal(z.shape)
+
+
+class PlantPen6:
+    """Truth model + sensor of examples/ukf-pen3.rs:35-77: state [x, x', x'', th, th', th''], accelerations recomputed
+    every step (the `x[2].cos()` in the denominator is the reference's, :38); o = 5."""
+
+    NOISE = (100.0, 100.0, 0.5, 100.0, 100.0)  # :68-74
+
+    def __init__(self):
+        self.p = _params(A.MODEL_PEN6)
+        self.dt = self.p.dt
+
+    def fx(self, x, u):
+        p = self.p
+        M1, R_W, M2, L, J1, J2, G, KT = p.m1, p.r_w, p.m2, p.l, p.j1, p.j2, p.g, p.kt
+        x = np.asarray(x, dtype=np.float64)
+        th, om = x[..., 3], x[..., 4]
+        D = (M1 + M2 + J1 / (R_W * R_W)) * (M2 * L * L + J2)
+        d = D - (M2 * L * np.cos(x[..., 2])) ** 2
+        drive = KT * u / R_W + M2 * L * om ** 2 * np.sin(th)
+        r = np.array(x, copy=True)
+        r[..., 0] += x[..., 1] * self.dt
+        r[..., 1] += x[..., 2] * self.dt
+        r[..., 2] = ((J2 + M2 * L * L) * drive + M2 * G * L * L * np.sin(th) * np.cos(th)) / d
+        r[..., 3] += x[..., 4] * self.dt
+        r[..., 4] += x[..., 5] * self.dt
+        r[..., 5] = ((M1 + M2 + J1 / (R_W * R_W)) * M2 * G * L * np.sin(th) - drive * M2 * L * np.cos(th)) / d
+        return r
+
+    def hx(self, x):
+        p = self.p
+        M2, L, G = p.m2, p.l, p.g
+        th = x[..., 3]
+        v = M2 * G * np.cos(th) + M2 * x[..., 2] * np.sin(th) - M2 * L * x[..., 4] ** 2
+        h = -M2 * G * np.sin(th) + M2 * x[..., 2] * np.cos(th) + M2 * L * x[..., 5]
+        rpm = 60.0 / (2.0 * np.pi * p.r_w) * x[..., 1]
+        return np.stack([rpm, rpm, np.degrees(th), v / G, h / G], axis=-1)
+
+    def sensor(self, x, rng):
+        z = self.hx(np.asarray(x, dtype=np.float64))
+        return z + np.asarray(self.NOISE) * rng.standard_normal(z.shape)
+
+
 class PlantNL6:
     """The robot of examples/mppi4-non-liner-ukf.rs: ddot :126-139, dynamics_short :149-159, hx :169-179,
     sensor :180-190 (R entries used as standard deviations), 2 N push for 1.0 < t < 1.5 (:236-241)."""

@@ -123,3 +123,35 @@ def test_example_ukf_pen_converges(gpu_required):
     # observed components (x1, x3) are tracked to within the sensor noise; P has contracted from 10 I
     assert np.sqrt(np.mean((x_est[:, 1] - x_act[:, 1]) ** 2)) < 0.5
     assert np.all(p[:, 1, 1] < 5.0) and np.all(p[:, 3, 3] < 5.0)
+
+
+@pytest.mark.parametrize("six", [False, True])
+def test_example_library_ukf_runs_like_the_reference(gpu_required, six, capsys):
+    """examples/ukf-pen2.rs / ukf-pen3.rs drivers (API-usage fixtures): 100 open-loop steps through
+    new / predict / update / state / covariance; the filter stays finite, P stays symmetric with a positive diagonal,
+    the observed velocity is tracked, and the printed line has the reference's fields."""
+    import ukf_pen2 as ex
+    x_act, x_est, p = ex.run(six=six, steps=100, quiet=False, seed=4)
+    n = 6 if six else 4
+    assert x_est.shape == (n,) and p.shape == (n, n)
+    assert np.all(np.isfinite(x_est)) and np.all(np.isfinite(p))
+    assert np.allclose(p, p.T, rtol=1e-9, atol=1e-12) and np.all(np.diag(p) > 0)
+    assert np.diag(p)[1] < 10.0          # the wheel odometry observes x' (P0 = 10 I)
+    lines = capsys.readouterr().out.strip().splitlines()
+    assert len(lines) == 100 and lines[0].startswith("t: 0.00 x_act: (") and " x_obs: (" in lines[0] and " p: (" in lines[0]
+
+
+def test_example_mppi4_non_liner_s(gpu_required, tmp_path):
+    """examples/mppi4-non-liner-s.rs driver: MPPI fed by the 4-state library UKF with run-time dt on the fixed schedule;
+    the loop runs, estimates stay finite, the observed wheel speed is tracked (theta is not observed by this filter, so
+    its estimate is only as good as the model, like in the reference), and the CSV has the reference's 6 columns."""
+    import mppi4_non_liner_s as ex
+    csv = str(tmp_path / "mppi.csv")
+    rows = ex.run(samples=65536, seconds=1.5, csv=csv, quiet=True, seed=2)
+    assert rows.shape[1] == 10 and len(rows) >= 50
+    assert np.all(np.isfinite(rows))
+    assert np.all(np.abs(rows[:, 1]) <= 10.0)                      # LIMIT
+    assert np.median(np.abs(rows[:, 3] - rows[:, 7])) < 0.5         # x' (wheel odometry, 50 rpm noise ~ 0.26 m/s)
+    data = np.loadtxt(csv, delimiter=",")                          # write_record only: no header row (:157-166)
+    assert data.shape == (len(rows), 6)
+    np.testing.assert_allclose(data[:, 1], rows[:, 1], rtol=0, atol=0)

@@ -5,7 +5,7 @@ import numpy as np
 
 import oracle_lib as O
 from mpc_rs_b200 import csvlog
-from mpc_rs_b200.plants import PlantL, PlantNL, PlantNL6, PlantPenLin
+from mpc_rs_b200.plants import PlantL, PlantNL, PlantNL6, PlantPen6, PlantPenLin, PlantPenNL
 
 
 def test_plants_match_the_oracle():
@@ -23,6 +23,14 @@ def test_plants_match_the_oracle():
     pl, p = PlantPenLin(), O.model_defaults(O.MODEL_PEN_LIN)
     x = rng.normal(0, 0.3, 4)
     np.testing.assert_allclose(pl.fx(x, 0.0015), O.fx(O.MODEL_PEN_LIN, p, x, 0.0015), rtol=1e-13, atol=1e-16)
+    # truth models of the library-UKF examples (examples/ukf-pen2.rs:31-53, examples/ukf-pen3.rs:35-63)
+    for cls, oid, n in ((PlantPenNL, O.MODEL_PEN_NL, 4), (PlantPen6, O.MODEL_PEN6, 6)):
+        pl, p = cls(), O.model_defaults(oid)
+        assert pl.dt == 0.01
+        for _ in range(10):
+            x = rng.normal(0, 0.4, n)
+            np.testing.assert_allclose(pl.fx(x, 0.1), O.fx(oid, p, x, 0.1), rtol=1e-12, atol=1e-14)
+            np.testing.assert_allclose(pl.hx(x), O.hx(oid, p, x), rtol=1e-12, atol=1e-12)
     p6, pn = PlantNL6(), O.model_defaults(O.MODEL_NL6_UKF)
     for f in (0.0, 2.0):
         x6 = rng.normal(0, 0.3, 6)
