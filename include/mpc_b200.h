@@ -43,7 +43,8 @@ typedef enum mpcb_status {
     MPCB_CUDA_ERROR = 7,
     MPCB_NCCL_ERROR = 8,
     MPCB_NOT_PREDICTED = 9,  /* update() before any predict(): the reference yields NaN (src/ukf.rs:32) */
-    MPCB_PEER_TIMEOUT = 10   /* multi-GPU exchange: a peer's partial row did not arrive within 20 s */
+    MPCB_PEER_TIMEOUT = 10,  /* multi-GPU exchange: a peer's partial row did not arrive within 20 s */
+    MPCB_RTC_ERROR = 11      /* user model: NVRTC missing or the source does not compile (see mpcb_rtc_log) */
 } mpcb_status;
 
 /* Message for a status; for MPCB_NO_FINITE_COST/SUM_ZERO/U_INVALID/INVERSE_FAIL/CHOLESKY_FAIL it is
@@ -63,6 +64,7 @@ typedef enum mpcb_model {
     MPCB_MODEL_L = 0,   /* linear cart-pendulum + clamped cost     examples/mppi4.rs:20-27,73-89 */
     MPCB_MODEL_NL = 1,  /* nonlinear pendulum, explicit Euler      examples/mppi4-non-liner.rs:20-27,73-94 */
     MPCB_MODEL_NL6 = 2, /* ddot + dynamics4, quadratic cost        examples/mppi4-non-liner-ukf.rs:33-35,126-148 */
+    MPCB_MODEL_USER = 3, /* dynamics + cost supplied as CUDA source to mpcb_mppi_create_user                       */
     /* UKF process/measurement models */
     MPCB_MODEL_PEN_LIN = 16, /* n=4,o=2  fx/hx of examples/ukf-pen.rs:76-91 */
     MPCB_MODEL_PEN_NL = 17,  /* n=4,o=3  fx/hx of examples/ukf-pen2.rs:31-53 */
@@ -133,6 +135,29 @@ typedef struct mpcb_mppi_info {
 } mpcb_mppi_info;
 
 mpcb_status mpcb_mppi_default_cfg(int32_t model_id, mpcb_mppi_cfg* out); /* the example's constants */
+
+/* User-supplied model.  Mppi::new takes `dynamics: fn(&SVector<f64,S>, f64) -> SVector<f64,S>` and
+ * `cost: fn(&SVector<f64,S>) -> f64` (src/mppi.rs:9-10,16-22); a kernel cannot call host functions, so the same two
+ * functions are given as CUDA C++ source and the fused MPPI kernel is compiled around them at create time (NVRTC,
+ * sm_100a; a few seconds).  `cuda_source` must define, at global scope (`__device__` may be omitted),
+ *
+ *     template <typename real> void dynamics(real (&x)[4], real u, const real* p);   // x <- f(x, u), in place
+ *     template <typename real> real cost(const real (&x)[4], const real* p);         // stage cost of the NEW state
+ *
+ * (plain `float` / `double` overloads work too; `real` is float for MPCB_F32, double for MPCB_F64, where the source
+ * is compiled without FMA contraction).  p[0..n_params) are the caller's constants (n_params <= MPCB_USER_PARAMS),
+ * delivered through the kernel-parameter bank.  Helpers of the built-in models may be used: mpcb::sincos_r(a, &s, &c),
+ * mpcb::fast_rcp(d), mpcb::clampm(v, lo, hi).  Everything else — noise, clamping of the control, control term,
+ * softmax, weighted mean, errors, replay / dump / sharding — is the built-in path.  cfg->model_id and cfg->model are
+ * ignored.  MPCB_RTC_ERROR if NVRTC is unavailable or the source does not compile. */
+#define MPCB_USER_PARAMS 24
+mpcb_status mpcb_mppi_create_user(mpcb_mppi** out, const mpcb_mppi_cfg* cfg, const char* cuda_source,
+                                  const double* params, int32_t n_params);
+/* Compile-only check of a user model for `precision` (needs NVRTC, not a GPU). */
+mpcb_status mpcb_mppi_check_user_source(const char* cuda_source, int32_t precision);
+/* NVRTC log (errors and warnings, lines of the user source as "user_model.cu(line)") of the calling thread's last
+ * mpcb_mppi_create_user / mpcb_mppi_check_user_source; "" if none. */
+const char* mpcb_rtc_log(void);
 mpcb_status mpcb_mppi_create(mpcb_mppi** out, const mpcb_mppi_cfg* cfg); /* Mppi::new, src/mppi.rs:16 */
 void mpcb_mppi_destroy(mpcb_mppi* h);
 

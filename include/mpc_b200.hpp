@@ -28,6 +28,7 @@
 #include <stdexcept>
 #include <string>
 #include <utility>
+#include <vector>
 
 #include "mpc_b200.h"
 
@@ -89,6 +90,30 @@ class Mppi {
         if (seed != 0) cfg.seed = seed;
         Mppi m;
         detail::check(mpcb_mppi_create(&m.h_, &cfg), "mpcb_mppi_create");
+        return m;
+    }
+
+    // Mppi::new with the caller's OWN dynamics and cost (src/mppi.rs:9-10): the two functions as CUDA C++ source
+    //     template <typename real> void dynamics(real (&x)[4], real u, const real* p);   // x <- f(x, u)
+    //     template <typename real> real cost(const real (&x)[4], const real* p);
+    // compiled into the fused kernel at construction (mpcb_mppi_create_user); `params` are the p[] constants.
+    static Mppi create_user(const std::string& cuda_source, const std::vector<double>& params, double lambda, double std_dev,
+                            std::pair<double, double> limit, int precision = MPCB_F32, uint64_t seed = 0) {
+        mpcb_mppi_cfg cfg;
+        detail::check(mpcb_mppi_default_cfg(MPCB_MODEL_USER, &cfg), "mpcb_mppi_default_cfg");
+        cfg.horizon = static_cast<int32_t>(N);
+        cfg.samples = static_cast<int64_t>(K);
+        cfg.state_dim = static_cast<int32_t>(S);
+        cfg.lambda = lambda;
+        cfg.std_dev = std_dev;
+        cfg.limit_lo = limit.first;
+        cfg.limit_hi = limit.second;
+        cfg.precision = precision;
+        if (seed != 0) cfg.seed = seed;
+        Mppi m;
+        const mpcb_status st = mpcb_mppi_create_user(&m.h_, &cfg, cuda_source.c_str(), params.data(), static_cast<int32_t>(params.size()));
+        if (st == MPCB_RTC_ERROR) throw std::runtime_error(std::string("user model did not compile: ") + mpcb_last_error_string() + "\n" + mpcb_rtc_log());
+        detail::check(st, "mpcb_mppi_create_user");
         return m;
     }
 

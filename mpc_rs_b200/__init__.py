@@ -7,11 +7,11 @@ and a CUDA device every constructor raises.
 """
 from . import _abi
 from ._abi import MpcB200Error
-from .mppi import DeviceModel, Mppi, MppiError, comm_unique_id
+from .mppi import DeviceModel, Mppi, MppiError, UserModel, check_user_source, comm_unique_id, user_model
 from . import models
 from . import ukf
 from .ukf import BatchedUkf, UnscentedKalmanFilter, UkfError
 from .gaussian import Gaussian
 
-__all__ = ["Mppi", "MppiError", "DeviceModel", "MpcB200Error", "models", "comm_unique_id", "ukf", "BatchedUkf",
+__all__ = ["Mppi", "MppiError", "DeviceModel", "UserModel", "user_model", "check_user_source", "MpcB200Error", "models", "comm_unique_id", "ukf", "BatchedUkf",
            "UnscentedKalmanFilter", "UkfError", "Gaussian"]

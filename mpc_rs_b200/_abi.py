@@ -13,8 +13,9 @@ LIB_PATH = os.environ.get("MPCB_LIB_PATH") or os.path.join(_HERE, "libmpc_b200.s
 
 # ---- enums (include/mpc_b200.h) ----
 OK, NO_FINITE_COST, SUM_ZERO, U_INVALID, INVERSE_FAIL, CHOLESKY_FAIL, BAD_ARG, CUDA_ERROR, NCCL_ERROR, NOT_PREDICTED, \
-    PEER_TIMEOUT = range(11)
-MODEL_L, MODEL_NL, MODEL_NL6 = 0, 1, 2
+    PEER_TIMEOUT, RTC_ERROR = range(12)
+MODEL_L, MODEL_NL, MODEL_NL6, MODEL_USER = 0, 1, 2, 3
+USER_PARAMS = 24
 MODEL_PEN_LIN, MODEL_PEN_NL, MODEL_PEN6, MODEL_NL6_UKF = 16, 17, 18, 19
 F32, F64 = 0, 1
 DT_F32, DT_F64 = 0, 1
@@ -89,6 +90,9 @@ SYMBOLS = {
     "mpcb_model_defaults": (C.c_int, [C.c_int32, C.POINTER(ModelParams)]),
     "mpcb_mppi_default_cfg": (C.c_int, [C.c_int32, C.POINTER(MppiCfg)]),
     "mpcb_mppi_create": (C.c_int, [C.POINTER(_H), C.POINTER(MppiCfg)]),
+    "mpcb_mppi_create_user": (C.c_int, [C.POINTER(_H), C.POINTER(MppiCfg), C.c_char_p, C.POINTER(C.c_double), C.c_int32]),
+    "mpcb_mppi_check_user_source": (C.c_int, [C.c_char_p, C.c_int32]),
+    "mpcb_rtc_log": (C.c_char_p, []),
     "mpcb_mppi_destroy": (None, [_H]),
     "mpcb_mppi_compute": (C.c_int, [_H, _dp, _dp, _dp, C.POINTER(MppiInfo)]),
     "mpcb_mppi_compute_replay": (C.c_int, [_H, _dp, _dp, _vp, C.c_int32, C.c_int32, _dp, C.POINTER(MppiInfo)]),

@@ -106,6 +106,7 @@ const char* mpcb_status_string(mpcb_status s) {
         case MPCB_NCCL_ERROR: return "NCCL error";
         case MPCB_NOT_PREDICTED: return "update before predict";
         case MPCB_PEER_TIMEOUT: return "peer exchange timed out";
+        case MPCB_RTC_ERROR: return "user model did not compile";
         default: return "unknown status";
     }
 }

@@ -8,7 +8,10 @@
 #include <new>
 
 #include "mppi_kernel.cuh"
+#include "mppi_rtc.h"
 #include "nccl_shim.h"
+
+#include <string>
 
 using namespace mpcb;
 
@@ -28,6 +31,10 @@ struct mpcb_mppi {
     size_t smem = 0;
     ModelConsts mc;
     MppiKernelFn k_noise[3] = {nullptr, nullptr, nullptr};  // indexed by MppiNoise
+    // user-supplied model (mpcb_mppi_create_user): CUDA source compiled at create time, kernels live in `rtc`
+    bool user = false;
+    std::string user_src;
+    RtcModule rtc;
     // device
     double* d_x = nullptr;
     double* d_u = nullptr;
@@ -132,6 +139,10 @@ mpcb_status pick_kernels(mpcb_mppi* h) {
         auto smem_of = [&](int sb, int vt) { return f64 ? mppi_smem_bytes<double>(h->H, sb, vt != 0) : mppi_smem_bytes<float>(h->H, sb, vt != 0); };
         auto kernel_of = [&](int sb, int noise, int vt) -> MppiKernelFn {
             if (sb % spt) return nullptr;
+            if (h->user) {  // compiled once the shape is chosen; here only: does this flavour exist for user models
+                const bool have = spt == 1 && (vt ? (sb == 128 || sb == 256) : (sb == 128 || sb == 64));
+                return have ? reinterpret_cast<MppiKernelFn>(1) : nullptr;
+            }
             if (f64) return mppi_kernel_f64(h->cfg.model_id, sb, noise, vt);
             return spt == 2 ? mppi_kernel_f32x2(h->cfg.model_id, sb / 2, noise, vt) : mppi_kernel_f32(h->cfg.model_id, sb, noise, vt);
         };
@@ -182,8 +193,13 @@ mpcb_status pick_kernels(mpcb_mppi* h) {
         }
         pl.block = pl.sb / spt;
         pl.smem = smem_of(pl.sb, pl.vt);
+        if (h->user) {
+            rtc_unload(&h->rtc);
+            mpcb_status rst = rtc_compile_mppi_user(h->user_src.c_str(), f64, pl.block, pl.vt != 0, true, &h->rtc);
+            if (rst != MPCB_OK) return rst;
+        }
         for (int noise = 0; noise < 3; ++noise) {
-            pl.k[noise] = kernel_of(pl.sb, noise, pl.vt);
+            pl.k[noise] = h->user ? reinterpret_cast<MppiKernelFn>(h->rtc.kernel[noise]) : kernel_of(pl.sb, noise, pl.vt);
             if (!pl.k[noise]) {
                 set_error("no MPPI kernel for model %d", h->cfg.model_id);
                 return MPCB_BAD_ARG;
@@ -216,7 +232,7 @@ mpcb_status pick_kernels(mpcb_mppi* h) {
     Plan plan;
     mpcb_status st = make_plan(1, &plan);
     if (st != MPCB_OK) return st;
-    if (!f64) {
+    if (!f64 && !h->user) {
         const char* spt_env = getenv("MPCB_MPPI_SPT");
         const int forced = spt_env ? atoi(spt_env) : 0;
         Plan p2;
@@ -314,8 +330,9 @@ mpcb_status launch(mpcb_mppi* h, MppiParams& p) {
     const dim3 grid((unsigned)(h->C * h->chunks)), block((unsigned)h->block);
     h->seq += 1;
     p.seq = h->seq;
-    fn<<<grid, block, h->smem, h->stream>>>(p);
-    MPCB_CUDA_TRY(cudaGetLastError());
+    // explicit cudaLaunchKernel: `fn` is either a compiled-in __global__ function or the cudaKernel_t of a user model
+    void* args[1] = {&p};
+    MPCB_CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(fn), grid, block, args, h->smem, h->stream));
     h->launches += 1;
     h->call_idx += 1;
     h->costs_valid = h->cfg.keep_costs != 0;
@@ -474,6 +491,21 @@ extern "C" {
 mpcb_status mpcb_mppi_default_cfg(int32_t model_id, mpcb_mppi_cfg* c) {
     if (!c) return MPCB_BAD_ARG;
     memset(c, 0, sizeof(*c));
+    if (model_id == MPCB_MODEL_USER) {  // neutral values; the model itself comes with mpcb_mppi_create_user
+        c->model_id = model_id;
+        c->precision = MPCB_F32;
+        c->horizon = 8;
+        c->state_dim = 4;
+        c->samples = 65536;
+        c->controllers = 1;
+        c->world_size = 1;
+        c->seed = 0x6d70632d72730001ull;
+        c->lambda = 1.0;
+        c->std_dev = 1.0;
+        c->limit_lo = -HUGE_VAL;
+        c->limit_hi = HUGE_VAL;
+        return MPCB_OK;
+    }
     mpcb_status st = mpcb_model_defaults(model_id, &c->model);
     if (st != MPCB_OK) return st;
     c->model_id = model_id;
@@ -506,7 +538,8 @@ mpcb_status mpcb_mppi_default_cfg(int32_t model_id, mpcb_mppi_cfg* c) {
     }
 }
 
-mpcb_status mpcb_mppi_create(mpcb_mppi** out, const mpcb_mppi_cfg* cfg) {
+static mpcb_status create_impl(mpcb_mppi** out, const mpcb_mppi_cfg* cfg, const char* user_src, const double* params,
+                               int32_t n_params) {
     MPCB_REQUIRE(out && cfg, "null pointer");
     *out = nullptr;
     MPCB_REQUIRE(cfg->state_dim == 4, "the built-in models have S = 4");
@@ -542,11 +575,22 @@ mpcb_status mpcb_mppi_create(mpcb_mppi** out, const mpcb_mppi_cfg* cfg) {
         set_error("rank %d of %d has no samples (K = %lld)", (int)r, (int)G, K);
         return fail(MPCB_BAD_ARG);
     }
-    st = build_model_consts(cfg->model_id, cfg->model, cfg->model.dt, &h->mc);
-    if (st != MPCB_OK) return fail(st);
-    if (cfg->model_id != MPCB_MODEL_L && cfg->model_id != MPCB_MODEL_NL && cfg->model_id != MPCB_MODEL_NL6) {
-        set_error("model %d is not an MPPI model", cfg->model_id);
-        return fail(MPCB_BAD_ARG);
+    if (user_src != nullptr) {
+        h->user = true;
+        h->user_src = user_src;
+        h->cfg.model_id = MPCB_MODEL_USER;
+        memset(&h->mc, 0, sizeof(h->mc));
+        for (int i = 0; i < n_params; ++i) {
+            h->mc.k[i] = params[i];
+            h->mc.kf[i] = (float)params[i];
+        }
+    } else {
+        st = build_model_consts(cfg->model_id, cfg->model, cfg->model.dt, &h->mc);
+        if (st != MPCB_OK) return fail(st);
+        if (cfg->model_id != MPCB_MODEL_L && cfg->model_id != MPCB_MODEL_NL && cfg->model_id != MPCB_MODEL_NL6) {
+            set_error("model %d is not a built-in MPPI model (user models: mpcb_mppi_create_user)", cfg->model_id);
+            return fail(MPCB_BAD_ARG);
+        }
     }
     st = pick_kernels(h);
     if (st != MPCB_OK) return fail(st);
@@ -592,10 +636,29 @@ mpcb_status mpcb_mppi_create(mpcb_mppi** out, const mpcb_mppi_cfg* cfg) {
     return MPCB_OK;
 }
 
+mpcb_status mpcb_mppi_create(mpcb_mppi** out, const mpcb_mppi_cfg* cfg) { return create_impl(out, cfg, nullptr, nullptr, 0); }
+
+mpcb_status mpcb_mppi_create_user(mpcb_mppi** out, const mpcb_mppi_cfg* cfg, const char* cuda_source, const double* params,
+                                  int32_t n_params) {
+    MPCB_REQUIRE(cuda_source != nullptr, "null source");
+    MPCB_REQUIRE(n_params >= 0 && n_params <= MPCB_USER_PARAMS && (n_params == 0 || params != nullptr), "bad params");
+    return create_impl(out, cfg, cuda_source, params, n_params);
+}
+
+mpcb_status mpcb_mppi_check_user_source(const char* cuda_source, int32_t precision) {
+    MPCB_REQUIRE(cuda_source != nullptr, "null source");
+    MPCB_REQUIRE(precision == MPCB_F32 || precision == MPCB_F64, "bad precision");
+    RtcModule m;
+    return rtc_compile_mppi_user(cuda_source, precision == MPCB_F64, 128, true, false, &m);
+}
+
+const char* mpcb_rtc_log(void) { return rtc_log(); }
+
 void mpcb_mppi_destroy(mpcb_mppi* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    rtc_unload(&h->rtc);
     if (h->comm) nccl_destroy(h->comm);
     for (int r = 0; r < kMergeFan; ++r)
         if (h->peer_ipc[r] && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);

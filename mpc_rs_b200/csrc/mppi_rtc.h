@@ -1,0 +1,20 @@
+// mppi_rtc.h — run-time compilation (NVRTC) of the fused MPPI kernel around a user-supplied dynamics/cost pair.
+#pragma once
+
+#include "common.cuh"
+
+namespace mpcb {
+
+struct RtcModule {
+    void* library = nullptr;                 // cudaLibrary_t
+    void* kernel[3] = {nullptr, nullptr, nullptr};  // cudaKernel_t per MppiNoise, usable wherever a `const void* func` is
+};
+
+// Compiles mppi_rollout_kernel<ModelUser, real, block, noise, 1, vt> for the three noise modes around `user_src` and,
+// when `load` is set, loads the cubin on the current device.  The compile log (errors AND warnings) is kept per thread
+// for mpcb_rtc_log().  MPCB_RTC_ERROR on a compile failure.
+mpcb_status rtc_compile_mppi_user(const char* user_src, bool f64, int block, bool vt, bool load, RtcModule* out);
+void rtc_unload(RtcModule* m);
+const char* rtc_log();
+
+}  // namespace mpcb

@@ -25,6 +25,34 @@ class DeviceModel:
     name: str
 
 
+@dataclass(frozen=True)
+class UserModel(DeviceModel):
+    """`dynamics` and `cost` of Mppi::new (src/mppi.rs:9-10) as CUDA C++ source + constants (mpcb_mppi_create_user):
+
+        template <typename real> void dynamics(real (&x)[4], real u, const real* p);   // x <- f(x, u)
+        template <typename real> real cost(const real (&x)[4], const real* p);
+
+    Build one with `user_model(source, params)`."""
+    source: str = ""
+    params: tuple = ()
+
+
+def user_model(source: str, params=(), name: str = "user") -> UserModel:
+    params = tuple(float(v) for v in params)
+    if len(params) > A.USER_PARAMS:
+        raise ValueError(f"at most {A.USER_PARAMS} parameters")
+    return UserModel(A.MODEL_USER, name, source, params)
+
+
+def check_user_source(source: str, precision: str = "f32") -> str:
+    """Compile-only check (NVRTC, no GPU needed); returns the compiler log, raises MpcB200Error if it does not compile."""
+    st = A.lib().mpcb_mppi_check_user_source(source.encode(), {"f32": A.F32, "f64": A.F64}[precision])
+    log = (A.lib().mpcb_rtc_log() or b"").decode()
+    if st != A.OK:
+        raise A.MpcB200Error(st, "user model did not compile:\n" + log)
+    return log
+
+
 class MppiError(RuntimeError):
     """Err(&'static str) of Mppi::compute (src/mppi.rs:69,77,88); str(e) is the reference's message."""
 
@@ -59,7 +87,7 @@ class Mppi:
         cfg.keep_costs = int(bool(keep_costs))
         if dt is not None:
             cfg.model.dt = float(dt)
-        for k, v in (params or {}).items():
+        for k, v in ({} if isinstance(model, UserModel) else (params or {})).items():
             if k == "cost":
                 for i, c in enumerate(v):
                     cfg.model.cost[i] = float(c)
@@ -69,7 +97,15 @@ class Mppi:
         self.N, self.K, self.S, self.C = int(N), int(K), int(S), int(controllers)
         self.precision = precision
         self._h = A._H()
-        A.check(L.mpcb_mppi_create(C.byref(self._h), C.byref(cfg)))
+        if isinstance(model, UserModel):
+            pa = (C.c_double * max(1, len(model.params)))(*model.params)
+            st = L.mpcb_mppi_create_user(C.byref(self._h), C.byref(cfg), model.source.encode(), pa, len(model.params))
+            if st == A.RTC_ERROR:
+                raise A.MpcB200Error(st, "user model did not compile: " + L.mpcb_last_error_string().decode() + "\n"
+                                      + (L.mpcb_rtc_log() or b"").decode())
+            A.check(st)
+        else:
+            A.check(L.mpcb_mppi_create(C.byref(self._h), C.byref(cfg)))
         self.K_local = L.mpcb_mppi_local_samples(self._h)
         self.info = None
 

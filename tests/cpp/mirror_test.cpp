@@ -69,6 +69,47 @@ int main() {
         try { bad.unwrap(); } catch (const std::runtime_error& e) { threw = std::strcmp(e.what(), "Cannot calculate max") == 0; }
         EXPECT(threw, "unwrap() must throw the reference's message");
     }
+    // ---- Mppi::create_user: examples/mppi4.rs's dynamics and cost handed over as source (the fn pointers of Mppi::new,
+    //      src/mppi.rs:9-10) must reproduce the oracle's model L
+    {
+        constexpr std::size_t N = 8, K = 8192;
+        const std::string src = R"SRC(
+template <typename real> void dynamics(real (&x)[4], real u, const real* p) {
+    // p = a1, b1, a2, b2, DT  (examples/mppi4.rs:81-88: semi-implicit Euler, x3 x2 x1 x0 in that order)
+    x[3] += (p[0] * x[2] - p[1] * u) * p[4];
+    x[2] += x[3] * p[4];
+    x[1] += (p[2] * x[2] + p[3] * u) * p[4];
+    x[0] += x[1] * p[4];
+}
+template <typename real> real cost(const real (&x)[4], const real* p) {
+    const real xc = mpcb::clampm(x[0], (real)-2.0, (real)2.0);
+    const real a = mpcb::clampm(x[1] + (real)2.0 * xc, (real)-5.0, (real)5.0);
+    const real b = x[2] + (real)0.35 * mpcb::clampm(x[0], (real)-0.75, (real)0.75);
+    return (real)2.0 * (xc * xc) + (real)3.0 * (a * a) + (real)5.0 * (b * b) + (real)1.2 * (x[3] * x[3]);
+}
+)SRC";
+        mpcb_model_params p;
+        orc_model_defaults(MPCB_MODEL_L, &p);
+        const double D = (p.m1 + p.m2 + p.j1 / (p.r_w * p.r_w)) * (p.m2 * p.l * p.l + p.j2) - p.m2 * p.m2 * p.l * p.l;
+        const std::vector<double> prm{(p.m1 + p.m2 + p.j1 / (p.r_w * p.r_w)) / D * p.m2 * p.g * p.l, p.m2 * p.l / D / p.r_w * p.kt,
+                                      -p.m2 * p.m2 * p.g * p.l * p.l / D, (p.m2 * p.l * p.l + p.j2) / D / p.r_w * p.kt, p.dt};
+        auto mu = mppi::Mppi<N, K, 4>::create_user(src, prm, 0.5, 3.0, {-20.0, 20.0}, MPCB_F64);
+        std::mt19937_64 rng(17);
+        std::normal_distribution<double> nd(0.0, 3.0);
+        const std::array<double, 4> x{0.5, 0.0, 0.1, 0.0};
+        std::array<double, N> u{};
+        std::vector<double> eps(K * N);
+        for (auto& e : eps) e = nd(rng);
+        double u_ref[N];
+        orc_mppi_out info;
+        EXPECT(orc_mppi_compute(MPCB_MODEL_L, &p, K, N, 0.5, 3.0, -20.0, 20.0, x.data(), u.data(), eps.data(), u_ref, nullptr, &info) == 0, "oracle");
+        const auto r = mu.compute_replay(x, u, eps.data());
+        EXPECT(r.ok && rel_err(r.value, u_ref) < 1e-9 && mu.info().argmax == info.argmax, "user model L: %.3e", r.ok ? rel_err(r.value, u_ref) : -1.0);
+        bool threw = false;
+        try { (void)mppi::Mppi<N, K, 4>::create_user("void dynamics() {}", {}, 0.5, 3.0, {-1.0, 1.0}); }
+        catch (const std::runtime_error& e) { threw = std::strstr(e.what(), "did not compile") != nullptr; }
+        EXPECT(threw, "a user model that does not compile must throw with the compiler log");
+    }
     // ---- mpc::ukf::UnscentedKalmanFilter (n=4, o=3), examples/ukf-pen2.rs constants, 5 predict/update pairs vs the oracle
     {
         const std::array<double, 16> Q{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0.25};

@@ -183,3 +183,21 @@ def test_two_rank_exchange_over_gloo():
     for rank, uid_ok, err, arg_ok in res:
         assert uid_ok and arg_ok
         assert err < 1e-12  # sharding changes only the reduction order
+
+
+def test_user_model_source_compiles_without_a_gpu():
+    """mpcb_mppi_check_user_source: the kernel headers embedded in the library compile under NVRTC around a user's
+    dynamics/cost (both precisions), and a broken source comes back as MPCB_RTC_ERROR with the compiler's log."""
+    import mpc_rs_b200 as M
+    from mpc_rs_b200 import _abi as A
+    ok = """
+    template <typename real> void dynamics(real (&x)[4], real u, const real* p) { x[0] += x[1] * p[0]; x[1] += u * p[0]; }
+    template <typename real> real cost(const real (&x)[4], const real* p) { return x[0] * x[0] + p[1] * (x[1] * x[1]); }
+    """
+    for prec in ("f32", "f64"):
+        assert "error" not in M.check_user_source(ok, prec)
+    import pytest
+    with pytest.raises(M.MpcB200Error) as e:
+        M.check_user_source("float cost(const float (&x)[4], const float* p) { return nope; }")
+    assert e.value.status == A.RTC_ERROR and "nope" in str(e.value) and "user_model.cu(1)" in str(e.value)
+    assert A.status_string(A.RTC_ERROR) == "user model did not compile"
