@@ -69,7 +69,8 @@ typedef enum mpcb_model {
     MPCB_MODEL_PEN_LIN = 16, /* n=4,o=2  fx/hx of examples/ukf-pen.rs:76-91 */
     MPCB_MODEL_PEN_NL = 17,  /* n=4,o=3  fx/hx of examples/ukf-pen2.rs:31-53 */
     MPCB_MODEL_PEN6 = 18,    /* n=6,o=5  fx/hx of examples/ukf-pen3.rs:35-63 (x[2].cos() as written) */
-    MPCB_MODEL_NL6_UKF = 19  /* n=6,o=5  dynamics_short(.,.,dt,0)/hx of examples/mppi4-non-liner-ukf.rs:149-179 */
+    MPCB_MODEL_NL6_UKF = 19, /* n=6,o=5  dynamics_short(.,.,dt,0)/hx of examples/mppi4-non-liner-ukf.rs:149-179 */
+    MPCB_MODEL_USER_UKF = 20 /* fx + hx supplied as CUDA source to mpcb_ukf_create_user */
 } mpcb_model;
 
 /* Physical constants of the two-wheeled pendulum + cost weights.  mpcb_model_defaults() fills the
@@ -266,6 +267,21 @@ mpcb_status mpcb_ukf_default_cfg(int32_t model_id, mpcb_ukf_cfg* out);
 /* Q[n][n], R[o][o], P0[n][n] the model's example ships with (row-major). */
 mpcb_status mpcb_ukf_default_noise(int32_t model_id, double dt, double* Q, double* R, double* P0);
 mpcb_status mpcb_ukf_create(mpcb_ukf** out, const mpcb_ukf_cfg* cfg);
+/* User-supplied process and measurement models.  predict(u, fx) / update(&z, hx) take closures
+ * `fx: Fn(&SVector<f64,N>, f64) -> SVector<f64,N>`, `hx: Fn(&SVector<f64,N>) -> SVector<f64,O>` (src/ukf.rs:44-46,54-56);
+ * here the two functions are CUDA C++ source compiled into the batched UKF kernel at create time (NVRTC), with
+ * cfg->n in 1..6 and cfg->o in 1..5 written as literals in the signatures:
+ *
+ *     void fx(double (&x)[N], double u, double dt, const double* p);        // x <- f(x, u), in place
+ *     void hx(const double (&x)[N], double (&z)[O], const double* p);       // z <- h(x)
+ *
+ * dt is the dt of mpcb_ukf_predict / mpcb_ukf_step (cfg->model.dt when that is 0); p[0..n_params) the caller's
+ * constants (n_params <= MPCB_USER_PARAMS).  cfg->model_id and the physical fields of cfg->model are ignored; sqrt_mode, sigma_order and exact
+ * (no FMA contraction) apply as for the built-in models.  mpcb_ukf_default_cfg(MPCB_MODEL_USER_UKF) gives the
+ * library-UKF defaults (eigen square root, library sigma order) with n = o = 0 for the caller to fill in. */
+mpcb_status mpcb_ukf_create_user(mpcb_ukf** out, const mpcb_ukf_cfg* cfg, const char* cuda_source, const double* params,
+                                 int32_t n_params);
+mpcb_status mpcb_ukf_check_user_source(const char* cuda_source, int32_t n, int32_t o);
 void mpcb_ukf_destroy(mpcb_ukf* h);
 
 /* UnscentedKalmanFilter::new(x,p,q,r) (src/ukf.rs:30): same x[n], P[n][n] (row-major) for every filter */

@@ -41,7 +41,8 @@ enum class DeviceModel : int32_t {
     PEN_LIN = MPCB_MODEL_PEN_LIN,  // examples/ukf-pen.rs:76-91
     PEN_NL = MPCB_MODEL_PEN_NL,    // examples/ukf-pen2.rs:31-53
     PEN6 = MPCB_MODEL_PEN6,        // examples/ukf-pen3.rs:35-63
-    NL6_UKF = MPCB_MODEL_NL6_UKF   // examples/mppi4-non-liner-ukf.rs:149-179
+    NL6_UKF = MPCB_MODEL_NL6_UKF,  // examples/mppi4-non-liner-ukf.rs:149-179
+    USER_UKF = MPCB_MODEL_USER_UKF  // fx / hx supplied as CUDA source (create_user)
 };
 
 template <typename T>
@@ -215,6 +216,20 @@ class UkfBase {
         check(mpcb_ukf_create(&h_, &cfg), "mpcb_ukf_create");
         check(mpcb_ukf_init(h_, x.data(), p.data(), q.data(), r.data()), "mpcb_ukf_init");
     }
+    // the caller's own fx / hx closures (src/ukf.rs:44-46,54-56) as CUDA C++ source — mpcb_ukf_create_user:
+    //     void fx(double (&x)[N], double u, double dt, const double* p);   void hx(const double (&x)[N], double (&z)[O], const double* p);
+    UkfBase(const State& x, const CovN& p, const CovN& q, const CovO& r, const std::string& cuda_source, const std::vector<double>& params)
+        : h_(nullptr), model_(DeviceModel::USER_UKF) {
+        mpcb_ukf_cfg cfg;
+        check(mpcb_ukf_default_cfg(MPCB_MODEL_USER_UKF, &cfg), "mpcb_ukf_default_cfg");
+        cfg.n = static_cast<int32_t>(NS);
+        cfg.o = static_cast<int32_t>(NO);
+        cfg.batch = 1;
+        const mpcb_status st = mpcb_ukf_create_user(&h_, &cfg, cuda_source.c_str(), params.data(), static_cast<int32_t>(params.size()));
+        if (st == MPCB_RTC_ERROR) throw std::runtime_error(std::string("user model did not compile: ") + mpcb_last_error_string() + "\n" + mpcb_rtc_log());
+        check(st, "mpcb_ukf_create_user");
+        check(mpcb_ukf_init(h_, x.data(), p.data(), q.data(), r.data()), "mpcb_ukf_init");
+    }
     void same_model(DeviceModel m) const {
         if (m != model_) throw std::invalid_argument("fx/hx must be the device model the filter was built with");
     }
@@ -239,6 +254,11 @@ class UnscentedKalmanFilter : public detail::UkfBase<4, 3> {
                                         DeviceModel model = DeviceModel::PEN_NL) {
         return UnscentedKalmanFilter(x, p, q, r, model);
     }
+    // new(x, p, q, r) for a filter whose predict/update get the caller's own fx / hx (CUDA source, params = p[])
+    static UnscentedKalmanFilter create_user(const State& x, const CovN& p, const CovN& q, const CovO& r, const std::string& cuda_source,
+                                             const std::vector<double>& params = {}) {
+        return UnscentedKalmanFilter(x, p, q, r, cuda_source, params);
+    }
 
    private:
     using UkfBase::UkfBase;
@@ -252,6 +272,10 @@ class UnscentedKalmanFilter : public detail::UkfBase<6, 5> {
     static UnscentedKalmanFilter create(const State& x, const CovN& p, const CovN& q, const CovO& r,
                                         DeviceModel model = DeviceModel::NL6_UKF) {
         return UnscentedKalmanFilter(x, p, q, r, model);
+    }
+    static UnscentedKalmanFilter create_user(const State& x, const CovN& p, const CovN& q, const CovO& r, const std::string& cuda_source,
+                                             const std::vector<double>& params = {}) {
+        return UnscentedKalmanFilter(x, p, q, r, cuda_source, params);
     }
     void set_q(const CovN& q) { detail::check(mpcb_ukf_set_q(h_, q.data()), "mpcb_ukf_set_q"); }  // src/ukf2.rs:96-98
     // called by examples/mppi4-ukf-commu.rs:280 but missing in the reference

@@ -10,8 +10,8 @@ from ._abi import MpcB200Error
 from .mppi import DeviceModel, Mppi, MppiError, UserModel, check_user_source, comm_unique_id, user_model
 from . import models
 from . import ukf
-from .ukf import BatchedUkf, UnscentedKalmanFilter, UkfError
+from .ukf import BatchedUkf, UnscentedKalmanFilter, UkfError, UserUkfModel, check_user_ukf_source, user_ukf_model
 from .gaussian import Gaussian
 
-__all__ = ["Mppi", "MppiError", "DeviceModel", "UserModel", "user_model", "check_user_source", "MpcB200Error", "models", "comm_unique_id", "ukf", "BatchedUkf",
+__all__ = ["Mppi", "MppiError", "DeviceModel", "UserModel", "user_model", "check_user_source", "UserUkfModel", "user_ukf_model", "check_user_ukf_source", "MpcB200Error", "models", "comm_unique_id", "ukf", "BatchedUkf",
            "UnscentedKalmanFilter", "UkfError", "Gaussian"]

@@ -16,7 +16,7 @@ OK, NO_FINITE_COST, SUM_ZERO, U_INVALID, INVERSE_FAIL, CHOLESKY_FAIL, BAD_ARG, C
     PEER_TIMEOUT, RTC_ERROR = range(12)
 MODEL_L, MODEL_NL, MODEL_NL6, MODEL_USER = 0, 1, 2, 3
 USER_PARAMS = 24
-MODEL_PEN_LIN, MODEL_PEN_NL, MODEL_PEN6, MODEL_NL6_UKF = 16, 17, 18, 19
+MODEL_PEN_LIN, MODEL_PEN_NL, MODEL_PEN6, MODEL_NL6_UKF, MODEL_USER_UKF = 16, 17, 18, 19, 20
 F32, F64 = 0, 1
 DT_F32, DT_F64 = 0, 1
 SQRT_CHOLESKY, SQRT_EIG = 0, 1
@@ -118,6 +118,8 @@ SYMBOLS = {
     "mpcb_ukf_default_cfg": (C.c_int, [C.c_int32, C.POINTER(UkfCfg)]),
     "mpcb_ukf_default_noise": (C.c_int, [C.c_int32, C.c_double, _dp, _dp, _dp]),
     "mpcb_ukf_create": (C.c_int, [C.POINTER(_H), C.POINTER(UkfCfg)]),
+    "mpcb_ukf_create_user": (C.c_int, [C.POINTER(_H), C.POINTER(UkfCfg), C.c_char_p, C.POINTER(C.c_double), C.c_int32]),
+    "mpcb_ukf_check_user_source": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32]),
     "mpcb_ukf_destroy": (None, [_H]),
     "mpcb_ukf_init": (C.c_int, [_H, _dp, _dp, _dp, _dp]),
     "mpcb_ukf_set_state": (C.c_int, [_H, _dp, _dp]),

@@ -119,34 +119,24 @@ void rtc_unload(RtcModule* m) {
     }
 }
 
-mpcb_status rtc_compile_mppi_user(const char* user_src, bool f64, int block, bool vt, bool load, RtcModule* out) {
+namespace {
+
+// compiles `src` for sm_100a, resolves the three kernels named by `names` and (load) loads the cubin on the current device
+mpcb_status compile_and_load(const std::string& src, const std::string (&names)[3], std::vector<const char*> opts, bool load, RtcModule* out) {
     g_log.clear();
     NvrtcApi* nv = nvrtc_api();
     if (!nv) {
         set_error("user models need NVRTC: libnvrtc.so.12 could not be opened (%s); set MPCB_NVRTC_PATH", dlerror());
         return MPCB_RTC_ERROR;
     }
-    std::string src = "#include \"mppi_kernel.cuh\"\n#line 1 \"user_model.cu\"\n";
-    src += user_src;
-    src += "\n#line 1 \"mpcb_user_adapter.cu\"\n";
-    src += kAdapter;
     nvrtcProgram prog = nullptr;
     nvrtcResult r = nv->CreateProgram(&prog, src.c_str(), "mpcb_user_model.cu", kRtcHeaderCount, kRtcHeaderSources, kRtcHeaderNames);
     if (r != NVRTC_SUCCESS) {
         set_error("nvrtcCreateProgram: %s", nv->GetErrorString(r));
         return MPCB_RTC_ERROR;
     }
-    std::string names[3];
-    for (int noise = 0; noise < 3; ++noise) {
-        char buf[160];
-        snprintf(buf, sizeof(buf), "mpcb::mppi_rollout_kernel<mpcb::ModelUser, %s, %d, %d, 1, %s>", f64 ? "double" : "float", block, noise,
-                 vt ? "true" : "false");
-        names[noise] = buf;
-        nv->AddNameExpression(prog, names[noise].c_str());
-    }
-    // the FP64 path is reference arithmetic: no FMA contraction (like the -fmad=false of the built-in FP64 kernels)
-    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
-    if (f64) opts.push_back("-fmad=false");
+    for (int i = 0; i < 3; ++i) nv->AddNameExpression(prog, names[i].c_str());
+    opts.insert(opts.begin(), {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"});
     r = nv->CompileProgram(prog, (int)opts.size(), opts.data());
     size_t n = 0;
     if (nv->GetProgramLogSize(prog, &n) == NVRTC_SUCCESS && n > 1) {
@@ -180,15 +170,15 @@ mpcb_status rtc_compile_mppi_user(const char* user_src, bool f64, int block, boo
                 st = MPCB_CUDA_ERROR;
             } else {
                 out->library = lib;
-                for (int noise = 0; noise < 3 && st == MPCB_OK; ++noise) {
+                for (int i = 0; i < 3 && st == MPCB_OK; ++i) {
                     const char* low = nullptr;
                     cudaKernel_t k = nullptr;
-                    if (nv->GetLoweredName(prog, names[noise].c_str(), &low) != NVRTC_SUCCESS || !low ||
+                    if (nv->GetLoweredName(prog, names[i].c_str(), &low) != NVRTC_SUCCESS || !low ||
                         la->GetKernel(&k, lib, low) != cudaSuccess) {
-                        set_error("kernel %s not found in the compiled user module", names[noise].c_str());
+                        set_error("kernel %s not found in the compiled user module", names[i].c_str());
                         st = MPCB_RTC_ERROR;
                     }
-                    out->kernel[noise] = k;
+                    out->kernel[i] = k;
                 }
                 if (st != MPCB_OK) rtc_unload(out);
             }
@@ -196,6 +186,43 @@ mpcb_status rtc_compile_mppi_user(const char* user_src, bool f64, int block, boo
     }
     nv->DestroyProgram(&prog);
     return st;
+}
+
+}  // namespace
+
+mpcb_status rtc_compile_mppi_user(const char* user_src, bool f64, int block, bool vt, bool load, RtcModule* out) {
+    std::string src = "#include \"mppi_kernel.cuh\"\n#line 1 \"user_model.cu\"\n";
+    src += user_src;
+    src += "\n#line 1 \"mpcb_user_adapter.cu\"\n";
+    src += kAdapter;
+    std::string names[3];
+    for (int noise = 0; noise < 3; ++noise) {
+        char buf[160];
+        snprintf(buf, sizeof(buf), "mpcb::mppi_rollout_kernel<mpcb::ModelUser, %s, %d, %d, 1, %s>", f64 ? "double" : "float", block, noise,
+                 vt ? "true" : "false");
+        names[noise] = buf;
+    }
+    // the FP64 path is reference arithmetic: no FMA contraction (like the -fmad=false of the built-in FP64 kernels)
+    std::vector<const char*> opts;
+    if (f64) opts.push_back("-fmad=false");
+    return compile_and_load(src, names, opts, load, out);
+}
+
+mpcb_status rtc_compile_ukf_user(const char* user_src, int n, int o, int sqrt_mode, int order, bool fast, bool load, RtcModule* out) {
+    // helpers first, then the user's fx / hx, then the kernel that calls them
+    std::string src = "#include \"models.cuh\"\n#line 1 \"user_model.cu\"\n";
+    src += user_src;
+    src += "\n#line 1 \"mpcb_user_adapter.cu\"\n#define MPCB_UKF_USER 1\n#include \"ukf_kernel.cuh\"\n";
+    std::string names[3];
+    for (int mode = 0; mode < 3; ++mode) {
+        char buf[160];
+        snprintf(buf, sizeof(buf), "mpcb::ukf_kernel<%d, %d, %d, %d, %d, %d, %s>", n, o, (int)MPCB_MODEL_USER_UKF, sqrt_mode, order, mode,
+                 fast ? "true" : "false");
+        names[mode] = buf;
+    }
+    std::vector<const char*> opts;
+    if (!fast) opts.push_back("-fmad=false");  // cfg.exact: the reference's operation order without FMA
+    return compile_and_load(src, names, opts, load, out);
 }
 
 }  // namespace mpcb

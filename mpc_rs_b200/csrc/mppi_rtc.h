@@ -14,6 +14,9 @@ struct RtcModule {
 // when `load` is set, loads the cubin on the current device.  The compile log (errors AND warnings) is kept per thread
 // for mpcb_rtc_log().  MPCB_RTC_ERROR on a compile failure.
 mpcb_status rtc_compile_mppi_user(const char* user_src, bool f64, int block, bool vt, bool load, RtcModule* out);
+// Same for the batched UKF: ukf_kernel<n, o, MPCB_MODEL_USER_UKF, sqrt, order, mode, fast> for the three UkfMode values
+// (kernel[0..2] = predict, update, fused) around the user's fx / hx.  `fast` = FMA contraction on (cfg.exact == 0).
+mpcb_status rtc_compile_ukf_user(const char* user_src, int n, int o, int sqrt_mode, int order, bool fast, bool load, RtcModule* out);
 void rtc_unload(RtcModule* m);
 const char* rtc_log();
 

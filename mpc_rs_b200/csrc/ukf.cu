@@ -4,6 +4,9 @@
 
 #include <new>
 
+#include <string>
+
+#include "mppi_rtc.h"
 #include "ukf_kernel.cuh"
 
 namespace mpcb {
@@ -40,6 +43,7 @@ struct mpcb_ukf {
     cudaStream_t stream = nullptr;
     ModelConsts mc;
     UkfKernelFn k_predict = nullptr, k_update = nullptr, k_fused = nullptr;
+    RtcModule rtc;  // user-supplied fx / hx (mpcb_ukf_create_user): the kernels above live in this module
     double Q[36], R[25];
     double wm0 = 0, wc0 = 0, wi = 0, cC = 0;
     double* d_x = nullptr;
@@ -118,8 +122,10 @@ void fill_params(const mpcb_ukf* h, UkfParams* p) {
 
 mpcb_status launch(mpcb_ukf* h, UkfKernelFn fn, const UkfParams& p) {
     const unsigned grid = (unsigned)((h->B + kThreads - 1) / kThreads);
-    fn<<<grid, kThreads, 0, h->stream>>>(p);
-    MPCB_CUDA_TRY(cudaGetLastError());
+    // explicit cudaLaunchKernel: `fn` is a compiled-in __global__ function or the cudaKernel_t of a user model
+    UkfParams pp = p;
+    void* args[1] = {&pp};
+    MPCB_CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(fn), dim3(grid), dim3(kThreads), args, 0, h->stream));
     h->launches += 1;
     return MPCB_OK;
 }
@@ -180,6 +186,13 @@ extern "C" {
 mpcb_status mpcb_ukf_default_cfg(int32_t model_id, mpcb_ukf_cfg* c) {
     if (!c) return MPCB_BAD_ARG;
     memset(c, 0, sizeof(*c));
+    if (model_id == MPCB_MODEL_USER_UKF) {  // the library UKF's defaults; n, o and the model come from the caller
+        c->model_id = model_id;
+        c->sqrt_mode = MPCB_SQRT_EIG;
+        c->sigma_order = MPCB_ORDER_LIBRARY;
+        c->batch = 1;
+        return MPCB_OK;
+    }
     int n, o;
     mpcb_status st = model_dims(model_id, &n, &o);
     if (st != MPCB_OK) return st;
@@ -227,17 +240,26 @@ mpcb_status mpcb_ukf_default_noise(int32_t model_id, double dt, double* Q, doubl
     return MPCB_OK;
 }
 
-mpcb_status mpcb_ukf_create(mpcb_ukf** out, const mpcb_ukf_cfg* cfg) {
+static mpcb_status ukf_create_impl(mpcb_ukf** out, const mpcb_ukf_cfg* cfg, const char* user_src, const double* params,
+                                   int32_t n_params) {
     MPCB_REQUIRE(out && cfg, "null pointer");
     *out = nullptr;
     int n, o;
-    mpcb_status st = model_dims(cfg->model_id, &n, &o);
-    if (st != MPCB_OK) return st;
-    MPCB_REQUIRE(cfg->n == n && cfg->o == o, "n/o do not match the model");
+    mpcb_status st = MPCB_OK;
+    if (user_src != nullptr) {
+        n = cfg->n;
+        o = cfg->o;
+        MPCB_REQUIRE(n >= 1 && n <= 6 && o >= 1 && o <= 5, "user UKF models: n in 1..6, o in 1..5");
+    } else {
+        st = model_dims(cfg->model_id, &n, &o);
+        if (st != MPCB_OK) return st;
+        MPCB_REQUIRE(cfg->n == n && cfg->o == o, "n/o do not match the model");
+    }
     MPCB_REQUIRE(cfg->batch >= 1, "batch must be >= 1");
     MPCB_REQUIRE(cfg->sqrt_mode == MPCB_SQRT_CHOLESKY || cfg->sqrt_mode == MPCB_SQRT_EIG, "bad sqrt_mode");
     MPCB_REQUIRE(cfg->sigma_order == MPCB_ORDER_LIBRARY || cfg->sigma_order == MPCB_ORDER_INTERLEAVED, "bad sigma_order");
-    MPCB_REQUIRE(!(n == 6 && cfg->sigma_order != MPCB_ORDER_LIBRARY), "n = 6 supports the library sigma order only");
+    MPCB_REQUIRE(user_src != nullptr || !(n == 6 && cfg->sigma_order != MPCB_ORDER_LIBRARY),
+                 "n = 6 supports the library sigma order only");
     int ndev = 0;
     MPCB_CUDA_TRY(cudaGetDeviceCount(&ndev));
     MPCB_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "no such CUDA device (this library has no CPU path)");
@@ -254,9 +276,18 @@ mpcb_status mpcb_ukf_create(mpcb_ukf** out, const mpcb_ukf_cfg* cfg) {
         mpcb_ukf_destroy(h);
         return s;
     };
-    st = build_model_consts(cfg->model_id, cfg->model, cfg->model.dt, &h->mc);
-    if (st != MPCB_OK) return fail(st);
-    {
+    if (user_src != nullptr) {
+        h->cfg.model_id = MPCB_MODEL_USER_UKF;
+        memset(&h->mc, 0, sizeof(h->mc));
+        for (int i = 0; i < n_params; ++i) {
+            h->mc.k[i] = params[i];
+            h->mc.kf[i] = (float)params[i];
+        }
+    } else {
+        st = build_model_consts(cfg->model_id, cfg->model, cfg->model.dt, &h->mc);
+        if (st != MPCB_OK) return fail(st);
+    }
+    if (user_src == nullptr) {
         // measurement constants, evaluated like the reference's expressions
         const double PI = 3.14159265358979323846264338327950288;
         const mpcb_model_params& mp = cfg->model;
@@ -286,10 +317,18 @@ mpcb_status mpcb_ukf_create(mpcb_ukf** out, const mpcb_ukf_cfg* cfg) {
         h->wm0 = LAMBDA / Cc;
         h->wc0 = LAMBDA / Cc + 1.0 - ALPHA * ALPHA + BETA;
     }
-    auto pick = cfg->exact ? ((n == 4) ? ukf_kernel_n4 : ukf_kernel_n6) : ((n == 4) ? ukf_kernel_n4_fast : ukf_kernel_n6_fast);
-    h->k_predict = pick(cfg->model_id, cfg->sqrt_mode, cfg->sigma_order, UKF_PREDICT);
-    h->k_update = pick(cfg->model_id, cfg->sqrt_mode, cfg->sigma_order, UKF_UPDATE);
-    h->k_fused = pick(cfg->model_id, cfg->sqrt_mode, cfg->sigma_order, UKF_FUSED);
+    if (user_src != nullptr) {
+        st = rtc_compile_ukf_user(user_src, n, o, cfg->sqrt_mode, cfg->sigma_order, cfg->exact == 0, true, &h->rtc);
+        if (st != MPCB_OK) return fail(st);
+        h->k_predict = reinterpret_cast<UkfKernelFn>(h->rtc.kernel[UKF_PREDICT]);
+        h->k_update = reinterpret_cast<UkfKernelFn>(h->rtc.kernel[UKF_UPDATE]);
+        h->k_fused = reinterpret_cast<UkfKernelFn>(h->rtc.kernel[UKF_FUSED]);
+    } else {
+        auto pick = cfg->exact ? ((n == 4) ? ukf_kernel_n4 : ukf_kernel_n6) : ((n == 4) ? ukf_kernel_n4_fast : ukf_kernel_n6_fast);
+        h->k_predict = pick(cfg->model_id, cfg->sqrt_mode, cfg->sigma_order, UKF_PREDICT);
+        h->k_update = pick(cfg->model_id, cfg->sqrt_mode, cfg->sigma_order, UKF_UPDATE);
+        h->k_fused = pick(cfg->model_id, cfg->sqrt_mode, cfg->sigma_order, UKF_FUSED);
+    }
     if (!h->k_predict || !h->k_update || !h->k_fused) {
         set_error("no UKF kernel for model %d / sqrt %d / order %d", cfg->model_id, cfg->sqrt_mode, cfg->sigma_order);
         return fail(MPCB_BAD_ARG);
@@ -318,10 +357,27 @@ mpcb_status mpcb_ukf_create(mpcb_ukf** out, const mpcb_ukf_cfg* cfg) {
     return MPCB_OK;
 }
 
+mpcb_status mpcb_ukf_create(mpcb_ukf** out, const mpcb_ukf_cfg* cfg) { return ukf_create_impl(out, cfg, nullptr, nullptr, 0); }
+
+mpcb_status mpcb_ukf_create_user(mpcb_ukf** out, const mpcb_ukf_cfg* cfg, const char* cuda_source, const double* params,
+                                 int32_t n_params) {
+    MPCB_REQUIRE(cuda_source != nullptr, "null source");
+    MPCB_REQUIRE(n_params >= 0 && n_params <= MPCB_USER_PARAMS && (n_params == 0 || params != nullptr), "bad params");
+    return ukf_create_impl(out, cfg, cuda_source, params, n_params);
+}
+
+mpcb_status mpcb_ukf_check_user_source(const char* cuda_source, int32_t n, int32_t o) {
+    MPCB_REQUIRE(cuda_source != nullptr, "null source");
+    MPCB_REQUIRE(n >= 1 && n <= 6 && o >= 1 && o <= 5, "user UKF models: n in 1..6, o in 1..5");
+    RtcModule m;
+    return rtc_compile_ukf_user(cuda_source, n, o, MPCB_SQRT_EIG, MPCB_ORDER_LIBRARY, true, false, &m);
+}
+
 void mpcb_ukf_destroy(mpcb_ukf* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    rtc_unload(&h->rtc);
     cudaFree(h->d_x);
     cudaFree(h->d_P);
     cudaFree(h->d_sigma);

@@ -67,6 +67,12 @@ __device__ __forceinline__ void nl6_ddot(const ModelConsts& mc, double th, doubl
 
 template <int MODEL, int N>
 __device__ __forceinline__ void ukf_fx(const ModelConsts& mc, double (&x)[N], double u, double dt) {
+#ifdef MPCB_UKF_USER
+    // run-time compiled user model (mpcb_ukf_create_user): ::fx is declared by the user source ahead of this header
+    if constexpr (MODEL == MPCB_MODEL_USER_UKF) {
+        ::fx(x, u, dt, mc.k);
+    } else
+#endif
     if constexpr (MODEL == MPCB_MODEL_PEN_LIN) {
         // examples/ukf-pen.rs:76-83
         x[3] += (mc.k[slot::L_A1] * x[2] - mc.k[slot::L_B1] * u) * dt;
@@ -119,6 +125,11 @@ __device__ __forceinline__ void ukf_fx(const ModelConsts& mc, double (&x)[N], do
 
 template <int MODEL, int N, int O>
 __device__ __forceinline__ void ukf_hx(const ModelConsts& mc, const double (&x)[N], double (&z)[O]) {
+#ifdef MPCB_UKF_USER
+    if constexpr (MODEL == MPCB_MODEL_USER_UKF) {
+        ::hx(x, z, mc.k);
+    } else
+#endif
     if constexpr (MODEL == MPCB_MODEL_PEN_LIN) {
         z[0] = x[1];  // examples/ukf-pen.rs:86-91
         z[1] = x[3];

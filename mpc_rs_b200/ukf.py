@@ -34,6 +34,38 @@ def _dp(a):
     return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
 
 
+class UserUkfModel(DeviceModel):
+    """`fx` / `hx` of predict(u, fx) / update(&z, hx) (src/ukf.rs:44-46,54-56) as CUDA C++ source (mpcb_ukf_create_user):
+
+        void fx(double (&x)[N], double u, double dt, const double* p);     // x <- f(x, u), in place
+        void hx(const double (&x)[N], double (&z)[O], const double* p);    // z <- h(x)
+
+    with N = n (1..6) and O = o (1..5) written as literals.  Build one with `user_ukf_model(source, n, o, params)`."""
+
+    def __init__(self, source: str, n: int, o: int, params=(), name: str = "user-ukf"):
+        object.__setattr__(self, "model_id", A.MODEL_USER_UKF)
+        object.__setattr__(self, "name", name)
+        object.__setattr__(self, "source", source)
+        object.__setattr__(self, "n", int(n))
+        object.__setattr__(self, "o", int(o))
+        object.__setattr__(self, "params", tuple(float(v) for v in params))
+
+
+def user_ukf_model(source: str, n: int, o: int, params=(), name: str = "user-ukf") -> UserUkfModel:
+    if len(params) > A.USER_PARAMS:
+        raise ValueError(f"at most {A.USER_PARAMS} parameters")
+    return UserUkfModel(source, n, o, params, name)
+
+
+def check_user_ukf_source(source: str, n: int, o: int) -> str:
+    """Compile-only check (NVRTC, no GPU needed); returns the compiler log, raises MpcB200Error if it does not compile."""
+    st = A.lib().mpcb_ukf_check_user_source(source.encode(), int(n), int(o))
+    log = (A.lib().mpcb_rtc_log() or b"").decode()
+    if st != A.OK:
+        raise A.MpcB200Error(st, "user model did not compile:\n" + log)
+    return log
+
+
 _DIMS = {A.MODEL_PEN_LIN: (4, 2), A.MODEL_PEN_NL: (4, 3), A.MODEL_PEN6: (6, 5), A.MODEL_NL6_UKF: (6, 5)}
 
 
@@ -53,6 +85,9 @@ class BatchedUkf:
         L = A.lib()
         cfg = A.UkfCfg()
         A.check(L.mpcb_ukf_default_cfg(model.model_id, C.byref(cfg)))
+        user = isinstance(model, UserUkfModel)
+        if user:
+            cfg.n, cfg.o = model.n, model.o
         cfg.batch, cfg.device, cfg.exact = int(batch), int(device), int(bool(exact))
         if sqrt_mode is not None:
             cfg.sqrt_mode = {"cholesky": A.SQRT_CHOLESKY, "eig": A.SQRT_EIG, "svd": A.SQRT_EIG}[sqrt_mode]
@@ -60,12 +95,20 @@ class BatchedUkf:
             cfg.sigma_order = {"library": A.ORDER_LIBRARY, "interleaved": A.ORDER_INTERLEAVED}[sigma_order]
         if dt is not None:
             cfg.model.dt = float(dt)
-        for k, v in (params or {}).items():
+        for k, v in ({} if user else (params or {})).items():
             setattr(cfg.model, k, float(v))
         self.cfg, self.model = cfg, model
         self.n, self.o, self.B = cfg.n, cfg.o, int(batch)
         self._h = A._H()
-        A.check(L.mpcb_ukf_create(C.byref(self._h), C.byref(cfg)))
+        if user:
+            pa = (C.c_double * max(1, len(model.params)))(*model.params)
+            st = L.mpcb_ukf_create_user(C.byref(self._h), C.byref(cfg), model.source.encode(), pa, len(model.params))
+            if st == A.RTC_ERROR:
+                raise A.MpcB200Error(st, "user model did not compile: " + L.mpcb_last_error_string().decode() + "\n"
+                                      + (L.mpcb_rtc_log() or b"").decode())
+            A.check(st)
+        else:
+            A.check(L.mpcb_ukf_create(C.byref(self._h), C.byref(cfg)))
 
     # -- lifetime --
     def close(self):

@@ -16,6 +16,7 @@ pub struct MpcbUkfCfg { pub model_id: i32, pub n: i32, pub o: i32, pub sqrt_mode
     pub device: i32, pub exact: i32, pub reserved: i32, pub batch: i64, pub model: MpcbModelParams }
 pub enum MpcbMppi {}
 pub enum MpcbUkf {}
+pub const MPCB_MODEL_USER_UKF: i32 = 20; // fx + hx supplied as CUDA source (mpcb_ukf_create_user)
 pub const MPCB_MODEL_USER: i32 = 3; // dynamics + cost supplied as CUDA source (mpcb_mppi_create_user)
 
 extern "C" {
@@ -26,6 +27,8 @@ extern "C" {
                                  params: *const f64, n_params: i32) -> i32;
     pub fn mpcb_mppi_check_user_source(cuda_source: *const std::os::raw::c_char, precision: i32) -> i32;
     pub fn mpcb_rtc_log() -> *const std::os::raw::c_char;
+    pub fn mpcb_ukf_create_user(out: *mut *mut MpcbUkf, cfg: *const MpcbUkfCfg, cuda_source: *const std::os::raw::c_char,
+                                params: *const f64, n_params: i32) -> i32;
     pub fn mpcb_mppi_destroy(h: *mut MpcbMppi);
     pub fn mpcb_mppi_compute(h: *mut MpcbMppi, x: *const f64, u_in: *const f64, u_out: *mut f64, info: *mut MpcbMppiInfo) -> i32;
     pub fn mpcb_ukf_default_cfg(model_id: i32, out: *mut MpcbUkfCfg) -> i32;

@@ -136,6 +136,44 @@ template <typename real> real cost(const real (&x)[4], const real* p) {
         try { f.predict(0.1, DeviceModel::PEN6); } catch (const std::invalid_argument&) { threw = true; }
         EXPECT(threw, "a foreign fx model must be rejected");
     }
+    // ---- ukf::UnscentedKalmanFilter::create_user: examples/ukf-pen2.rs's fx / hx closures as source vs the oracle's PEN_NL
+    {
+        const std::string src = R"SRC(
+void fx(double (&x)[4], double u, double dt, const double* p) {
+    const double M1 = p[0], R_W = p[1], M2 = p[2], L = p[3], J1 = p[4], J2 = p[5], G = p[6], KT = p[7];
+    const double s = sin(x[2]), c = cos(x[2]);
+    const double D = (M1 + M2 + J1 / (R_W * R_W)) * (M2 * L * L + J2);
+    const double d = D - M2 * M2 * L * L * c * c;
+    const double drive = KT * u / R_W + M2 * L * (x[3] * x[3]) * s;
+    const double r3 = x[3] + ((M1 + M2 + J1 / (R_W * R_W)) * M2 * G * L * s - drive * M2 * L * c) / d * dt;
+    const double r2 = x[2] + x[3] * dt;
+    const double r1 = x[1] + ((J2 + M2 * L * L) * drive + M2 * G * L * L * s * c) / d * dt;
+    const double r0 = x[0] + x[1] * dt;
+    x[0] = r0; x[1] = r1; x[2] = r2; x[3] = r3;
+}
+void hx(const double (&x)[4], double (&z)[3], const double* p) {
+    const double PI = 3.14159265358979323846264338327950288;
+    z[0] = 60.0 / (2.0 * PI * p[1]) * x[1];
+    z[1] = 60.0 / (2.0 * PI * p[1]) * x[1];
+    z[2] = x[3] * (180.0 / PI);
+}
+)SRC";
+        mpcb_model_params p;
+        orc_model_defaults(MPCB_MODEL_PEN_NL, &p);
+        const std::array<double, 16> Q{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0.25};
+        const std::array<double, 9> R{100, 0, 0, 0, 100, 0, 0, 0, 0.5};
+        const std::array<double, 16> P0{10, 0, 0, 0, 0, 10, 0, 0, 0, 0, 10, 0, 0, 0, 0, 10};
+        auto f = ukf::UnscentedKalmanFilter::create_user({0.01, 0, 0.02, 0}, P0, Q, R, src, {p.m1, p.r_w, p.m2, p.l, p.j1, p.j2, p.g, p.kt});
+        double xo[4] = {0.01, 0, 0.02, 0}, Po[16], sf[4 * 9];
+        std::memcpy(Po, P0.data(), sizeof(Po));
+        const std::array<double, 3> z{12.0, -7.0, 0.3};
+        EXPECT(orc_ukf_predict(MPCB_MODEL_PEN_NL, &p, 4, MPCB_SQRT_EIG, MPCB_ORDER_LIBRARY, xo, Po, Q.data(), 0.1, 0.01, sf) == 0, "oracle predict");
+        EXPECT(orc_ukf_update(MPCB_MODEL_PEN_NL, &p, 4, 3, xo, Po, R.data(), z.data(), sf) == 0, "oracle update");
+        f.predict(0.1, DeviceModel::USER_UKF, 0.01);
+        f.update(z, DeviceModel::USER_UKF);
+        EXPECT(rel_err(f.state(), xo) < 1e-6 && rel_err(f.covariance(), Po) < 1e-6, "user ukf: %.3e %.3e", rel_err(f.state(), xo),
+               rel_err(f.covariance(), Po));
+    }
     // ---- mpc::ukf2 (n=6, o=5): set_q / set_r / set_enable / gen_r exist and a gated step runs
     {
         std::array<double, 36> Q{}, P0{};

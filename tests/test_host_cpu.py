@@ -201,3 +201,12 @@ def test_user_model_source_compiles_without_a_gpu():
         M.check_user_source("float cost(const float (&x)[4], const float* p) { return nope; }")
     assert e.value.status == A.RTC_ERROR and "nope" in str(e.value) and "user_model.cu(1)" in str(e.value)
     assert A.status_string(A.RTC_ERROR) == "user model did not compile"
+    # the UKF twin: fx / hx for n = 3, o = 2
+    ukf_src = """
+    void fx(double (&x)[3], double u, double dt, const double* p) { x[0] += x[1] * dt; x[1] += (u - p[0] * sin(x[0])) * dt; x[2] *= 0.9; }
+    void hx(const double (&x)[3], double (&z)[2], const double* p) { z[0] = x[0]; z[1] = x[1] + x[2]; }
+    """
+    assert "error" not in M.check_user_ukf_source(ukf_src, 3, 2)
+    with pytest.raises(M.MpcB200Error) as e:
+        M.check_user_ukf_source(ukf_src, 4, 2)  # the signatures say N = 3
+    assert e.value.status == A.RTC_ERROR

@@ -195,3 +195,125 @@ def test_example_user_model_parks_the_cart(gpu_required):
     rows = ex.run(samples=32768, seconds=6.0, quiet=True, seed=3)
     assert np.all(np.isfinite(rows)) and np.all(np.abs(rows[:, 1]) <= 3.0)
     assert abs(rows[-1, 2] - 1.0) < 0.15 and abs(rows[-1, 4]) < 0.1 and abs(rows[-1, 3]) < 0.3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# UKF: fx / hx closures of predict(u, fx) / update(&z, hx) (src/ukf.rs:44-46,54-56) as CUDA source
+# ---------------------------------------------------------------------------------------------------------------
+from mpc_rs_b200 import BatchedUkf, UnscentedKalmanFilter, user_ukf_model  # noqa: E402
+
+# examples/ukf-pen2.rs:31-53 the way a user would port it (p = M1, R_W, M2, L, J1, J2, G, KT)
+PEN_NL_SOURCE = r"""
+void fx(double (&x)[4], double u, double dt, const double* p) {
+    const double M1 = p[0], R_W = p[1], M2 = p[2], L = p[3], J1 = p[4], J2 = p[5], G = p[6], KT = p[7];
+    const double s = sin(x[2]), c = cos(x[2]);
+    const double D = (M1 + M2 + J1 / (R_W * R_W)) * (M2 * L * L + J2);
+    const double d = D - M2 * M2 * L * L * c * c;
+    const double term1 = (M1 + M2 + J1 / (R_W * R_W)) * M2 * G * L * s;
+    const double drive = KT * u / R_W + M2 * L * (x[3] * x[3]) * s;
+    const double term2 = drive * M2 * L * c;
+    const double r3 = x[3] + (term1 - term2) / d * dt;
+    const double r2 = x[2] + x[3] * dt;
+    const double term3 = (J2 + M2 * L * L) * drive;
+    const double term4 = M2 * G * L * L * s * c;
+    const double r1 = x[1] + (term3 + term4) / d * dt;
+    const double r0 = x[0] + x[1] * dt;
+    x[0] = r0; x[1] = r1; x[2] = r2; x[3] = r3;
+}
+void hx(const double (&x)[4], double (&z)[3], const double* p) {
+    const double PI = 3.14159265358979323846264338327950288;
+    z[0] = 60.0 / (2.0 * PI * p[1]) * x[1];
+    z[1] = 60.0 / (2.0 * PI * p[1]) * x[1];
+    z[2] = x[3] * (180.0 / PI);
+}
+"""
+
+
+# the port recomputes D, 60/(2 pi R_W), ... per call where the built-in model folds them on the host: rounding-level
+# differences times the 1.7e5 sigma-weight amplification
+@pytest.mark.parametrize("sqrt_mode,exact,tol", [("eig", True, 1e-8), ("cholesky", True, 1e-8), ("eig", False, 1e-7)])
+def test_reference_ukf_model_as_user_source_matches_the_oracle(gpu_required, sqrt_mode, exact, tol):
+    B, T, u, dt = 129, 5, 0.1, 0.01
+    oid = O.MODEL_PEN_NL
+    p = O.model_defaults(oid)
+    Q, R, P0 = O.ukf_default_noise(oid, 0.0)
+    rng = np.random.default_rng(8)
+    um = user_ukf_model(PEN_NL_SOURCE, 4, 3, [p.m1, p.r_w, p.m2, p.l, p.j1, p.j2, p.g, p.kt])
+    x = rng.normal(0, 0.1, (B, 4))
+    P = np.tile(P0, (B, 1, 1))
+    osq = {"eig": O.SQRT_EIG, "cholesky": O.SQRT_CHOLESKY}[sqrt_mode]
+    with BatchedUkf(um, B, sqrt_mode=sqrt_mode, sigma_order="library", exact=exact, dt=dt) as f:
+        assert (f.n, f.o) == (4, 3)
+        f.init(np.zeros(4), P0, Q, R)
+        for t in range(T):
+            z = rng.normal(0, 1.0, (B, 3)) * np.sqrt(np.diag(R))
+            f.set_state(x, P)
+            if t % 2:
+                f.predict(u, dt)
+                f.update(z)
+            else:
+                f.step(u, z, dt)
+            xg, Pg = f.get_state()
+            x, P, st = O.ukf_step_batch(oid, p, x, P, Q, R, u, z, dt, osq, O.ORDER_LIBRARY)
+            assert not st.any()
+            assert rel_err(xg, x) < tol and rel_err(Pg, P) < tol, (t, rel_err(xg, x), rel_err(Pg, P))
+
+
+# a filter the library has never seen: n = 3, o = 2 (damped pendulum with a slowly adapting bias; range + mixed sensor)
+UKF3_SOURCE = r"""
+void fx(double (&x)[3], double u, double dt, const double* p) {
+    const double th = x[0], om = x[1], b = x[2];
+    x[0] = th + om * dt;
+    x[1] = om + (u - p[0] * sin(th) - p[1] * om + b) * dt;
+    x[2] = 0.98 * b;
+}
+void hx(const double (&x)[3], double (&z)[2], const double* p) {
+    z[0] = p[2] * sin(x[0]);
+    z[1] = x[1] + 0.1 * x[0] * x[0];
+}
+"""
+UKF3_PARAMS = [9.81 / 0.5, 0.2, 1.5]
+
+
+def ukf3_fx(x, u, dt):
+    a, bq, _ = UKF3_PARAMS
+    return np.array([x[0] + x[1] * dt, x[1] + (u - a * np.sin(x[0]) - bq * x[1] + x[2]) * dt, 0.98 * x[2]])
+
+
+def ukf3_hx(x):
+    return np.array([UKF3_PARAMS[2] * np.sin(x[0]), x[1] + 0.1 * x[0] * x[0]])
+
+
+@pytest.mark.parametrize("sqrt_mode,order", [("cholesky", "interleaved"), ("eig", "library")])
+def test_unseen_ukf_model_against_numpy(gpu_required, sqrt_mode, order):
+    dt, u, T = 0.02, 0.3, 6
+    Q = np.diag([1e-4, 1e-2, 1e-3])
+    Rm = np.diag([0.05, 0.2])
+    P = np.array([[1.0, 0.1, 0.0], [0.1, 2.0, 0.2], [0.0, 0.2, 3.0]])  # distinct eigenvalues: the eigen square root is unique
+    x = np.array([0.4, -0.2, 0.05])
+    rng = np.random.default_rng(5)
+    f = UnscentedKalmanFilter.new(x, P, Q, Rm, fx=user_ukf_model(UKF3_SOURCE, 3, 2, UKF3_PARAMS), sqrt_mode=sqrt_mode,
+                                  sigma_order=order, exact=True)
+    for t in range(T):
+        z = ukf3_hx(x) + rng.normal(0, 0.1, 2)
+        f.set_state(x[None, :], P[None, :, :])
+        f.predict(u, dt=dt)
+        f.update(z)
+        xr, Pr, sig = R_ukf_predict(x, P, Q, u, dt, sqrt_mode, order)
+        x, P = R.ukf_update(ukf3_hx, xr, Pr, Rm, z, sig)
+        assert rel_err(f.state(), x) < 1e-8, (t, rel_err(f.state(), x))
+        assert rel_err(f.covariance(), P) < 1e-8, (t, rel_err(f.covariance(), P))
+    f.close()
+
+
+def R_ukf_predict(x, P, Q, u, dt, sqrt_mode, order):
+    return R.ukf_predict(lambda s: ukf3_fx(s, u, dt), x, P, Q, sqrt_mode="cholesky" if sqrt_mode == "cholesky" else "svd",
+                         order=order)
+
+
+def test_user_ukf_errors(gpu_required):
+    with pytest.raises(MpcB200Error) as e:
+        BatchedUkf(user_ukf_model("void fx(double (&x)[2], double u, double dt, const double* p) { x[0] = oops; }", 2, 1), 4)
+    assert e.value.status == A.RTC_ERROR and "oops" in str(e.value)
+    with pytest.raises(MpcB200Error):
+        BatchedUkf(user_ukf_model("void fx(){}", 7, 1), 4)  # n out of range
