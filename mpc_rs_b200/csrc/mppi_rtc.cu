@@ -45,18 +45,16 @@ bool sym(void* lib, const char* name, F* out) {
     return *out != nullptr;
 }
 
-NvrtcApi* nvrtc_api() {
-    static NvrtcApi api;
-    static bool tried = false;
-    if (tried) return api.lib ? &api : nullptr;
-    tried = true;
+// both tables are filled once, on first use (function-local statics: thread-safe initialisation)
+NvrtcApi load_nvrtc() {
+    NvrtcApi api;
     const char* override_path = getenv("MPCB_NVRTC_PATH");
     const char* names[] = {override_path, "libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"};
     void* lib = nullptr;
     for (const char* n : names) {
         if (n && (lib = dlopen(n, RTLD_NOW | RTLD_LOCAL))) break;
     }
-    if (!lib) return nullptr;
+    if (!lib) return api;
     const bool ok = sym(lib, "nvrtcCreateProgram", &api.CreateProgram) && sym(lib, "nvrtcDestroyProgram", &api.DestroyProgram) &&
                     sym(lib, "nvrtcCompileProgram", &api.CompileProgram) && sym(lib, "nvrtcGetProgramLogSize", &api.GetProgramLogSize) &&
                     sym(lib, "nvrtcGetProgramLog", &api.GetProgramLog) && sym(lib, "nvrtcAddNameExpression", &api.AddNameExpression) &&
@@ -64,25 +62,32 @@ NvrtcApi* nvrtc_api() {
                     sym(lib, "nvrtcGetCUBIN", &api.GetCUBIN) && sym(lib, "nvrtcGetErrorString", &api.GetErrorString);
     if (!ok) {
         dlclose(lib);
-        return nullptr;
+        return api;
     }
     api.lib = lib;
-    return &api;
+    return api;
+}
+NvrtcApi* nvrtc_api() {
+    static NvrtcApi api = load_nvrtc();
+    return api.lib ? &api : nullptr;
 }
 
-LibraryApi* library_api() {
-    static LibraryApi api;
-    static bool tried = false, ok = false;
-    if (tried) return ok ? &api : nullptr;
-    tried = true;
+LibraryApi load_library_api() {
+    LibraryApi api;
     Dl_info info;
     void* rt = nullptr;
-    if (dladdr(reinterpret_cast<void*>(static_cast<cudaError_t (*)(int*)>(&cudaGetDeviceCount)), &info) && info.dli_fname) rt = dlopen(info.dli_fname, RTLD_NOW | RTLD_NOLOAD);
+    if (dladdr(reinterpret_cast<void*>(static_cast<cudaError_t (*)(int*)>(&cudaGetDeviceCount)), &info) && info.dli_fname)
+        rt = dlopen(info.dli_fname, RTLD_NOW | RTLD_NOLOAD);
     if (!rt) rt = dlopen("libcudart.so.12", RTLD_NOW | RTLD_NOLOAD);
     if (!rt) rt = RTLD_DEFAULT;
-    ok = sym(rt, "cudaLibraryLoadData", &api.LoadData) && sym(rt, "cudaLibraryGetKernel", &api.GetKernel) &&
-         sym(rt, "cudaLibraryUnload", &api.Unload);
-    return ok ? &api : nullptr;
+    if (!(sym(rt, "cudaLibraryLoadData", &api.LoadData) && sym(rt, "cudaLibraryGetKernel", &api.GetKernel) &&
+          sym(rt, "cudaLibraryUnload", &api.Unload)))
+        api = LibraryApi();
+    return api;
+}
+LibraryApi* library_api() {
+    static LibraryApi api = load_library_api();
+    return api.LoadData ? &api : nullptr;
 }
 
 // The adapter between the user's two functions and the model interface of mppi_kernel.cuh (load / step / cost).
