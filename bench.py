@@ -48,9 +48,9 @@ UKF_B = 1 << 20
 UKF_T = 50
 UKF_BYTES = 336.0  # 8*(2n + 2n^2 + o), n=4, o=2
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures of these kernels
-# (profiles/mppi_r1_final2_ncu_full_summary.txt, profiles/ukf_r1_final_ncu_full_summary.txt)
+# (profiles/mppi_r1_final2_ncu_full_summary.txt, profiles/ukf_r1_pipe_ncu_full_summary.txt)
 MPPI_DRAM_TRAFFIC_BYTES = 87_296 + 0
-UKF_DRAM_TRAFFIC_BYTES = 188_768_000 + 112_360_448
+UKF_DRAM_TRAFFIC_BYTES = 138_434_048 + 114_366_976
 FP32_FALLBACK_TFLOPS = 69.5  # tools/peak_bench on this pool's B200 (profiles/peaks_r1.json)
 FP64_FALLBACK_TFLOPS = 33.9
 METRIC = "mppi_rollout_steps_per_sec"
@@ -401,7 +401,9 @@ def run_gpu(args):
         gbs = ukf_out["value"] / world * UKF_BYTES / 1e9
         ukf_out["roofline"] = {"bound": "hbm", "kernel": "ukf_kernel<4,2,PEN_LIN,cholesky,interleaved,fused>", "achieved": gbs,
                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": UKF_DRAM_TRAFFIC_BYTES,
-                               "note": f"{UKF_BYTES:.0f} algorithmic bytes per filter-update; peak = {peaks['hbm_source']}; "
+                               "note": f"{UKF_BYTES:.0f} algorithmic bytes per filter-update (x, full P in and out, z: SURVEY.md 8d); the "
+                                       "kernel does not read the strictly-upper triangle of P (predict never uses it), so the DRAM "
+                                       f"traffic is lower than the algorithmic figure; peak = {peaks['hbm_source']}; "
                                        f"FP64 pipe peak {peaks['fp64_tflops']:.1f} TFLOP/s ({peaks['fp32_source']})"}
     cpu_val, cpu_info = cpu_baseline(None, 2, budget_s=12.0) if world == 1 else (None, None)
     line = {

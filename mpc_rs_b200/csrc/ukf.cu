@@ -43,6 +43,7 @@ struct mpcb_ukf {
     cudaStream_t stream = nullptr;
     ModelConsts mc;
     UkfKernelFn k_predict = nullptr, k_update = nullptr, k_fused = nullptr;
+    long long grid_cap = 0;  // resident blocks of the fused kernel on this device
     RtcModule rtc;  // user-supplied fx / hx (mpcb_ukf_create_user): the kernels above live in this module
     double Q[36], R[25];
     double wm0 = 0, wc0 = 0, wi = 0, cC = 0;
@@ -121,7 +122,11 @@ void fill_params(const mpcb_ukf* h, UkfParams* p) {
 }
 
 mpcb_status launch(mpcb_ukf* h, UkfKernelFn fn, const UkfParams& p) {
-    const unsigned grid = (unsigned)((h->B + kThreads - 1) / kThreads);
+    // the kernels walk tiles of 128 filters grid-stride; at most one resident wave of blocks, so that the fused kernel's
+    // prefetch of the next tile overlaps the current tile's arithmetic
+    long long tiles = (h->B + kThreads - 1) / kThreads;
+    if (h->grid_cap > 0 && tiles > h->grid_cap) tiles = h->grid_cap;
+    const unsigned grid = (unsigned)tiles;
     // explicit cudaLaunchKernel: `fn` is a compiled-in __global__ function or the cudaKernel_t of a user model
     UkfParams pp = p;
     void* args[1] = {&pp};
@@ -332,6 +337,15 @@ static mpcb_status ukf_create_impl(mpcb_ukf** out, const mpcb_ukf_cfg* cfg, cons
     if (!h->k_predict || !h->k_update || !h->k_fused) {
         set_error("no UKF kernel for model %d / sqrt %d / order %d", cfg->model_id, cfg->sqrt_mode, cfg->sigma_order);
         return fail(MPCB_BAD_ARG);
+    }
+    {
+        int occ = 0, sms = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void*>(h->k_fused), kThreads, 0) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device) != cudaSuccess || occ < 1 || sms < 1) {
+            cudaGetLastError();
+            occ = 0;
+        }
+        h->grid_cap = (long long)occ * sms;
     }
     memset(h->Q, 0, sizeof(h->Q));
     memset(h->R, 0, sizeof(h->R));

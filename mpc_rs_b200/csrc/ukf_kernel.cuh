@@ -176,7 +176,8 @@ __device__ __noinline__ void ukf_hx_call(const ModelConsts& mc, const double (&x
 // small dense kernels, fully unrolled
 // ------------------------------------------------------------------------------------------------
 // nalgebra-style lower Cholesky (reads the lower triangle); false if a pivot is not > 0
-template <int N>
+// FAST: one rsqrt per pivot instead of a sqrt and N-j-1 divisions on the serial chain (rounding-level differences)
+template <int N, bool FAST = false>
 __device__ __forceinline__ bool chol_lower(double (&m)[N][N]) {
     bool ok = true;
 #pragma unroll
@@ -189,10 +190,17 @@ __device__ __forceinline__ bool chol_lower(double (&m)[N][N]) {
         }
         const double diag = m[j][j];
         if (!(diag > 0.0)) ok = false;
-        const double denom = sqrt(diag);
-        m[j][j] = denom;
+        if constexpr (FAST) {
+            const double inv = rsqrt(diag);
+            m[j][j] = diag * inv;
 #pragma unroll
-        for (int i = j + 1; i < N; ++i) m[i][j] /= denom;
+            for (int i = j + 1; i < N; ++i) m[i][j] *= inv;
+        } else {
+            const double denom = sqrt(diag);
+            m[j][j] = denom;
+#pragma unroll
+            for (int i = j + 1; i < N; ++i) m[i][j] /= denom;
+        }
     }
 #pragma unroll
     for (int i = 0; i < N; ++i)
@@ -305,12 +313,17 @@ __device__ __forceinline__ void sym_eig_sqrt(double (&A)[N][N], double (&Lo)[N][
 }
 
 // try_inverse: closed forms for 2x2 / 3x3, LU with partial pivoting otherwise; false = singular
-template <int O>
+template <int O, bool FAST = false>
 __device__ __forceinline__ bool inverse_small(const double (&A)[O][O], double (&Ai)[O][O]) {
     if constexpr (O == 2) {
         const double det = A[0][0] * A[1][1] - A[1][0] * A[0][1];
         if (det == 0.0) return false;
-        Ai[0][0] = A[1][1] / det; Ai[0][1] = -A[0][1] / det; Ai[1][0] = -A[1][0] / det; Ai[1][1] = A[0][0] / det;
+        if constexpr (FAST) {  // one reciprocal instead of four divisions
+            const double id = __drcp_rn(det);
+            Ai[0][0] = A[1][1] * id; Ai[0][1] = -A[0][1] * id; Ai[1][0] = -A[1][0] * id; Ai[1][1] = A[0][0] * id;
+        } else {
+            Ai[0][0] = A[1][1] / det; Ai[0][1] = -A[0][1] / det; Ai[1][0] = -A[1][0] / det; Ai[1][1] = A[0][0] / det;
+        }
         return true;
     } else if constexpr (O == 3) {
         const double m11 = A[0][0], m12 = A[0][1], m13 = A[0][2], m21 = A[1][0], m22 = A[1][1], m23 = A[1][2],
@@ -475,30 +488,115 @@ __device__ __forceinline__ void unscented_transform(const double (&sig)[S][M], d
     }
 }
 
-template <int N, int O, int MODEL, int SQRT, int ORDER, int MODE, bool FAST>
-__global__ void __launch_bounds__(128) ukf_kernel(const __grid_constant__ UkfParams p) {
-    constexpr int M = 2 * N + 1;
-    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= p.B) return;
-    const long long B = p.B;
+// 8- and 4-byte asynchronous global -> shared copies (LDGSTS): a thread stages ITS OWN filter's inputs of the next tile
+// while it computes the current one, so no barrier is needed — only the thread's own cp.async.wait_group.
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int KEEP>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(KEEP) : "memory"); }
 
-    double x[N], P[N][N], sig[N][M];
-    int st = p.status[b];
+constexpr int kUkfThreads = 128;
+
+// One thread per filter, a block walks tiles of 128 filters (grid-stride).  The fused predict+update kernel of the
+// four-state filters is bound by HBM *latency* when every block loads, computes and stores in sequence (ncu: 12 warps
+// per SM at 158 registers, top stall long_scoreboard, DRAM 46 % and FP64 pipe 47 % busy): there the inputs of tile
+// t+1 (x, P, z of step 0, status: 23 rows of 128 values) are copied into a second shared-memory buffer with cp.async
+// while tile t is computed (PIPE).  The other modes and n = 6 (FP64-bound, 2x the rows) load directly.
+template <int N, int O, int MODEL, int SQRT, int ORDER, int MODE, bool FAST>
+__global__ void __launch_bounds__(kUkfThreads) ukf_kernel(const __grid_constant__ UkfParams p) {
+    constexpr int M = 2 * N + 1;
+    // predict never reads the strictly-upper triangle of P (the Cholesky / eigen square root take the lower one, the
+    // unscented transform then rewrites P entirely), so the fused and predict kernels do not load it: 288 instead of
+    // 336 bytes of DRAM traffic per n = 4, o = 2 update, same result bit for bit
+    constexpr int NTRI = N * (N + 1) / 2;
+    constexpr int ROWS = N + NTRI + O;
+    constexpr bool PIPE = (MODE == UKF_FUSED) && (2 * ROWS * kUkfThreads * 8 + 2 * kUkfThreads * 4 <= 48 * 1024);
+    __shared__ double s_in[PIPE ? 2 : 1][PIPE ? ROWS : 1][PIPE ? kUkfThreads : 1];
+    __shared__ int s_st[PIPE ? 2 : 1][PIPE ? kUkfThreads : 1];
+    const long long B = p.B;
+    const int tid = threadIdx.x;
+    const long long ntiles = (B + kUkfThreads - 1) / kUkfThreads;
+
+    // stage the inputs of `tile` for this thread's filter into buffer `slot`
+    auto prefetch = [&](long long tile, int slot) {
+        const long long bb = tile * kUkfThreads + tid;
+        if (bb < B) {
 #pragma unroll
-    for (int r = 0; r < N; ++r) x[r] = p.x[(long long)r * B + b];
+            for (int r = 0; r < N; ++r) cp_async8(&s_in[slot][r][tid], p.x + (long long)r * B + bb);
 #pragma unroll
-    for (int r = 0; r < N; ++r)
+            for (int r = 0; r < N; ++r)
 #pragma unroll
-        for (int c = 0; c < N; ++c) P[r][c] = p.P[(long long)(r * N + c) * B + b];
-    if constexpr (MODE == UKF_UPDATE) {
+                for (int c = 0; c <= r; ++c) cp_async8(&s_in[slot][N + r * (r + 1) / 2 + c][tid], p.P + (long long)(r * N + c) * B + bb);
+#pragma unroll
+            for (int c = 0; c < O; ++c) cp_async8(&s_in[slot][N + NTRI + c][tid], p.z + (long long)c * B + bb);
+            cp_async4(&s_st[slot][tid], p.status + bb);
+        }
+    };
+    if constexpr (PIPE) {
+        if ((long long)blockIdx.x < ntiles) prefetch(blockIdx.x, 0);
+        cp_async_commit();
+    }
+
+  int it = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const long long b = tile * kUkfThreads + tid;
+    const bool live = b < B;
+    double x[N], P[N][N], sig[N][M], z0[O];
+    int st = MPCB_OK;
+    if constexpr (PIPE) {
+        const int slot = it & 1;
+        if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x, slot ^ 1);
+        cp_async_commit();   // one group per iteration (possibly empty): wait<1> always means "this tile has landed"
+        cp_async_wait<1>();
+        if (live) {
+            st = s_st[slot][tid];
+#pragma unroll
+            for (int r = 0; r < N; ++r) x[r] = s_in[slot][r][tid];
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int c = 0; c < N; ++c) P[r][c] = (c <= r) ? s_in[slot][N + r * (r + 1) / 2 + c][tid] : 0.0;
+#pragma unroll
+            for (int c = 0; c < O; ++c) z0[c] = s_in[slot][N + NTRI + c][tid];
+        }
+    } else if (live) {
+        st = p.status[b];
+#pragma unroll
+        for (int r = 0; r < N; ++r) x[r] = p.x[(long long)r * B + b];
 #pragma unroll
         for (int r = 0; r < N; ++r)
 #pragma unroll
-            for (int i = 0; i < M; ++i) sig[r][i] = p.sigma_f[(long long)(r * M + i) * B + b];
+            for (int c = 0; c < N; ++c) P[r][c] = (MODE == UKF_UPDATE || c <= r) ? p.P[(long long)(r * N + c) * B + b] : 0.0;
+        if constexpr (MODE == UKF_UPDATE) {
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int i = 0; i < M; ++i) sig[r][i] = p.sigma_f[(long long)(r * M + i) * B + b];
+        }
     }
+    if (!live) continue;
+    // x / P go back to memory only once they are fully defined in registers: a filter that enters with a sticky failure,
+    // or whose first square root fails, leaves its state in memory as it was
+    bool p_full = (MODE == UKF_UPDATE);
 
     const int steps = (MODE == UKF_FUSED) ? p.steps : 1;
+    // the measurement of step s is fetched one step ahead (registers), so that the multi-step loop never waits on it
+    double zc[O];
+    if constexpr (MODE != UKF_PREDICT) {
+#pragma unroll
+        for (int c = 0; c < O; ++c) zc[c] = PIPE ? z0[c] : p.z[(long long)c * B + b];
+    }
     for (int s = 0; s < steps && st == MPCB_OK; ++s) {
+        double zn[O];
+        if constexpr (MODE == UKF_FUSED) {
+#pragma unroll
+            for (int c = 0; c < O; ++c) zn[c] = (s + 1 < steps) ? p.z[((long long)(s + 1) * O + c) * B + b] : 0.0;
+        }
         if constexpr (MODE != UKF_UPDATE) {
             // ---- predict (src/ukf.rs:44-52) ----
             const double u = p.has_u ? p.u[(long long)s * B + b] : p.u_scalar;
@@ -509,7 +607,7 @@ __global__ void __launch_bounds__(128) ukf_kernel(const __grid_constant__ UkfPar
                 for (int r = 0; r < N; ++r)
 #pragma unroll
                     for (int c = 0; c < N; ++c) Lm[r][c] = p.cC * P[r][c];
-                ok = chol_lower<N>(Lm);
+                ok = chol_lower<N, FAST>(Lm);
             } else {
                 double cp[N][N];
 #pragma unroll
@@ -539,6 +637,7 @@ __global__ void __launch_bounds__(128) ukf_kernel(const __grid_constant__ UkfPar
                 for (int r = 0; r < N; ++r) sig[r][i] = col[r];
             }
             unscented_transform<N, M, FAST>(sig, p.wm0, p.wc0, p.wi, p.Q, x, P);
+            p_full = true;
         }
         if constexpr (MODE != UKF_PREDICT) {
             // ---- update (src/ukf.rs:54-74) ----
@@ -597,7 +696,7 @@ __global__ void __launch_bounds__(128) ukf_kernel(const __grid_constant__ UkfPar
                 }
             }
             double pzi[O][O];
-            if (!inverse_small<O>(pz, pzi)) { st = MPCB_INVERSE_FAIL; break; }
+            if (!inverse_small<O, FAST>(pz, pzi)) { st = MPCB_INVERSE_FAIL; break; }
             double k[N][O];
 #pragma unroll
             for (int r = 0; r < N; ++r)
@@ -610,7 +709,7 @@ __global__ void __launch_bounds__(128) ukf_kernel(const __grid_constant__ UkfPar
                 }
             double innov[O];
 #pragma unroll
-            for (int c = 0; c < O; ++c) innov[c] = p.z[((long long)s * O + c) * B + b] - zp[c];
+            for (int c = 0; c < O; ++c) innov[c] = zc[c] - zp[c];
 #pragma unroll
             for (int r = 0; r < N; ++r) {
                 double acc = k[r][0] * innov[0];
@@ -661,14 +760,20 @@ __global__ void __launch_bounds__(128) ukf_kernel(const __grid_constant__ UkfPar
                     }
             }
         }
+        if constexpr (MODE == UKF_FUSED) {
+#pragma unroll
+            for (int c = 0; c < O; ++c) zc[c] = zn[c];
+        }
     }
 
+    if (p_full) {
 #pragma unroll
-    for (int r = 0; r < N; ++r) p.x[(long long)r * B + b] = x[r];
+        for (int r = 0; r < N; ++r) p.x[(long long)r * B + b] = x[r];
 #pragma unroll
-    for (int r = 0; r < N; ++r)
+        for (int r = 0; r < N; ++r)
 #pragma unroll
-        for (int c = 0; c < N; ++c) p.P[(long long)(r * N + c) * B + b] = P[r][c];
+            for (int c = 0; c < N; ++c) p.P[(long long)(r * N + c) * B + b] = P[r][c];
+    }
     if constexpr (MODE == UKF_PREDICT) {
 #pragma unroll
         for (int r = 0; r < N; ++r)
@@ -676,6 +781,8 @@ __global__ void __launch_bounds__(128) ukf_kernel(const __grid_constant__ UkfPar
             for (int i = 0; i < M; ++i) p.sigma_f[(long long)(r * M + i) * B + b] = sig[r][i];
     }
     p.status[b] = st;
+  }
+  if constexpr (PIPE) cp_async_wait<0>();
 }
 
 // AoS <-> SoA transposes for the host-facing calls: in[B][W] <-> out[W][B]
