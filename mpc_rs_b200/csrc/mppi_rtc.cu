@@ -5,6 +5,8 @@
 #include <dlfcn.h>
 #include <nvrtc.h>
 
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -15,6 +17,15 @@ namespace mpcb {
 namespace {
 
 thread_local std::string g_log;
+
+// compiled modules of this process, keyed by everything that goes into the compilation: a second handle on the same
+// model (another rank of a sharded controller, another device, a re-created filter) skips the ~2.5 s NVRTC run
+struct CachedCubin {
+    std::vector<char> cubin;
+    std::string lowered[3];
+};
+std::mutex g_cache_mutex;
+std::map<std::string, CachedCubin> g_cache;
 
 struct NvrtcApi {
     void* lib = nullptr;
@@ -127,8 +138,42 @@ void rtc_unload(RtcModule* m) {
 namespace {
 
 // compiles `src` for sm_100a, resolves the three kernels named by `names` and (load) loads the cubin on the current device
+mpcb_status load_cubin(const CachedCubin& c, const std::string (&names)[3], RtcModule* out) {
+    LibraryApi* la = library_api();
+    if (!la) {
+        set_error("user models need cudaLibraryLoadData (CUDA runtime >= 12.0 with library management)");
+        return MPCB_RTC_ERROR;
+    }
+    cudaLibrary_t lib = nullptr;
+    cudaError_t e = la->LoadData(&lib, c.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e != cudaSuccess) {
+        set_error("cudaLibraryLoadData failed: %s", cudaGetErrorString(e));
+        return MPCB_CUDA_ERROR;
+    }
+    out->library = lib;
+    for (int i = 0; i < 3; ++i) {
+        cudaKernel_t k = nullptr;
+        if (la->GetKernel(&k, lib, c.lowered[i].c_str()) != cudaSuccess) {
+            set_error("kernel %s not found in the compiled user module", names[i].c_str());
+            rtc_unload(out);
+            return MPCB_RTC_ERROR;
+        }
+        out->kernel[i] = k;
+    }
+    return MPCB_OK;
+}
+
+// compiles `src` for sm_100a, resolves the three kernels named by `names` and (load) loads the cubin on the current device
 mpcb_status compile_and_load(const std::string& src, const std::string (&names)[3], std::vector<const char*> opts, bool load, RtcModule* out) {
     g_log.clear();
+    std::string key = src;
+    for (const char* o : opts) { key += '\n'; key += o; }
+    for (const std::string& n : names) { key += '\n'; key += n; }
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mutex);
+        auto it = g_cache.find(key);
+        if (it != g_cache.end()) return load ? load_cubin(it->second, names, out) : MPCB_OK;
+    }
     NvrtcApi* nv = nvrtc_api();
     if (!nv) {
         set_error("user models need NVRTC: libnvrtc.so.12 could not be opened (%s); set MPCB_NVRTC_PATH", dlerror());
@@ -154,42 +199,32 @@ mpcb_status compile_and_load(const std::string& src, const std::string (&names)[
         nv->DestroyProgram(&prog);
         return MPCB_RTC_ERROR;
     }
+    CachedCubin c;
+    size_t cn = 0;
     mpcb_status st = MPCB_OK;
-    if (load) {
-        LibraryApi* la = library_api();
-        size_t cn = 0;
-        std::vector<char> cubin;
-        if (!la) {
-            set_error("user models need cudaLibraryLoadData (CUDA runtime >= 12.0 with library management)");
-            st = MPCB_RTC_ERROR;
-        } else if (nv->GetCUBINSize(prog, &cn) != NVRTC_SUCCESS || cn == 0) {
-            set_error("nvrtcGetCUBIN returned nothing");
-            st = MPCB_RTC_ERROR;
-        } else {
-            cubin.resize(cn);
-            nv->GetCUBIN(prog, cubin.data());
-            cudaLibrary_t lib = nullptr;
-            cudaError_t e = la->LoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-            if (e != cudaSuccess) {
-                set_error("cudaLibraryLoadData failed: %s", cudaGetErrorString(e));
-                st = MPCB_CUDA_ERROR;
+    if (nv->GetCUBINSize(prog, &cn) != NVRTC_SUCCESS || cn == 0) {
+        set_error("nvrtcGetCUBIN returned nothing");
+        st = MPCB_RTC_ERROR;
+    } else {
+        c.cubin.resize(cn);
+        nv->GetCUBIN(prog, c.cubin.data());
+        for (int i = 0; i < 3 && st == MPCB_OK; ++i) {
+            const char* low = nullptr;
+            if (nv->GetLoweredName(prog, names[i].c_str(), &low) != NVRTC_SUCCESS || !low) {
+                set_error("kernel %s not found in the compiled user module", names[i].c_str());
+                st = MPCB_RTC_ERROR;
             } else {
-                out->library = lib;
-                for (int i = 0; i < 3 && st == MPCB_OK; ++i) {
-                    const char* low = nullptr;
-                    cudaKernel_t k = nullptr;
-                    if (nv->GetLoweredName(prog, names[i].c_str(), &low) != NVRTC_SUCCESS || !low ||
-                        la->GetKernel(&k, lib, low) != cudaSuccess) {
-                        set_error("kernel %s not found in the compiled user module", names[i].c_str());
-                        st = MPCB_RTC_ERROR;
-                    }
-                    out->kernel[i] = k;
-                }
-                if (st != MPCB_OK) rtc_unload(out);
+                c.lowered[i] = low;
             }
         }
     }
     nv->DestroyProgram(&prog);
+    if (st != MPCB_OK) return st;
+    if (load) st = load_cubin(c, names, out);
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mutex);
+        g_cache.emplace(std::move(key), std::move(c));
+    }
     return st;
 }
 
