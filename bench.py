@@ -13,6 +13,8 @@ per control step inside the library.
               handle's stream, L2 flushed between timed steps, max over ranks
     e2e       the same step through the C-ABI call mpcb_mppi_compute with HOST buffers (inputs travel in the kernel
               parameters, u_out/info come back through mapped pinned memory and a completion word), host wall clock
+              around a compiled closed loop (tools/e2e_loop.c, like the reference's compiled callers); the same loop
+              written in Python is reported next to it (python_loop_value)
     roofline  algorithmic FP32 flops (60 per rollout-step) / kernel time vs the FFMA peak measured
               live by tools/peak_bench (MEASURED_PEAKS.json has no FP32 vector number)
     ukf       BASELINE configs[2] on the side: 2^20 independent examples/ukf-pen.rs filters per GPU, FP64,
@@ -323,13 +325,30 @@ def run_gpu(args):
             raise SystemExit(f"mpcb_mppi_compute returned {st} in the e2e loop")
         np.copyto(u_h, out_h)
 
+    # the loop itself runs compiled (tools/e2e_loop.c -> tools/libmpcb_e2e.so): the reference's callers are compiled
+    # programs looping over Mppi::compute (examples/mppi4.rs:41-68).  The same loop written in Python is timed too.
+    e2e_lib = None
+    e2e_so = os.path.join(ROOT, "tools", "libmpcb_e2e.so")
+    if os.path.exists(e2e_so):
+        e2e_lib = C.CDLL(e2e_so)
+        e2e_lib.mpcb_e2e_loop.restype = C.c_double
+        e2e_lib.mpcb_e2e_loop.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                          C.c_int, C.c_int, C.POINTER(C.c_int)]
     for _ in range(args.warmup):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e2e_step()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_py_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_s, e2e_caller = e2e_py_s, "python loop over the ctypes call"
+    if e2e_lib is not None:
+        st_c = C.c_int(0)
+        barrier()
+        el = e2e_lib.mpcb_e2e_loop(mppi._h, px, pu, po, H, args.steps, C.byref(st_c))
+        if el < 0:
+            raise SystemExit(f"mpcb_mppi_compute returned {st_c.value} in the compiled e2e loop")
+        e2e_s, e2e_caller = max_over_ranks(el), "compiled loop (tools/e2e_loop.c) over mpcb_mppi_compute"
     e2e_value = steps_total / e2e_s
     clocks = sampler.stop() if rank == 0 else None
 
@@ -411,7 +430,8 @@ def run_gpu(args):
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload(world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * (4 + H) * world,
-                "d2h_bytes_per_step": (8 * H + 40) * world, "ms_per_step": e2e_s / args.steps * 1e3},
+                "d2h_bytes_per_step": (8 * H + 40) * world, "ms_per_step": e2e_s / args.steps * 1e3, "caller": e2e_caller,
+                "python_loop_value": steps_total / e2e_py_s, "python_loop_ms_per_step": e2e_py_s / args.steps * 1e3},
         "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
         "state_updates_per_sec": value * 4, "ukf": ukf_out,
     }
