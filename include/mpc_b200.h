@@ -109,7 +109,7 @@ typedef struct mpcb_mppi_cfg {
     int32_t model_id;    /* MPCB_MODEL_L / NL / NL6                                             */
     int32_t precision;   /* mpcb_precision                                                      */
     int32_t horizon;     /* N of Mppi<N,K,S> (1..512)                                           */
-    int32_t state_dim;   /* S of Mppi<N,K,S>; the built-in models have S = 4                    */
+    int32_t state_dim;   /* S of Mppi<N,K,S>; the built-in models have S = 4, user models 1..8  */
     int64_t samples;     /* K of Mppi<N,K,S>: GLOBAL sample count per controller                */
     int32_t controllers; /* C independent controllers batched in one call (1 = the reference)   */
     int32_t device;      /* CUDA device ordinal                                                 */
@@ -142,9 +142,10 @@ mpcb_status mpcb_mppi_default_cfg(int32_t model_id, mpcb_mppi_cfg* out); /* the 
  * functions are given as CUDA C++ source and the fused MPPI kernel is compiled around them at create time (NVRTC,
  * sm_100a; a few seconds).  `cuda_source` must define, at global scope (`__device__` may be omitted),
  *
- *     template <typename real> void dynamics(real (&x)[4], real u, const real* p);   // x <- f(x, u), in place
- *     template <typename real> real cost(const real (&x)[4], const real* p);         // stage cost of the NEW state
+ *     template <typename real> void dynamics(real (&x)[S], real u, const real* p);   // x <- f(x, u), in place
+ *     template <typename real> real cost(const real (&x)[S], const real* p);         // stage cost of the NEW state
  *
+ * with S = cfg->state_dim written as a literal (1..8: Mppi<N,K,S> is generic in S; the built-in models have S = 4)
  * (plain `float` / `double` overloads work too; `real` is float for MPCB_F32, double for MPCB_F64, where the source
  * is compiled without FMA contraction).  p[0..n_params) are the caller's constants (n_params <= MPCB_USER_PARAMS),
  * delivered through the kernel-parameter bank.  Helpers of the built-in models may be used: mpcb::sincos_r(a, &s, &c),
@@ -154,8 +155,8 @@ mpcb_status mpcb_mppi_default_cfg(int32_t model_id, mpcb_mppi_cfg* out); /* the 
 #define MPCB_USER_PARAMS 24
 mpcb_status mpcb_mppi_create_user(mpcb_mppi** out, const mpcb_mppi_cfg* cfg, const char* cuda_source,
                                   const double* params, int32_t n_params);
-/* Compile-only check of a user model for `precision` (needs NVRTC, not a GPU). */
-mpcb_status mpcb_mppi_check_user_source(const char* cuda_source, int32_t precision);
+/* Compile-only check of a user model with state dimension `state_dim` for `precision` (needs NVRTC, not a GPU). */
+mpcb_status mpcb_mppi_check_user_source(const char* cuda_source, int32_t state_dim, int32_t precision);
 /* NVRTC log (errors and warnings, lines of the user source as "user_model.cu(line)") of the calling thread's last
  * mpcb_mppi_create_user / mpcb_mppi_check_user_source; "" if none. */
 const char* mpcb_rtc_log(void);

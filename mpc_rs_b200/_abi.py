@@ -91,7 +91,7 @@ SYMBOLS = {
     "mpcb_mppi_default_cfg": (C.c_int, [C.c_int32, C.POINTER(MppiCfg)]),
     "mpcb_mppi_create": (C.c_int, [C.POINTER(_H), C.POINTER(MppiCfg)]),
     "mpcb_mppi_create_user": (C.c_int, [C.POINTER(_H), C.POINTER(MppiCfg), C.c_char_p, C.POINTER(C.c_double), C.c_int32]),
-    "mpcb_mppi_check_user_source": (C.c_int, [C.c_char_p, C.c_int32]),
+    "mpcb_mppi_check_user_source": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32]),
     "mpcb_rtc_log": (C.c_char_p, []),
     "mpcb_mppi_destroy": (None, [_H]),
     "mpcb_mppi_compute": (C.c_int, [_H, _dp, _dp, _dp, C.POINTER(MppiInfo)]),

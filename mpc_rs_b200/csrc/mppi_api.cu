@@ -21,6 +21,7 @@ struct mpcb_mppi {
     int num_sms = 0;
     long long K_local = 0, k_offset = 0;
     int H = 0, C = 0, PL = 0;
+    int S = 4;  // state dimension (4 for the built-in models; 1..8 for user-supplied ones)
     int block = 0, chunks = 0, group_size = 0, groups = 0;
     int Hp = 8, lgHp = 3;
     int spt = 1;            // samples per thread (2: packed f32x2 kernels)
@@ -195,7 +196,7 @@ mpcb_status pick_kernels(mpcb_mppi* h) {
         pl.smem = smem_of(pl.sb, pl.vt);
         if (h->user) {
             rtc_unload(&h->rtc);
-            mpcb_status rst = rtc_compile_mppi_user(h->user_src.c_str(), f64, pl.block, pl.vt != 0, true, &h->rtc);
+            mpcb_status rst = rtc_compile_mppi_user(h->user_src.c_str(), h->S, f64, pl.block, pl.vt != 0, true, &h->rtc);
             if (rst != MPCB_OK) return rst;
         }
         for (int noise = 0; noise < 3; ++noise) {
@@ -351,11 +352,11 @@ mpcb_status ensure_eps(mpcb_mppi* h, size_t bytes) {
 
 // Stages host x/u_in: inline in the kernel parameters for the single-controller case, else one pinned H2D copy.
 mpcb_status stage_inputs(mpcb_mppi* h, MppiParams& p, const double* x, const double* u_in) {
-    const size_t nx = (size_t)h->C * 4, nu = (size_t)h->C * h->H;
+    const size_t nx = (size_t)h->C * h->S, nu = (size_t)h->C * h->H;
     if (h->C == 1 && h->H <= kInlineHorizon) {
         p.use_inline = 1;
-        memcpy(p.xu_inline, x, 4 * sizeof(double));
-        memcpy(p.xu_inline + 4, u_in, (size_t)h->H * sizeof(double));
+        memcpy(p.xu_inline, x, (size_t)h->S * sizeof(double));
+        memcpy(p.xu_inline + h->S, u_in, (size_t)h->H * sizeof(double));
         return MPCB_OK;
     }
     memcpy(h->h_in, x, nx * sizeof(double));
@@ -542,7 +543,8 @@ static mpcb_status create_impl(mpcb_mppi** out, const mpcb_mppi_cfg* cfg, const 
                                int32_t n_params) {
     MPCB_REQUIRE(out && cfg, "null pointer");
     *out = nullptr;
-    MPCB_REQUIRE(cfg->state_dim == 4, "the built-in models have S = 4");
+    if (user_src != nullptr) MPCB_REQUIRE(cfg->state_dim >= 1 && cfg->state_dim <= kMaxStateDim, "user models: state_dim in 1..8");
+    else MPCB_REQUIRE(cfg->state_dim == 4, "the built-in models have S = 4");
     MPCB_REQUIRE(cfg->horizon >= 1 && cfg->horizon <= kMaxHorizon, "horizon out of range");
     MPCB_REQUIRE(cfg->samples >= 1, "samples must be >= 1");
     MPCB_REQUIRE(cfg->controllers >= 1, "controllers must be >= 1");
@@ -560,6 +562,7 @@ static mpcb_status create_impl(mpcb_mppi** out, const mpcb_mppi_cfg* cfg, const 
     MPCB_REQUIRE(h != nullptr, "out of memory");
     h->cfg = *cfg;
     h->H = cfg->horizon;
+    h->S = cfg->state_dim;
     h->C = cfg->controllers;
     h->PL = mppi_partial_len(h->H);
     // contiguous shard of the global sample index
@@ -605,7 +608,7 @@ static mpcb_status create_impl(mpcb_mppi** out, const mpcb_mppi_cfg* cfg, const 
     } while (0)
     TRY_OR_FAIL(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     const size_t C = h->C, H = h->H;
-    TRY_OR_FAIL(cudaMalloc(&h->d_x, C * 4 * sizeof(double)));
+    TRY_OR_FAIL(cudaMalloc(&h->d_x, C * (size_t)h->S * sizeof(double)));
     TRY_OR_FAIL(cudaMalloc(&h->d_u, C * H * sizeof(double)));
     TRY_OR_FAIL(cudaMalloc(&h->d_u_out, C * H * sizeof(double)));
     TRY_OR_FAIL(cudaMalloc(&h->d_partial, C * (size_t)(h->chunks + h->groups) * h->PL * sizeof(double)));
@@ -621,7 +624,7 @@ static mpcb_status create_impl(mpcb_mppi** out, const mpcb_mppi_cfg* cfg, const 
         TRY_OR_FAIL(cudaMemset(h->d_ts, 0, C * (size_t)h->chunks * 16 * sizeof(unsigned long long)));
     }
     if (cfg->keep_costs) TRY_OR_FAIL(cudaMalloc(&h->d_costs, C * (size_t)h->K_local * sizeof(double)));
-    TRY_OR_FAIL(cudaHostAlloc(&h->h_in, C * (4 + H) * sizeof(double), cudaHostAllocDefault));
+    TRY_OR_FAIL(cudaHostAlloc(&h->h_in, C * ((size_t)h->S + H) * sizeof(double), cudaHostAllocDefault));
     TRY_OR_FAIL(cudaHostAlloc(&h->h_out, C * H * sizeof(double), cudaHostAllocMapped));
     TRY_OR_FAIL(cudaHostAlloc(&h->h_info, C * sizeof(mpcb_mppi_info), cudaHostAllocMapped));
     memset(h->h_out, 0, C * H * sizeof(double));
@@ -645,11 +648,12 @@ mpcb_status mpcb_mppi_create_user(mpcb_mppi** out, const mpcb_mppi_cfg* cfg, con
     return create_impl(out, cfg, cuda_source, params, n_params);
 }
 
-mpcb_status mpcb_mppi_check_user_source(const char* cuda_source, int32_t precision) {
+mpcb_status mpcb_mppi_check_user_source(const char* cuda_source, int32_t state_dim, int32_t precision) {
     MPCB_REQUIRE(cuda_source != nullptr, "null source");
+    MPCB_REQUIRE(state_dim >= 1 && state_dim <= kMaxStateDim, "state_dim in 1..8");
     MPCB_REQUIRE(precision == MPCB_F32 || precision == MPCB_F64, "bad precision");
     RtcModule m;
-    return rtc_compile_mppi_user(cuda_source, precision == MPCB_F64, 128, true, false, &m);
+    return rtc_compile_mppi_user(cuda_source, state_dim, precision == MPCB_F64, 128, true, false, &m);
 }
 
 const char* mpcb_rtc_log(void) { return rtc_log(); }

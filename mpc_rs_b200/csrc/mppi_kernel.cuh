@@ -60,7 +60,7 @@ struct MppiParams {
     long long K_global;
     long long k_offset;  // global index of this rank's first sample
     long long W;         // warps of 32 samples in K_local
-    const double* x;  // [C][4]
+    const double* x;  // [C][S]
     const double* u;  // [C][H]
     const void* eps;  // replay: [C][K_global][H]
     int eps_f64;
@@ -86,7 +86,7 @@ struct MppiParams {
     unsigned int xepoch, pad2;     // exchange epoch (same on every rank), parity = xepoch & 1
     unsigned long long* debug_ts;  // optional [blocks][8] %globaltimer stamps (diagnostics)
     ModelConsts mc;
-    double xu_inline[4 + kInlineHorizon];
+    double xu_inline[8 + kInlineHorizon];  // x[S] (S <= kMaxStateDim = 8) then u_n[H]
 };
 
 __device__ __forceinline__ double ll_as_double(long long v) { return __longlong_as_double(v); }
@@ -512,6 +512,17 @@ static __device__ __noinline__ void mppi_combine_ranks_warp(const double* rows, 
     }
 }
 
+// state dimension S of Mppi<N,K,S>: 4 for the built-in models; run-time compiled user models declare kStateDim (1..8)
+constexpr int kMaxStateDim = 8;
+template <typename M, typename = void>
+struct ModelStateDim {
+    static constexpr int value = 4;
+};
+template <typename M>
+struct ModelStateDim<M, decltype((void)M::kStateDim)> {
+    static constexpr int value = M::kStateDim;
+};
+
 template <typename real>
 struct RealTraits;
 template <>
@@ -634,18 +645,21 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
     // ---- prologue: model constants, x0, u_n ----
     ModelT<areal> model;
     model.load(p.mc);
-    real x0[4];
+    constexpr int S = ModelStateDim<ModelT<areal>>::value;
+    static_assert(S >= 1 && S <= kMaxStateDim, "state dimension out of range");
+    static_assert(SPT == 1 || S == 4, "the packed kernels are written for the built-in four-state models");
+    real x0[S];
     if (p.use_inline) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) x0[i] = (real)p.xu_inline[i];
+        for (int i = 0; i < S; ++i) x0[i] = (real)p.xu_inline[i];
         for (int t = tid; t < H; t += BLOCK) {
-            const double ut = p.xu_inline[4 + t];
+            const double ut = p.xu_inline[S + t];
             su[t] = (real)ut;
             sui[t] = (real)(ut * p.inv_var);
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) x0[i] = (real)p.x[(long long)c * 4 + i];
+        for (int i = 0; i < S; ++i) x0[i] = (real)p.x[(long long)c * S + i];
         for (int t = tid; t < H; t += BLOCK) {
             const double ut = p.u[(long long)c * H + t];
             su[t] = (real)ut;
@@ -747,7 +761,9 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
             for (int s = 0; s < SPT; ++s) { J[s] = 0.0; CT[s] = 0.0; }
 
             if constexpr (SPT == 1) {
-                real x[4] = {x0[0], x0[1], x0[2], x0[3]};
+                real x[S];
+#pragma unroll
+                for (int i = 0; i < S; ++i) x[i] = x0[i];
                 real cw = (real)0, cu = (real)0;
                 // one rollout step: v = clamp(u_n[t] + eps), x <- dynamics(x, v), cost, control term
                 auto step = [&](int t, real eps, real ut, real uit) {

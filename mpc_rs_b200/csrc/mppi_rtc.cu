@@ -111,14 +111,15 @@ template <> __device__ __forceinline__ const double* user_params<double>(const M
 template <typename real>
 struct UserCost {
     const real* p;  // the caller's parameters, read from the kernel-parameter (constant) bank
-    __device__ __forceinline__ real operator()(const real (&x)[4]) const { return ::cost(x, p); }
-    __device__ __forceinline__ real acc(const real (&x)[4], real s) const { return s + ::cost(x, p); }
+    __device__ __forceinline__ real operator()(const real (&x)[MPCB_USER_STATE_DIM]) const { return ::cost(x, p); }
+    __device__ __forceinline__ real acc(const real (&x)[MPCB_USER_STATE_DIM], real s) const { return s + ::cost(x, p); }
 };
 template <typename real>
 struct ModelUser {
+    static constexpr int kStateDim = MPCB_USER_STATE_DIM;  // S of Mppi<N,K,S>
     UserCost<real> cost;
     __device__ __forceinline__ void load(const ModelConsts& mc) { cost.p = user_params<real>(mc); }
-    __device__ __forceinline__ void step(real (&x)[4], real u) const { ::dynamics(x, u, cost.p); }
+    __device__ __forceinline__ void step(real (&x)[MPCB_USER_STATE_DIM], real u) const { ::dynamics(x, u, cost.p); }
 };
 }  // namespace mpcb
 )RTC";
@@ -230,8 +231,8 @@ mpcb_status compile_and_load(const std::string& src, const std::string (&names)[
 
 }  // namespace
 
-mpcb_status rtc_compile_mppi_user(const char* user_src, bool f64, int block, bool vt, bool load, RtcModule* out) {
-    std::string src = "#include \"mppi_kernel.cuh\"\n#line 1 \"user_model.cu\"\n";
+mpcb_status rtc_compile_mppi_user(const char* user_src, int state_dim, bool f64, int block, bool vt, bool load, RtcModule* out) {
+    std::string src = "#define MPCB_USER_STATE_DIM " + std::to_string(state_dim) + "\n#include \"mppi_kernel.cuh\"\n#line 1 \"user_model.cu\"\n";
     src += user_src;
     src += "\n#line 1 \"mpcb_user_adapter.cu\"\n";
     src += kAdapter;

@@ -29,10 +29,10 @@ class DeviceModel:
 class UserModel(DeviceModel):
     """`dynamics` and `cost` of Mppi::new (src/mppi.rs:9-10) as CUDA C++ source + constants (mpcb_mppi_create_user):
 
-        template <typename real> void dynamics(real (&x)[4], real u, const real* p);   // x <- f(x, u)
-        template <typename real> real cost(const real (&x)[4], const real* p);
+        template <typename real> void dynamics(real (&x)[S], real u, const real* p);   // x <- f(x, u)
+        template <typename real> real cost(const real (&x)[S], const real* p);
 
-    Build one with `user_model(source, params)`."""
+    S = the S of Mppi<N,K,S> (1..8, the `S` argument of Mppi).  Build one with `user_model(source, params)`."""
     source: str = ""
     params: tuple = ()
 
@@ -44,9 +44,9 @@ def user_model(source: str, params=(), name: str = "user") -> UserModel:
     return UserModel(A.MODEL_USER, name, source, params)
 
 
-def check_user_source(source: str, precision: str = "f32") -> str:
+def check_user_source(source: str, precision: str = "f32", S: int = 4) -> str:
     """Compile-only check (NVRTC, no GPU needed); returns the compiler log, raises MpcB200Error if it does not compile."""
-    st = A.lib().mpcb_mppi_check_user_source(source.encode(), {"f32": A.F32, "f64": A.F64}[precision])
+    st = A.lib().mpcb_mppi_check_user_source(source.encode(), int(S), {"f32": A.F32, "f64": A.F64}[precision])
     log = (A.lib().mpcb_rtc_log() or b"").decode()
     if st != A.OK:
         raise A.MpcB200Error(st, "user model did not compile:\n" + log)

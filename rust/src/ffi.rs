@@ -25,7 +25,7 @@ extern "C" {
     pub fn mpcb_mppi_create(out: *mut *mut MpcbMppi, cfg: *const MpcbMppiCfg) -> i32;
     pub fn mpcb_mppi_create_user(out: *mut *mut MpcbMppi, cfg: *const MpcbMppiCfg, cuda_source: *const std::os::raw::c_char,
                                  params: *const f64, n_params: i32) -> i32;
-    pub fn mpcb_mppi_check_user_source(cuda_source: *const std::os::raw::c_char, precision: i32) -> i32;
+    pub fn mpcb_mppi_check_user_source(cuda_source: *const std::os::raw::c_char, state_dim: i32, precision: i32) -> i32;
     pub fn mpcb_rtc_log() -> *const std::os::raw::c_char;
     pub fn mpcb_ukf_create_user(out: *mut *mut MpcbUkf, cfg: *const MpcbUkfCfg, cuda_source: *const std::os::raw::c_char,
                                 params: *const f64, n_params: i32) -> i32;

@@ -196,6 +196,11 @@ def test_user_model_source_compiles_without_a_gpu():
     """
     for prec in ("f32", "f64"):
         assert "error" not in M.check_user_source(ok, prec)
+    two = """
+    template <typename real> void dynamics(real (&x)[2], real u, const real* p) { x[0] += x[1] * p[0]; x[1] += u * p[0]; }
+    template <typename real> real cost(const real (&x)[2], const real* p) { return x[0] * x[0]; }
+    """
+    assert "error" not in M.check_user_source(two, "f32", S=2)  # Mppi<N,K,S> is generic in S
     import pytest
     with pytest.raises(M.MpcB200Error) as e:
         M.check_user_source("float cost(const float (&x)[4], const float* p) { return nope; }")

@@ -317,3 +317,87 @@ def test_user_ukf_errors(gpu_required):
     assert e.value.status == A.RTC_ERROR and "oops" in str(e.value)
     with pytest.raises(MpcB200Error):
         BatchedUkf(user_ukf_model("void fx(){}", 7, 1), 4)  # n out of range
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Mppi<N,K,S> is generic in S: user models with S = 2 and S = 6 against the numpy MPPI
+# ---------------------------------------------------------------------------------------------------------------
+S2_SOURCE = r"""
+template <typename real> void dynamics(real (&x)[2], real u, const real* p) {
+    const real v = x[1];
+    x[0] += v * p[0];
+    x[1] += (u - p[1] * v * fabs(v)) * p[0];
+}
+template <typename real> real cost(const real (&x)[2], const real* p) {
+    const real e = x[0] - p[2];
+    return e * e + (real)0.1 * (x[1] * x[1]);
+}
+"""
+S2_PARAMS = [0.05, 0.4, 1.0]
+S6_SOURCE = r"""
+// three masses on a line coupled by springs, the control pushes the first: x = [q0, v0, q1, v1, q2, v2]
+template <typename real> void dynamics(real (&x)[6], real u, const real* p) {
+    const real dt = p[0], k = p[1], c = p[2];
+    const real a0 = u - k * (x[0] - x[2]) - c * x[1];
+    const real a1 = k * (x[0] - x[2]) - k * (x[2] - x[4]) - c * x[3];
+    const real a2 = k * (x[2] - x[4]) - c * x[5] - (real)0.3 * sin(x[4]);
+    x[0] += x[1] * dt; x[2] += x[3] * dt; x[4] += x[5] * dt;
+    x[1] += a0 * dt; x[3] += a1 * dt; x[5] += a2 * dt;
+}
+template <typename real> real cost(const real (&x)[6], const real* p) {
+    const real e = x[4] - p[3];
+    return (real)2.0 * (e * e) + (real)0.05 * (x[1] * x[1] + x[3] * x[3] + x[5] * x[5]) + (real)0.2 * ((x[0] - x[4]) * (x[0] - x[4]));
+}
+"""
+S6_PARAMS = [0.04, 6.0, 0.3, 0.5]
+
+
+def _s2_dyn(x, u, _):
+    dt, drag, _t = S2_PARAMS
+    v = x[..., 1]
+    return np.stack([x[..., 0] + v * dt, v + (u - drag * v * np.abs(v)) * dt], axis=-1)
+
+
+def _s2_cost(x):
+    e = x[..., 0] - S2_PARAMS[2]
+    return e * e + 0.1 * x[..., 1] ** 2
+
+
+def _s6_dyn(x, u, _):
+    dt, k, c, _t = S6_PARAMS
+    a0 = u - k * (x[..., 0] - x[..., 2]) - c * x[..., 1]
+    a1 = k * (x[..., 0] - x[..., 2]) - k * (x[..., 2] - x[..., 4]) - c * x[..., 3]
+    a2 = k * (x[..., 2] - x[..., 4]) - c * x[..., 5] - 0.3 * np.sin(x[..., 4])
+    return np.stack([x[..., 0] + x[..., 1] * dt, x[..., 1] + a0 * dt, x[..., 2] + x[..., 3] * dt, x[..., 3] + a1 * dt,
+                     x[..., 4] + x[..., 5] * dt, x[..., 5] + a2 * dt], axis=-1)
+
+
+def _s6_cost(x):
+    e = x[..., 4] - S6_PARAMS[3]
+    return 2.0 * e * e + 0.05 * (x[..., 1] ** 2 + x[..., 3] ** 2 + x[..., 5] ** 2) + 0.2 * (x[..., 0] - x[..., 4]) ** 2
+
+
+@pytest.mark.parametrize("S,source,params,dyn,cost", [(2, S2_SOURCE, S2_PARAMS, _s2_dyn, _s2_cost), (6, S6_SOURCE, S6_PARAMS, _s6_dyn, _s6_cost)])
+@pytest.mark.parametrize("precision,tol", [("f64", 1e-10), ("f32", 1e-5)])
+def test_other_state_dimensions(gpu_required, S, source, params, dyn, cost, precision, tol):
+    R.MPPI_MODELS["custom_s"] = (dyn, cost)
+    lam, sig, lim = 0.6, 1.2, (-4.0, 4.0)
+    rng = np.random.default_rng(10 + S)
+    um = user_model(source, params)
+    # the long horizon (two merge levels, no v tile) only in FP64: 12 s of FP32 rollout is beyond the 1e-5 bar (DESIGN §7)
+    for K, H, C in ((4096, 16, 1), (1500, 9, 2), (40000, 300 if precision == "f64" else 40, 1)):
+        with Mppi(H, K, S, model=um, lam=lam, std_dev=sig, limit=lim, precision=precision, controllers=C) as m:
+            assert m.S == S
+            xs = rng.normal(0, 0.4, (C, S))
+            us = rng.uniform(-1, 1, (C, H))
+            eps = (sig * rng.standard_normal((C, K, H))).astype(np.float64 if precision == "f64" else np.float32)
+            u_g = np.reshape(m.compute_replay(xs if C > 1 else xs[0], us if C > 1 else us[0], eps if C > 1 else eps[0]), (C, H))
+            for c in range(C):
+                u_r, c_r = R.mppi_compute("custom_s", 0.0, lam, sig, lim, xs[c], us[c], eps[c].astype(np.float64))
+                assert m.info[c]["argmax"] == int(np.argmax(c_r))
+                assert rel_err(u_g[c], u_r) < tol, (S, K, H, c, rel_err(u_g[c], u_r))
+            # generate mode on host buffers (x travels inline in the kernel parameters for one controller)
+            ug = np.reshape(m.compute(xs if C > 1 else xs[0], us if C > 1 else us[0]), (C, H))
+            assert np.all(np.isfinite(ug)) and np.all(np.abs(ug) <= 4.0)
+    with pytest.raises(MpcB200Error):
+        Mppi(8, 1024, 3, model=models.NL, lam=1.0, std_dev=1.0)  # the built-in models are S = 4
