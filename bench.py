@@ -411,6 +411,9 @@ def run_gpu(args):
         "bound": "fp32", "kernel": "mppi_rollout_kernel<ModelNL,float,256 threads x 2 samples (packed f32x2),generate,v tile>",
         "achieved": ach_tflops, "peak": peaks["fp32_tflops"], "unit": "TFLOP/s", "frac": ach_tflops / peaks["fp32_tflops"],
         "traffic": MPPI_DRAM_TRAFFIC_BYTES, "kernel_ms": kern_ms,
+        # instruction-level view of the same kernel from the committed ncu --set full capture (not measured in this run)
+        "ncu": {"fma_pipe_cycles_active_pct": 46.4, "alu_pipe_inst_pct": 34.0, "xu_pipe_inst_pct": 22.2, "issue_active_pct": 50.7,
+                "registers": 122, "source": "profiles/mppi_r1_final2_ncu_full_summary.txt"},
         "note": f"{FLOPS_PER_STEP:.0f} algorithmic FP32 flops per rollout-step (SURVEY.md 8d) x {K_PER_GPU * H} steps per launch; "
                 f"peak = {peaks['fp32_source']}; neither 'hbm' nor 'tensor' bounds this kernel: it issues FP32/MUFU "
                 "instructions and moves 87 KB of DRAM per launch (traffic, bytes, ncu); kernel_ms = back-to-back launches "
@@ -420,6 +423,8 @@ def run_gpu(args):
         gbs = ukf_out["value"] / world * UKF_BYTES / 1e9
         ukf_out["roofline"] = {"bound": "hbm", "kernel": "ukf_kernel<4,2,PEN_LIN,cholesky,interleaved,fused>", "achieved": gbs,
                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": UKF_DRAM_TRAFFIC_BYTES,
+                               "ncu": {"fp64_pipe_cycles_active_pct": 59.8, "dram_throughput_pct": 50.7, "issue_active_pct": 52.6,
+                                       "registers": 162, "source": "profiles/ukf_r1_pipe_ncu_full_summary.txt"},
                                "note": f"{UKF_BYTES:.0f} algorithmic bytes per filter-update (x, full P in and out, z: SURVEY.md 8d); the "
                                        "kernel does not read the strictly-upper triangle of P (predict never uses it), so the DRAM "
                                        f"traffic is lower than the algorithmic figure; peak = {peaks['hbm_source']}; "
