@@ -265,6 +265,28 @@ class UnscentedKalmanFilter : public detail::UkfBase<4, 3> {
 };
 }  // namespace ukf
 
+namespace ukfn {
+// The same filter for any dimensions (n = NS in 1..6, o = NO in 1..5) with the caller's own fx / hx closures given as CUDA
+// C++ source (mpcb_ukf_create_user) — the reference hard-codes (4,3) in mpc::ukf and (6,5) in mpc::ukf2; its algorithm,
+// which is what the kernel implements, does not depend on them.
+template <std::size_t NS, std::size_t NO>
+class UnscentedKalmanFilter : public detail::UkfBase<NS, NO> {
+    using Base = detail::UkfBase<NS, NO>;
+
+   public:
+    static UnscentedKalmanFilter create_user(const typename Base::State& x, const typename Base::CovN& p, const typename Base::CovN& q,
+                                             const typename Base::CovO& r, const std::string& cuda_source,
+                                             const std::vector<double>& params = {}) {
+        return UnscentedKalmanFilter(x, p, q, r, cuda_source, params);
+    }
+    void set_q(const typename Base::CovN& q) { detail::check(mpcb_ukf_set_q(this->h_, q.data()), "mpcb_ukf_set_q"); }
+    void set_r(const typename Base::CovO& r) { detail::check(mpcb_ukf_set_r(this->h_, r.data()), "mpcb_ukf_set_r"); }
+
+   private:
+    using Base::Base;
+};
+}  // namespace ukfn
+
 namespace ukf2 {
 // mpc::ukf2::UnscentedKalmanFilter — n = 6, o = 5 (src/ukf2.rs:1-137)
 class UnscentedKalmanFilter : public detail::UkfBase<6, 5> {

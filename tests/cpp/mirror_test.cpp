@@ -174,6 +174,50 @@ void hx(const double (&x)[4], double (&z)[3], const double* p) {
         EXPECT(rel_err(f.state(), xo) < 1e-6 && rel_err(f.covariance(), Po) < 1e-6, "user ukf: %.3e %.3e", rel_err(f.state(), xo),
                rel_err(f.covariance(), Po));
     }
+    // ---- ukfn::UnscentedKalmanFilter<3, 2>: a filter of other dimensions with the caller's own fx / hx; a linear model,
+    //      so that the unscented filter has a closed form: the Kalman filter of examples/two-liner-kf.rs:17-52, except
+    //      that the reference's update reuses the sigma points propagated by predict (src/ukf.rs:54-74), which do not
+    //      carry Q — innovation covariance and cross covariance are built from F P F^T, the covariance update from
+    //      F P F^T + Q
+    {
+        const std::string src = R"SRC(
+void fx(double (&x)[3], double u, double dt, const double* p) { x[0] += x[1] * dt; x[1] += (u + x[2]) * dt; }
+void hx(const double (&x)[3], double (&z)[2], const double* p) { z[0] = x[0]; z[1] = x[1] + p[0] * x[2]; }
+)SRC";
+        const double dt = 0.1, u = 0.7, c = 0.5;
+        const std::array<double, 9> Q{1e-3, 0, 0, 0, 1e-2, 0, 0, 0, 1e-4}, P0{1, 0.1, 0, 0.1, 2, 0.2, 0, 0.2, 3};
+        const std::array<double, 4> R{0.05, 0, 0, 0.2};
+        auto f = ukfn::UnscentedKalmanFilter<3, 2>::create_user({0.3, -0.1, 0.05}, P0, Q, R, src, {c});
+        // closed-form KF with F = [[1,dt,0],[0,1,dt],[0,0,1]], B = [0,dt,0], H = [[1,0,0],[0,1,c]]
+        double x[3] = {0.3, -0.1, 0.05}, P[3][3] = {{1, 0.1, 0}, {0.1, 2, 0.2}, {0, 0.2, 3}};
+        const double F[3][3] = {{1, dt, 0}, {0, 1, dt}, {0, 0, 1}}, Hm[2][3] = {{1, 0, 0}, {0, 1, c}};
+        const std::array<double, 2> z{0.25, 0.1};
+        {
+            double xp[3] = {x[0] + x[1] * dt, x[1] + (u + x[2]) * dt, x[2]}, FP[3][3] = {}, Pp[3][3] = {};
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) for (int k = 0; k < 3; ++k) FP[i][j] += F[i][k] * P[k][j];
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { for (int k = 0; k < 3; ++k) Pp[i][j] += FP[i][k] * F[j][k]; Pp[i][j] += Q[i * 3 + j]; }
+            double S[2][2] = {}, PHt[3][2] = {}, Pm[3][3];
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Pm[i][j] = Pp[i][j] - Q[i * 3 + j];  // F P F^T
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j) for (int k = 0; k < 3; ++k) PHt[i][j] += Pm[i][k] * Hm[j][k];
+            for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) { for (int k = 0; k < 3; ++k) S[i][j] += Hm[i][k] * PHt[k][j]; S[i][j] += R[i * 2 + j]; }
+            const double det = S[0][0] * S[1][1] - S[0][1] * S[1][0];
+            const double Si[2][2] = {{S[1][1] / det, -S[0][1] / det}, {-S[1][0] / det, S[0][0] / det}};
+            double K[3][2] = {};
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j) for (int k = 0; k < 2; ++k) K[i][j] += PHt[i][k] * Si[k][j];
+            const double inn[2] = {z[0] - xp[0], z[1] - (xp[1] + c * xp[2])};
+            for (int i = 0; i < 3; ++i) x[i] = xp[i] + K[i][0] * inn[0] + K[i][1] * inn[1];
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { double kskt = 0; for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) kskt += K[i][a] * S[a][b] * K[j][b]; P[i][j] = Pp[i][j] - kskt; }
+        }
+        f.predict(u, DeviceModel::USER_UKF, dt);
+        f.update(z, DeviceModel::USER_UKF);
+        const auto xs = f.state();
+        const auto Ps = f.covariance();
+        double ex = 0, ep = 0;
+        for (int i = 0; i < 3; ++i) ex = std::fmax(ex, std::fabs(xs[i] - x[i]));
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) ep = std::fmax(ep, std::fabs(Ps[i * 3 + j] - P[i][j]));
+        // exact for linear models up to the sigma-weight amplification of rounding (1.7e5 x 1e-16 per operation)
+        EXPECT(ex < 1e-8 && ep < 1e-8, "linear-model UKF<3,2> vs closed-form KF: %.3e %.3e", ex, ep);
+    }
     // ---- mpc::ukf2 (n=6, o=5): set_q / set_r / set_enable / gen_r exist and a gated step runs
     {
         std::array<double, 36> Q{}, P0{};
