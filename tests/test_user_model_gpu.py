@@ -401,3 +401,17 @@ def test_other_state_dimensions(gpu_required, S, source, params, dyn, cost, prec
             assert np.all(np.isfinite(ug)) and np.all(np.abs(ug) <= 4.0)
     with pytest.raises(MpcB200Error):
         Mppi(8, 1024, 3, model=models.NL, lam=1.0, std_dev=1.0)  # the built-in models are S = 4
+
+
+def test_example_user_ukf_finds_the_bias(gpu_required):
+    """examples/ukf_user_model.py: n = 3, o = 2 with the caller's own fx / hx; 256 filters on noisy measurements of
+    plants with an unknown torque bias of 1.5: every filter finds the bias and tracks angle and rate."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples"))
+    import ukf_user_model as ex
+    x_act, x_est, p = ex.run(batch=256, steps=400, quiet=True, seed=1)
+    assert np.all(np.isfinite(x_est)) and np.all(np.isfinite(p))
+    assert np.max(np.abs(x_est[:, 2] - x_act[:, 2])) < 0.15      # bias found (prior 0 +- 2, truth 1.5)
+    assert np.max(np.abs(x_est[:, 0] - x_act[:, 0])) < 0.05 and np.max(np.abs(x_est[:, 1] - x_act[:, 1])) < 0.1
+    assert np.all(p[:, 2, 2] < 0.05)                             # and it knows it (P0 = 4)
