@@ -1,0 +1,62 @@
+"""Build-time resource contract of the two headline kernels, read from the ptxas logs the Makefile keeps next to the
+objects (no GPU needed): the launch plans in mppi_api.cu / ukf.cu and the measured numbers in DESIGN.md assume these
+register, spill and shared-memory figures — one block of 256 threads x 2 samples per SM with headroom for the MPPI
+kernel of BASELINE configs[1], three resident blocks of 128 filters for the fused four-state UKF kernel."""
+import os
+import re
+
+import pytest
+
+CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "mpc_rs_b200", "csrc")
+
+
+def entries(log):
+    path = os.path.join(CSRC, log)
+    if not os.path.exists(path):
+        pytest.skip(f"{log} not built yet (run __graft_entry__.build())")
+    out, cur = {}, None
+    for line in open(path):
+        m = re.search(r"Compiling entry function '(\S+)'", line)
+        if m:
+            cur = m.group(1)
+            out[cur] = {"regs": None, "smem": 0, "spill_st": 0, "spill_ld": 0}
+            continue
+        if cur is None:
+            continue
+        m = re.search(r"(\d+) bytes spill stores, (\d+) bytes spill loads", line)
+        if m and out[cur]["regs"] is None:  # the entry's own frame comes before its 'Used' line
+            out[cur]["spill_st"], out[cur]["spill_ld"] = int(m.group(1)), int(m.group(2))
+        m = re.search(r"Used (\d+) registers", line)
+        if m and out[cur]["regs"] is None:
+            out[cur]["regs"] = int(m.group(1))
+            s = re.search(r"(\d+) bytes smem", line)
+            out[cur]["smem"] = int(s.group(1)) if s else 0
+    return out
+
+
+def test_mppi_configs1_kernel_resources():
+    # mppi_rollout_kernel<ModelNL, float, BLOCK=256, NOISE_GENERATE=0, SPT=2, VT=true>
+    e = entries("mppi_f32x2_NL.o.ptxas.log")
+    name = "_ZN4mpcb19mppi_rollout_kernelINS_7ModelNLEfLi256ELi0ELi2ELb1EEEvNS_10MppiParamsE"
+    assert name in e, sorted(e)[:4]
+    k = e[name]
+    assert k["regs"] <= 128, k            # 256 threads x 128 registers = half the register file: one block per SM + headroom
+    assert k["spill_st"] == 0 and k["spill_ld"] == 0, k
+    # every generate-mode (NOISE = 0) FP32 flavour of model NL that keeps the v tile stays within 128 registers and does not spill: the
+    # multi-batch plans then hold 16 warps per SM (the dump / replay flavours are verification modes and may use more)
+    for log in ("mppi_f32x2_NL.o.ptxas.log", "mppi_f32_NL.o.ptxas.log"):
+        for n, v in entries(log).items():
+            if re.search(r"mppi_rollout_kernelINS_7ModelNLEfLi\d+ELi0ELi\dELb1E", n):  # generate mode, v tile kept
+                assert v["regs"] <= 128 and v["spill_st"] == 0, (n, v)
+
+
+def test_ukf_config3_kernel_resources():
+    # ukf_kernel<4, 2, PEN_LIN=16, CHOLESKY=0, INTERLEAVED=1, FUSED=2, FAST=true>
+    e = entries("ukf_n4_fast.o.ptxas.log")
+    name = "_ZN4mpcb10ukf_kernelILi4ELi2ELi16ELi0ELi1ELi2ELb1EEEvNS_9UkfParamsE"
+    assert name in e, sorted(e)[:4]
+    k = e[name]
+    assert k["regs"] <= 168, k            # 3 blocks x 128 threads x 168 registers <= 65536
+    assert k["spill_st"] == 0 and k["spill_ld"] == 0, k
+    assert 0 < k["smem"] <= 48 * 1024, k  # the cp.async double buffer is static shared memory (no opt-in attribute)
+    assert 3 * (k["smem"] + 1024) <= 227 * 1024
