@@ -60,3 +60,29 @@ def test_ukf_config3_kernel_resources():
     assert k["spill_st"] == 0 and k["spill_ld"] == 0, k
     assert 0 < k["smem"] <= 48 * 1024, k  # the cp.async double buffer is static shared memory (no opt-in attribute)
     assert 3 * (k["smem"] + 1024) <= 227 * 1024
+
+
+def test_sass_has_the_instructions_the_design_relies_on():
+    """cuobjdump -sass of the built objects: packed FP32 (FFMA2) in the two-samples-per-thread MPPI kernels, asynchronous
+    global->shared copies (LDGSTS = cp.async) in the fused four-state UKF kernel, which keeps everything in registers."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+
+    def sass(obj, mangled):
+        path = os.path.join(CSRC, obj)
+        if not os.path.exists(path):
+            pytest.skip(f"{obj} not built yet")
+        out = subprocess.run(["cuobjdump", "-sass", "-fun", mangled, path], capture_output=True, text=True, timeout=300).stdout
+        assert "Function :" in out, out[:300]
+        return out
+
+    m = sass("mppi_f32x2_NL.o", "_ZN4mpcb19mppi_rollout_kernelINS_7ModelNLEfLi256ELi0ELi2ELb1EEEvNS_10MppiParamsE")
+    assert m.count("FFMA2") > 100 and m.count("FMUL2") > 50, (m.count("FFMA2"), m.count("FMUL2"))
+    assert "MUFU.SIN" in m and "MUFU.LG2" in m          # Box-Muller on the special-function unit
+    # the only local memory is the MergeOut argument block of the out-of-line merge functions (the 176-byte frame)
+    assert m.count(" LDL") + m.count(" STL") < 120, (m.count(" LDL"), m.count(" STL"))
+    u = sass("ukf_n4_fast.o", "_ZN4mpcb10ukf_kernelILi4ELi2ELi16ELi0ELi1ELi2ELb1EEEvNS_9UkfParamsE")
+    assert u.count("LDGSTS") >= 17, u.count("LDGSTS")  # x (4) + lower triangle of P (10) + z (2) + status per tile
+    assert u.count("DFMA") > 200 and " LDL" not in u and " STL" not in u
