@@ -155,3 +155,52 @@ def test_example_mppi4_non_liner_s(gpu_required, tmp_path):
     data = np.loadtxt(csv, delimiter=",")                          # write_record only: no header row (:157-166)
     assert data.shape == (len(rows), 6)
     np.testing.assert_allclose(data[:, 1], rows[:, 1], rtol=0, atol=0)
+
+
+def test_handles_are_send_and_distinct_handles_run_concurrently(gpu_required):
+    """The reference's examples run the controller in the main thread while a second thread owns the filter
+    (examples/mppi4-non-liner-ukf.rs:162-168,273-284: Arc<Mutex<UnscentedKalmanFilter>>): a handle must be usable from
+    a thread other than the one that created it (Send), and distinct handles must work concurrently.  Two worker
+    threads drive an MPPI handle and a UKF handle created by the main thread at the same time (ctypes drops the GIL
+    inside the calls); the results must be the bits a single-threaded run produces."""
+    import threading
+    from mpc_rs_b200 import Mppi
+    H, K, B, T = 16, 20000, 3000, 25
+    rng = np.random.default_rng(12)
+    eps = (3.0 * rng.standard_normal((T, K, H))).astype(np.float32)
+    x0 = np.array([0.5, 0.0, 0.1, 0.0])
+    Q, R, P0 = ukf.default_noise(models.PEN_LIN)
+    zs = rng.normal(0, 0.7, (T, B, 2))
+
+    def run_mppi(m, out):
+        u = np.zeros(H)
+        for t in range(T):
+            u = m.compute_replay(x0, u, eps[t])
+            out.append(u.copy())
+
+    def run_ukf(f, out):
+        for t in range(T):
+            f.predict(0.0015)
+            f.update(zs[t])
+        out.extend(f.get_state())
+
+    kw = dict(model=models.NL, lam=0.5, std_dev=3.0, limit=(-20, 20), precision="f32", dt=0.05)
+    with Mppi(H, K, **kw) as m1, Mppi(H, K, **kw) as m2, BatchedUkf(models.PEN_LIN, B) as f1, BatchedUkf(models.PEN_LIN, B) as f2:
+        for f in (f1, f2):
+            f.init(np.zeros(4), P0, Q, R)
+        ref_m, ref_f, thr_m, thr_f, errors = [], [], [], [], []
+        run_mppi(m1, ref_m)  # single-threaded reference
+        run_ukf(f1, ref_f)
+
+        def guard(fn, *a):
+            try:
+                fn(*a)
+            except Exception as e:  # noqa: BLE001 - surfaced below
+                errors.append(e)
+
+        ta = threading.Thread(target=guard, args=(run_mppi, m2, thr_m))
+        tb = threading.Thread(target=guard, args=(run_ukf, f2, thr_f))
+        ta.start(); tb.start(); ta.join(); tb.join()
+        assert not errors, errors
+        assert len(thr_m) == T and all(np.array_equal(a, b) for a, b in zip(ref_m, thr_m))
+        assert np.array_equal(ref_f[0], thr_f[0]) and np.array_equal(ref_f[1], thr_f[1])
