@@ -379,3 +379,42 @@ def test_golden_fixtures_gpu(gpu_required):
                     u = m.compute_replay(g[f"x_{s}"], g[f"u_in_{s}"], g[f"eps_{s}"])
                     assert m.info[0]["argmax"] == int(g[f"argmax_{s}"])
                     assert rel_err(u, g[f"u_out_{s}"]) < tol, (name, prec, s)
+
+
+def test_property_random_problems_with_poisoned_samples(gpu_required):
+    """SURVEY.md §4 property layer: hypothesis draws (model, K, H, x, u_n, lambda, sigma, limits) and optionally poisons
+    one sample's noise with NaN or +-inf; the FP64 kernel must return what the oracle returns — the same Err of
+    src/mppi.rs:69,77,88 or the same controls and argmin."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    finite = dict(allow_nan=False, allow_infinity=False)
+
+    @settings(max_examples=40, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(case=st.sampled_from(["L_shipped", "NL_shipped", "NL6_shipped"]), K=st.integers(1, 700), H=st.integers(1, 24),
+           lam=st.floats(0.05, 5.0, **finite), sig=st.floats(0.1, 6.0, **finite), lo=st.floats(-25.0, -0.5, **finite),
+           hi=st.floats(0.5, 25.0, **finite), seed=st.integers(0, 2 ** 31 - 1),
+           poison=st.sampled_from([None, "nan", "inf", "-inf", "nan_state"]))
+    def check(case, K, H, lam, sig, lo, hi, seed, poison):
+        model, oid, _, dt, _, _, _ = CASES[case]
+        p = O.model_defaults(oid, dt=dt)
+        rng = np.random.default_rng(seed)
+        x = rng.normal(0, 0.3, 4)
+        u_n = rng.uniform(lo, hi, H)
+        eps = sig * rng.standard_normal((K, H))
+        if poison == "nan_state":
+            x[rng.integers(0, 4)] = np.nan
+        elif poison is not None:
+            eps[rng.integers(0, K), rng.integers(0, H)] = {"nan": np.nan, "inf": np.inf, "-inf": -np.inf}[poison]
+        st_o, u_o, io, _ = O.mppi_compute(oid, p, K, H, lam, sig, lo, hi, x, u_n, eps)
+        with Mppi(H, K, model=model, lam=lam, std_dev=sig, limit=(lo, hi), precision="f64", dt=dt) as m:
+            try:
+                u_g = m.compute_replay(x, u_n, eps)
+                st_g = 0
+            except MppiError as e:
+                st_g, u_g = e.status, None
+            assert st_g == st_o, (st_g, st_o, poison)
+            if st_o == 0:
+                assert m.info[0]["argmax"] == io["argmax"] and m.info[0]["n_finite"] == io["n_finite"]
+                assert rel_err(u_g, u_o) < 1e-8, rel_err(u_g, u_o)
+
+    check()

@@ -279,3 +279,46 @@ def test_many_tiles_per_block_ragged_batch(gpu_required, name, steps_per_launch)
     assert relerr(xg[pick], xr) < tol, relerr(xg[pick], xr)
     assert relerr(Pg[pick], Pr) < tol, relerr(Pg[pick], Pr)
     assert np.all(np.isfinite(xg)) and np.all(np.isfinite(Pg))
+
+
+def test_property_random_covariances_and_failures(gpu_required):
+    """SURVEY.md §4 property layer for the filter: hypothesis draws (model, square root, state, a random covariance that is
+    sometimes NOT positive definite, Q, R, z); one fused step of the reference-order kernel must give the oracle's state
+    and covariance, or the oracle's failure status for exactly the same filters."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @settings(max_examples=30, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(name=st.sampled_from(["PEN_LIN", "PEN_NL"]), sqrt_mode=st.sampled_from(["cholesky", "eig"]), B=st.integers(1, 70),
+           seed=st.integers(0, 2 ** 31 - 1), scale=st.floats(1e-3, 50.0, allow_nan=False, allow_infinity=False),
+           break_pd=st.booleans())
+    def check(name, sqrt_mode, B, seed, scale, break_pd):
+        model, oid, u = MODELS[name]
+        p = O.model_defaults(oid)
+        n, o = O.dims(oid)
+        rng = np.random.default_rng(seed)
+        a = rng.normal(0, 1, (B, n, n))
+        P = scale * (a @ np.transpose(a, (0, 2, 1)) + 0.05 * np.eye(n))
+        if break_pd and sqrt_mode == "cholesky":
+            bad = rng.integers(0, B)
+            P[bad] = -P[bad]  # Cholesky must fail for this filter only
+        x = rng.normal(0, 0.2, (B, n))
+        Q = np.diag(rng.uniform(0, 1, n))
+        R = np.diag(rng.uniform(0.05, 5.0, o))
+        z = rng.normal(0, 1, (B, o))
+        xr, Pr, st_o = O.ukf_step_batch(oid, p, x, P, Q, R, u, z, 0.0, SQRT[sqrt_mode], O.ORDER_LIBRARY)
+        with BatchedUkf(model, B, sqrt_mode=sqrt_mode, sigma_order="library", exact=True) as f:
+            f.init(np.zeros(n), np.eye(n), Q, R)
+            f.set_state(x, P)
+            f.step(u, z, check=False)
+            st_g = f.status()
+            xg, Pg = f.get_state()
+        assert np.array_equal(st_g != 0, np.asarray(st_o) != 0), (st_g, st_o)
+        ok = np.asarray(st_o) == 0
+        if ok.any():
+            assert relerr(xg[ok], xr[ok]) < 1e-7, relerr(xg[ok], xr[ok])
+            assert relerr(Pg[ok], Pr[ok]) < 1e-7, relerr(Pg[ok], Pr[ok])
+        if (~ok).any():  # a failed filter keeps the state it had
+            np.testing.assert_array_equal(Pg[~ok], P[~ok])
+            np.testing.assert_array_equal(xg[~ok], x[~ok])
+
+    check()
