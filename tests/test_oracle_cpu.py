@@ -261,3 +261,45 @@ def test_golden_fixtures(name):
     fresh = make_golden.CASES[name]()
     for k in g.files:
         np.testing.assert_allclose(fresh[k], g[k], rtol=1e-12, atol=1e-13, err_msg=f"{name}:{k}")
+
+
+def test_property_oracle_against_numpy_with_poisoned_samples():
+    """The C oracle against the independent numpy restatement over hypothesis-drawn problems, with one sample's noise
+    optionally NaN / +-inf or a NaN in the state: the same Err of src/mppi.rs:69,77,88 or the same controls and argmin.
+    (Both are restatements — parity stays unpinned — but they share no code, so agreement here is what the GPU parity
+    tests stand on.)"""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    finite = dict(allow_nan=False, allow_infinity=False)
+    msgs = {1: "Cannot calculate max", 2: "sum is zero", 3: "u is invalid"}
+
+    @settings(max_examples=60, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(oid=st.sampled_from([O.MODEL_L, O.MODEL_NL, O.MODEL_NL6]), K=st.integers(1, 400), H=st.integers(1, 20),
+           lam=st.floats(0.05, 5.0, **finite), sig=st.floats(0.1, 6.0, **finite), lo=st.floats(-25.0, -0.5, **finite),
+           hi=st.floats(0.5, 25.0, **finite), seed=st.integers(0, 2 ** 31 - 1),
+           poison=st.sampled_from([None, "nan", "inf", "-inf", "nan_state"]))
+    def check(oid, K, H, lam, sig, lo, hi, seed, poison):
+        dt = 0.15 if oid == O.MODEL_NL6 else 0.1
+        p = O.model_defaults(oid, dt=dt)
+        rng = np.random.default_rng(seed)
+        x = rng.normal(0, 0.3, 4)
+        u_n = rng.uniform(lo, hi, H)
+        eps = sig * rng.standard_normal((K, H))
+        if poison == "nan_state":
+            x[rng.integers(0, 4)] = np.nan
+        elif poison is not None:
+            eps[rng.integers(0, K), rng.integers(0, H)] = {"nan": np.nan, "inf": np.inf, "-inf": -np.inf}[poison]
+        st_o, u_o, info, _ = O.mppi_compute(oid, p, K, H, lam, sig, lo, hi, x, u_n, eps)
+        try:
+            with np.errstate(all="ignore"):
+                u_r, c_r = RN.mppi_compute(oid, dt, lam, sig, (lo, hi), x, u_n, eps)
+            st_r = 0
+        except ValueError as e:
+            st_r = {v: k for k, v in msgs.items()}[str(e)]
+        assert st_o == st_r, (st_o, st_r, poison)
+        if st_o == 0:
+            fin = np.isfinite(c_r)
+            assert info["argmax"] == int(np.flatnonzero(fin)[np.argmax(c_r[fin])]) and info["n_finite"] == int(fin.sum())
+            np.testing.assert_allclose(u_o, u_r, rtol=1e-9, atol=1e-12)
+
+    check()
