@@ -119,6 +119,7 @@ void fill_params(const mpcb_ukf* h, UkfParams* p) {
     memcpy(p->R, h->R, sizeof(p->R));
     p->mc = h->mc;
     p->enable = h->enable;
+    p->reverse = (getenv("MPCB_UKF_NO_REVERSE") == nullptr) ? (unsigned int)(h->launches & 1) : 0u;
 }
 
 mpcb_status launch(mpcb_ukf* h, UkfKernelFn fn, const UkfParams& p) {

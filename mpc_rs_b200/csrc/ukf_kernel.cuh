@@ -36,7 +36,7 @@ struct UkfParams {
     double u_scalar;
     double dt;
     unsigned int enable;  // sensor bit mask: hx rows of cleared bits read 0 (examples/mppi4-ukf-commu.rs:279-293)
-    unsigned int pad0;
+    unsigned int reverse;  // 1: walk the tiles from the end (alternates per launch: the tiles the previous launch wrote last are still in L2)
     double wm0, wc0, wi, cC;  // sigma_weight (src/ukf.rs:112-118), C = alpha^2 (n + kappa)
     double Q[36];
     double R[25];
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(kUkfThreads) ukf_kernel(const __grid_constant_
 
     // stage the inputs of `tile` for this thread's filter into buffer `slot`
     auto prefetch = [&](long long tile, int slot) {
-        const long long bb = tile * kUkfThreads + tid;
+        const long long bb = (p.reverse ? ntiles - 1 - tile : tile) * kUkfThreads + tid;
         if (bb < B) {
 #pragma unroll
             for (int r = 0; r < N; ++r) cp_async8(&s_in[slot][r][tid], p.x + (long long)r * B + bb);
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(kUkfThreads) ukf_kernel(const __grid_constant_
 
   int it = 0;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const long long b = tile * kUkfThreads + tid;
+    const long long b = (p.reverse ? ntiles - 1 - tile : tile) * kUkfThreads + tid;
     const bool live = b < B;
     double x[N], P[N][N], sig[N][M], z0[O];
     int st = MPCB_OK;
