@@ -55,6 +55,12 @@ mpcb_status build_model_consts(int model_id, const mpcb_model_params& p, double 
             k[slot::NL_T4] = M2 * G * L * L;
             k[slot::NL_DT] = dt;
             k[slot::NL_KTR] = KT / R_W;
+            // folded constants of the FP32 form (ModelNL<float>)
+            k[slot::NL_KU] = k[slot::NL_KTR] / k[slot::NL_ML];
+            k[slot::NL_K3] = k[slot::NL_ML] * k[slot::NL_ML] / k[slot::NL_T1];
+            k[slot::NL_K1] = k[slot::NL_JML] * k[slot::NL_ML] / k[slot::NL_T4];
+            k[slot::NL_DT1] = dt * k[slot::NL_T1];
+            k[slot::NL_DT4] = dt * k[slot::NL_T4];
             return MPCB_OK;
         }
         case MPCB_MODEL_NL6:

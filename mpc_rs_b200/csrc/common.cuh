@@ -32,7 +32,7 @@ const char* last_error();
     } while (0)
 
 // Number of generic model constants handed to a kernel (filled on the host in f64, see models_host.cpp).
-constexpr int kModelConsts = 24;
+constexpr int kModelConsts = 32;
 struct ModelConsts {
     double k[kModelConsts];
     float kf[kModelConsts];  // the same constants rounded to FP32 on the host: the packed kernels read them straight

@@ -7,7 +7,7 @@
 
 #include <new>
 
-#include "mppi_kernel.cuh"
+#include "mppi_ws_kernel.cuh"
 #include "mppi_rtc.h"
 #include "nccl_shim.h"
 
@@ -25,6 +25,9 @@ struct mpcb_mppi {
     int block = 0, chunks = 0, group_size = 0, groups = 0;
     int Hp = 8, lgHp = 3;
     int spt = 1;            // samples per thread (2: packed f32x2 kernels)
+    int ws_variant = -1;    // >= 0: warp-specialised kernel, index into kWsVariants (mppi_ws_kernel.cuh)
+    int ws_cq = 2;          // its producer->consumer chunk, in 4-step groups
+    int ws_debug = 0;       // MPCB_MPPI_WS_DEBUG: 1 = producers idle, 2 = consumers idle (timing decomposition only)
     int block_samples = 0;  // samples per block and batch = block * spt
     int mergers = 0;        // blocks sharing the final merge (0: last arriver merges alone)
     unsigned int seq = 0;   // launches so far (arrival counters are monotonic)
@@ -243,6 +246,65 @@ mpcb_status pick_kernels(mpcb_mppi* h) {
             if (forced == 2 || take) plan = p2;
         }
     }
+    // FP32 built-in models: the warp-specialised kernels (mppi_ws_kernel.cuh) — noise and control term in producer
+    // warps, the serial rollout chain in consumer warps — when one block per SM covers the controller in a single
+    // batch (BASELINE configs[1]: 13-14 sample-warps per SM).  MPCB_MPPI_WS=<variant> forces a variant of
+    // kWsVariants for any shape (several batches per block included), MPCB_MPPI_WS=-1 disables them.
+    h->ws_variant = -1;
+    if (const char* cq_env = getenv("MPCB_MPPI_WS_CQ")) {
+        const int cq = atoi(cq_env);
+        if (cq >= 1 && cq <= 128) h->ws_cq = cq;
+    }
+    if (const char* dbg_env = getenv("MPCB_MPPI_WS_DEBUG")) h->ws_debug = atoi(dbg_env);
+    if (!f64 && !h->user) {
+        const char* ws_env = getenv("MPCB_MPPI_WS");
+        int want = -2;  // auto
+        if (ws_env) want = atoi(ws_env);
+        long long chunks1 = h->num_sms / h->C;
+        if (chunks1 < 1) chunks1 = 1;
+        if (chunks1 > h->W) chunks1 = h->W;
+        const long long wpc = (h->W + chunks1 - 1) / chunks1;
+        auto ws_fits = [&](int v) {
+            if (v < 0 || v >= kNumWsVariants) return false;
+            const MppiWsVariant& wv = kWsVariants[v];
+            return mppi_kernel_ws(h->cfg.model_id, v, NOISE_GENERATE) != nullptr &&
+                   mppi_ws_smem_bytes(h->H, wv.ncw, wv.npw, wv.spt) + 2048 <= smem_max;
+        };
+        int pick = -1;
+        if (want >= 0) {
+            if (ws_fits(want)) pick = want;
+        } else if (want == -2) {
+            for (int v : {6, 0, 4}) {  // 8 / 14 / 16 sample-warps per batch, scalar consumers
+                if (wpc <= kWsVariants[v].ncw * kWsVariants[v].spt && ws_fits(v)) {
+                    pick = v;
+                    break;
+                }
+            }
+        }
+        if (pick >= 0) {
+            const MppiWsVariant& wv = kWsVariants[pick];
+            const int cap = wv.ncw * wv.spt;  // sample-warps per batch
+            plan.spt = wv.spt;
+            plan.block = (wv.ncw + wv.npw) * 32;
+            plan.sb = cap * 32;
+            plan.vt = 1;
+            plan.smem = mppi_ws_smem_bytes(h->H, wv.ncw, wv.npw, wv.spt);
+            for (int noise = 0; noise < 3; ++noise) {
+                plan.k[noise] = mppi_kernel_ws(h->cfg.model_id, pick, noise);
+                MPCB_CUDA_TRY(cudaFuncSetAttribute((const void*)plan.k[noise], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+            }
+            plan.single_batch = wpc <= cap;
+            if (plan.single_batch) {
+                plan.chunks = (h->W + wpc - 1) / wpc;
+            } else {
+                plan.chunks = h->num_sms / h->C;  // one resident block per SM
+                const long long nbatches = (h->W + cap - 1) / cap;
+                if (plan.chunks > nbatches) plan.chunks = nbatches;
+                if (plan.chunks < 1) plan.chunks = 1;
+            }
+            h->ws_variant = pick;
+        }
+    }
     h->spt = plan.spt;
     const int block = plan.block;  // threads
     h->block = block;
@@ -273,7 +335,8 @@ mpcb_status pick_kernels(mpcb_mppi* h) {
         const int npl = 1 + (ncol2 - 1 + nm - 1) / nm;
         int Hpm = 2;
         while (Hpm < npl) Hpm <<= 1;
-        int nq = block / Hpm;
+        const int tail_threads = h->ws_variant >= 0 ? mppi_ws_tail_threads(block) : block;  // threads that run the merges
+        int nq = tail_threads / Hpm;
         if (nq < 1) nq = 1;
         if (nq > kMergeMaxPart) nq = kMergeMaxPart;
         if (h->chunks <= kMergeFan && h->chunks <= 2 * kMergeBatch * nq) {
@@ -322,6 +385,8 @@ void fill_params(const mpcb_mppi* h, MppiParams* p) {
     for (int i = 0; i < kModelConsts; ++i) p->mc.kf[i] = (float)h->mc.k[i];
     p->costs = h->cfg.keep_costs ? h->d_costs : nullptr;
     p->debug_ts = h->d_ts;
+    p->ws_cq = h->ws_cq;
+    p->ws_debug = h->ws_debug;
 }
 
 // Enqueue one fused control step.

@@ -85,6 +85,7 @@ struct MppiParams {
     int G, rank;
     unsigned int xepoch, pad2;     // exchange epoch (same on every rank), parity = xepoch & 1
     unsigned long long* debug_ts;  // optional [blocks][8] %globaltimer stamps (diagnostics)
+    int ws_cq, ws_debug;           // warp-specialised kernels: 4-step groups per producer->consumer chunk; diagnostics bits
     ModelConsts mc;
     double xu_inline[8 + kInlineHorizon];  // x[S] (S <= kMaxStateDim = 8) then u_n[H]
 };
@@ -113,6 +114,10 @@ __device__ __forceinline__ unsigned int atom_add_acq_rel_gpu_u32(unsigned int* p
     unsigned int old;
     asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
     return old;
+}
+// arrival without a return value (nobody needs to know who was last when designated mergers wait for the count)
+__device__ __forceinline__ void red_add_release_gpu_u32(unsigned int* p, unsigned int v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
     unsigned int v;
@@ -158,6 +163,22 @@ __device__ __forceinline__ void warp_argmax(double v, long long tag, bool fin, d
         *vmax = -CUDART_INF;
         *tmax = kNoArg;
     }
+}
+
+// Warp max of v over the lanes with `has`, and the smallest idx among the lanes holding that max.
+__device__ __forceinline__ void warp_max_minidx(double v, long long idx, bool has, double* vmax, long long* imin) {
+    const unsigned int full = 0xffffffffu;
+    double wm;
+    long long wa;
+    int dummy;
+    warp_argmax(v, idx, has, &wm, &wa, &dummy);
+    const bool holds = has && v == wm;
+    const unsigned int ahi = holds ? (unsigned int)((unsigned long long)idx >> 32) : 0xffffffffu;
+    const unsigned int mh = __reduce_min_sync(full, ahi);
+    const unsigned int alo = (holds && ahi == mh) ? (unsigned int)idx : 0xffffffffu;
+    const unsigned int ml = __reduce_min_sync(full, alo);
+    *vmax = wm;
+    *imin = (wa == kNoArg) ? kNoArg : (long long)(((unsigned long long)mh << 32) | ml);
 }
 
 // 4 consecutive elements of shared memory (16-byte aligned for float, 32-byte for double)
@@ -230,7 +251,11 @@ __device__ __noinline__ void mppi_merge_rows(const double* rows, long long row_s
     const int p_lo = 1 + mi * cp;
     int p_hi = p_lo + cp;
     if (p_hi > ncol2) p_hi = ncol2;
-    const int npl = 1 + (p_hi > p_lo ? p_hi - p_lo : 0);  // local pairs: pair 0 + the owned ones
+    // local pairs: pair 0 (sum_w, n_finite), for mergers other than 0 also pair 1 (it holds u[0], which decides
+    // MPCB_U_INVALID: every merger must reach the same status), then the owned ones
+    const int n_extra = (mi == 0) ? 1 : 2;
+    const int npl = n_extra + (p_hi > p_lo ? p_hi - p_lo : 0);
+    auto pair_of = [&](int jl) { return jl < n_extra ? jl : p_lo + jl - n_extra; };
     int Hpm = 2, lgHpm = 1;
     while (Hpm < npl) { Hpm <<= 1; ++lgHpm; }
     int nq = BLOCK >> lgHpm;  // row partitions (power of two)
@@ -251,7 +276,7 @@ __device__ __noinline__ void mppi_merge_rows(const double* rows, long long row_s
     double2 v0[kMergeBatch];
     {
         const int jl = tid & (Hpm - 1), q = tid >> lgHpm;
-        const int pair = (jl == 0) ? 0 : p_lo + jl - 1;
+        const int pair = pair_of(jl);
         const int r0 = q * rq;
         const double2* col = reinterpret_cast<const double2*>(rows + 2 + 2 * pair + (long long)r0 * row_stride);
         const bool live = tid < items && jl < npl;
@@ -304,7 +329,7 @@ __device__ __noinline__ void mppi_merge_rows(const double* rows, long long row_s
     for (int item = tid; item < items; item += BLOCK) {
         const int jl = item & (Hpm - 1), q = item >> lgHpm;
         if (jl >= npl) continue;
-        const int pair = (jl == 0) ? 0 : p_lo + jl - 1;
+        const int pair = pair_of(jl);
         const int r0 = q * rq;
         int r1 = r0 + rq;
         if (r1 > n_rows) r1 = n_rows;
@@ -350,12 +375,15 @@ __device__ __noinline__ void mppi_merge_rows(const double* rows, long long row_s
     __shared__ int s_status;
     __syncthreads();
     const double s = tot2[0].x, nf = tot2[0].y;  // pair 0: sum_w, n_finite
+    // src/mppi.rs:69 no finite cost, :76-78 sum is zero, :87-89 u[0] not finite (element 0 only; local pair 1 is pair 1)
     if (tid == 0)
-        s_status = (o.forced_status != MPCB_OK) ? o.forced_status : (!any ? MPCB_NO_FINITE_COST : (s == 0.0 ? MPCB_SUM_ZERO : MPCB_OK));
+        s_status = (o.forced_status != MPCB_OK) ? o.forced_status
+                   : (!any ? MPCB_NO_FINITE_COST : (s == 0.0 ? MPCB_SUM_ZERO : ((final_mode != FINAL_RANK_ROW && !finite_f64(tot2[1].x / s)) ? MPCB_U_INVALID : MPCB_OK)));
     __syncthreads();
     for (int jl = tid; jl < npl; jl += BLOCK) {
         const double ax = tot2[jl].x, ay = tot2[jl].y;
-        const int pair = (jl == 0) ? 0 : p_lo + jl - 1;
+        const int pair = pair_of(jl);
+        if (mi != 0 && jl == 1) continue;  // pair 1 belongs to merger 0
         if (final_mode == FINAL_RANK_ROW) {
             // the row goes to out_row and, for the cross-GPU exchange, straight into the peers' mailboxes (NVLink stores)
             for (int r = -1; r < o.n_copies; ++r) {
@@ -373,10 +401,10 @@ __device__ __noinline__ void mppi_merge_rows(const double* rows, long long row_s
             }
         } else if (pair > 0) {
             const int t0 = 2 * pair - 2;
-            const double u0 = any ? ax / s : 0.0;
-            const double u1 = any ? ay / s : 0.0;
-            // src/mppi.rs:69 no finite cost, :76-78 sum is zero, :87-89 u[0] not finite (element 0 only)
-            if (t0 == 0 && s_status == MPCB_OK && !finite_f64(u0)) s_status = MPCB_U_INVALID;
+            // a controller whose status is not OK gets a zero row, like the reference's callers fall back to zeros
+            // (examples/mppi4-non-liner-ukf.rs:80-86)
+            const double u0 = (s_status == MPCB_OK) ? ax / s : 0.0;
+            const double u1 = (s_status == MPCB_OK) ? ay / s : 0.0;
             o.u_out[t0] = u0;
             if (o.u_out_host) o.u_out_host[t0] = u0;
             if (t0 + 1 < H) {
@@ -409,6 +437,140 @@ __device__ __noinline__ void mppi_merge_rows(const double* rows, long long row_s
     }
 }
 
+// w = exp(a) for the FP32 path: a <= 0 is computed in f64 by the caller; ex2.approx (2 ulp) on a*log2(e).
+// Underflows to exactly 0 below a ~ -87; the f64 reference would keep weights down to e^-745, all of which
+// are < 1e-37 of the block maximum.
+__device__ __forceinline__ float fast_exp_neg(double a) {
+    const float t = (float)(a * 1.4426950408889634074);
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+    return r;
+}
+
+// Single-level merge without block barriers: ONE WARP merges one column pair of the n_rows (<= kMergeFan) rows.
+// Lane l takes rows l, l + 32, ...: every load of the warp — the rows' headers (m, argmax), pair 0 (sum_w, n_finite),
+// pair 1 (it holds u[0], the element src/mppi.rs:87 checks) and the warp's own pair — is issued before anything is
+// consumed, the max/argmax runs on redux, each lane scales and sums its rows in order and a fixed xor tree adds the
+// lanes, so the result does not depend on timing and every warp of every merger block computes the same m, sum_w,
+// u[0] and status.  The round-1 merge (mppi_merge_rows: all threads of the block, five block barriers, a
+// partition pass through shared memory) took ~3.3 us of dependent latency for 147 rows; this takes one L2 round
+// trip, the exps of the lane's rows and one shuffle tree.
+// final_mode FINAL_NORMALISE: u_out[2 pair - 2 .. 2 pair - 1] = sums / sum_w — or 0 when the controller's status is not
+// OK, like the reference's callers fall back to zeros (examples/mppi4-non-liner-ukf.rs:80-86); FINAL_RANK_ROW: the
+// un-normalised pair goes to o.out_row (the warp of pair 1 also writes the header and pair 0).  write_info: this
+// warp also writes info/status (the warp of pair 1 in merger 0).  Returns the status.
+// kFastExp (FP32 kernels): the row scales use ex2.approx like the block's own weights do; the FP64 kernels call exp().
+// The rows are stored PAIR-MAJOR here (slot q of row r at rows + q * pair_stride + 2 r; q = 0: header (m, argmax),
+// q = 1: pair 0, q = j + 1: pair j): the rows a warp reads for one slot are consecutive 16-byte cells, i.e. coalesced
+// loads (row-major rows made every load of the warp touch 32 different 128-byte lines: 2.9 us for the 20 loads).
+template <bool kFastExp>
+static __device__ __forceinline__ int mppi_warp_merge(const double* rows, long long pair_stride, int n_rows, int H, int pair,
+                                                      double inv_lambda, int final_mode, const MergeOut& o, bool write_info) {
+    constexpr int RPL = kMergeFan / 32;  // rows per lane
+    const unsigned int full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    double2 hd[RPL], p0[RPL], p1[RPL], pv[RPL];
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) {
+        const int r = lane + 32 * i;
+        hd[i] = make_double2(-CUDART_INF, ll_as_double(-1ll));
+        p0[i] = p1[i] = pv[i] = make_double2(0.0, 0.0);
+        if (r < n_rows) {
+            const double* cell = rows + 2 * r;
+            hd[i] = __ldcg(reinterpret_cast<const double2*>(cell));
+            p0[i] = __ldcg(reinterpret_cast<const double2*>(cell + pair_stride));
+            p1[i] = __ldcg(reinterpret_cast<const double2*>(cell + 2 * pair_stride));
+            pv[i] = __ldcg(reinterpret_cast<const double2*>(cell + (long long)(pair + 1) * pair_stride));
+        }
+    }
+    // max over the rows, lowest sample index among equal maxima
+    double m = -CUDART_INF;
+    long long a = kNoArg;
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) {
+        const long long ai = double_as_ll(hd[i].y);
+        if (ai >= 0 && (hd[i].x > m || (hd[i].x == m && ai < a))) { m = hd[i].x; a = ai; }
+    }
+    if (o.ts != nullptr && lane == 0 && m > -1e300) o.ts[8] = globaltimer_ns();  // (diagnostics) headers have arrived
+    double wm;
+    long long wa;
+    warp_max_minidx(m, a, a != kNoArg, &wm, &wa);
+    const bool any = (wa != kNoArg);
+    if (o.ts != nullptr && lane == 0) o.ts[9] = globaltimer_ns();
+    // the lane's rows, scaled by exp((m_r - m)/lambda); rows without a finite cost get 0 (0 * NaN keeps their poison)
+    // (branch-free: the exps of a lane's rows are independent chains the scheduler interleaves; exp(-746) == 0 in f64, and
+    // a row without a finite cost has m_r = -inf, i.e. exactly the scale 0 that keeps 0 * NaN = NaN)
+    double fsc[RPL];
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) {
+        double arg = (hd[i].x - wm) * inv_lambda;
+        arg = (arg > -746.0) ? arg : -746.0;  // also catches -inf and NaN arguments
+        if constexpr (kFastExp) fsc[i] = (double)fast_exp_neg(arg);
+        else fsc[i] = exp(arg);
+    }
+    double s = 0.0, nf = 0.0, a0 = 0.0, ax = 0.0, ay = 0.0;
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) {
+        if (lane + 32 * i < n_rows) {
+            const double f = fsc[i];
+            s += f * p0[i].x;
+            nf += p0[i].y;
+            a0 += f * p1[i].x;
+            ax += f * pv[i].x;
+            ay += f * pv[i].y;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        s += __hiloint2double(__shfl_xor_sync(full, __double2hiint(s), off), __shfl_xor_sync(full, __double2loint(s), off));
+        nf += __hiloint2double(__shfl_xor_sync(full, __double2hiint(nf), off), __shfl_xor_sync(full, __double2loint(nf), off));
+        a0 += __hiloint2double(__shfl_xor_sync(full, __double2hiint(a0), off), __shfl_xor_sync(full, __double2loint(a0), off));
+        ax += __hiloint2double(__shfl_xor_sync(full, __double2hiint(ax), off), __shfl_xor_sync(full, __double2loint(ax), off));
+        ay += __hiloint2double(__shfl_xor_sync(full, __double2hiint(ay), off), __shfl_xor_sync(full, __double2loint(ay), off));
+    }
+    if (o.ts != nullptr && lane == 0 && s == s) o.ts[10] = globaltimer_ns();  // (diagnostics) sums reduced
+    if (final_mode == FINAL_RANK_ROW) {
+        if (lane == 0) {
+            for (int r = -1; r < o.n_copies; ++r) {
+                if (r == o.copy_skip) continue;
+                double* dst = (r < 0) ? o.out_row : o.copy_rows[r] + o.copy_offset;
+                if (pair == 1) {
+                    *reinterpret_cast<double2*>(dst) = make_double2(any ? wm : -CUDART_INF, ll_as_double(any ? wa : -1ll));
+                    *reinterpret_cast<double2*>(dst + 2) = make_double2(s, nf);
+                }
+                *reinterpret_cast<double2*>(dst + 2 + 2 * pair) = make_double2(ax, ay);
+            }
+        }
+        return MPCB_OK;
+    }
+    // src/mppi.rs:69 no finite cost, :76-78 sum is zero, :87-89 u[0] not finite (element 0 only)
+    int status = o.forced_status;
+    if (status == MPCB_OK) status = !any ? MPCB_NO_FINITE_COST : (s == 0.0 ? MPCB_SUM_ZERO : (!finite_f64(a0 / s) ? MPCB_U_INVALID : MPCB_OK));
+    if (lane == 0) {
+        const int t0 = 2 * pair - 2;
+        const double u0 = (status == MPCB_OK) ? ax / s : 0.0;
+        const double u1 = (status == MPCB_OK) ? ay / s : 0.0;
+        o.u_out[t0] = u0;
+        if (o.u_out_host) o.u_out_host[t0] = u0;
+        if (t0 + 1 < H) {
+            o.u_out[t0 + 1] = u1;
+            if (o.u_out_host) o.u_out_host[t0 + 1] = u1;
+        }
+        if (write_info) {
+            mpcb_mppi_info out;
+            out.status = status;
+            out.reserved = 0;
+            out.argmax = any ? wa : -1ll;
+            out.max = any ? wm : 0.0;
+            out.sum = s;
+            out.n_finite = (long long)nf;
+            *o.info = out;
+            if (o.info_host) *o.info_host = out;
+        }
+    }
+    return status;
+}
+
 // Combines the G (<= 32) rank rows of the cross-GPU exchange: same result as mppi_merge_rows, done by ONE warp with no
 // block barrier — lane r holds row r's header and (sum_w, n_finite), the scales are shuffled around, and lane jl sums
 // its column pair over the G rows.  Called by warp 0 of a merger block; mi/nm select the merger's column slice.
@@ -422,10 +584,11 @@ static __device__ __noinline__ void mppi_combine_ranks_warp(const double* rows, 
     int p_hi = p_lo + cp;
     if (p_hi > ncol2) p_hi = ncol2;
     const bool has = lane < G;
-    double2 hd = make_double2(-CUDART_INF, ll_as_double(-1ll)), p0 = make_double2(0.0, 0.0);
+    double2 hd = make_double2(-CUDART_INF, ll_as_double(-1ll)), p0 = make_double2(0.0, 0.0), p1 = make_double2(0.0, 0.0);
     if (has) {
         hd = __ldcg(reinterpret_cast<const double2*>(rows + (long long)lane * row_stride));
         p0 = __ldcg(reinterpret_cast<const double2*>(rows + (long long)lane * row_stride + 2));
+        p1 = __ldcg(reinterpret_cast<const double2*>(rows + (long long)lane * row_stride + 4));  // pair 1 holds u[0]
     }
     // max over the ranks, lowest sample index among equal maxima
     double m = hd.x, wm;
@@ -442,15 +605,19 @@ static __device__ __noinline__ void mppi_combine_ranks_warp(const double* rows, 
     const long long arg = any ? (long long)(((unsigned long long)mh << 32) | ml) : -1ll;
     const double sc = (!has || hd.x == -CUDART_INF) ? 0.0 : exp((hd.x - wm) * inv_lambda);
     // sum_w and n_finite in rank order (a serial chain over <= 32 shuffles keeps the order fixed)
-    double s = 0.0, nf = 0.0;
+    double s = 0.0, nf = 0.0, a0 = 0.0;
     for (int r = 0; r < G; ++r) {
         const double fr = __hiloint2double(__shfl_sync(full, __double2hiint(sc), r), __shfl_sync(full, __double2loint(sc), r));
         const double sr = __hiloint2double(__shfl_sync(full, __double2hiint(p0.x), r), __shfl_sync(full, __double2loint(p0.x), r));
         const double nr = __hiloint2double(__shfl_sync(full, __double2hiint(p0.y), r), __shfl_sync(full, __double2loint(p0.y), r));
+        const double ur = __hiloint2double(__shfl_sync(full, __double2hiint(p1.x), r), __shfl_sync(full, __double2loint(p1.x), r));
         s += fr * sr;  // scale 0 * NaN = NaN keeps the reference's poisoning
         nf += nr;
+        a0 += fr * ur;  // the same sum, in the same order, as the owner of pair 1 forms below: every merger sees the same u[0]
     }
-    int status = (o.forced_status != MPCB_OK) ? o.forced_status : (!any ? MPCB_NO_FINITE_COST : (s == 0.0 ? MPCB_SUM_ZERO : MPCB_OK));
+    // src/mppi.rs:69 no finite cost, :76-78 sum is zero, :87-89 u[0] not finite (element 0 only)
+    const int status = (o.forced_status != MPCB_OK) ? o.forced_status
+                       : (!any ? MPCB_NO_FINITE_COST : (s == 0.0 ? MPCB_SUM_ZERO : (!finite_f64(a0 / s) ? MPCB_U_INVALID : MPCB_OK)));
     const int npairs = p_hi > p_lo ? p_hi - p_lo : 0;
     for (int j0 = 0; j0 < npairs || j0 == 0; j0 += 32) {  // at least one pass so that the shuffles below are uniform
         const int j = j0 + lane;
@@ -478,15 +645,15 @@ static __device__ __noinline__ void mppi_combine_ranks_warp(const double* rows, 
         }
         if (live) {
             const int t0 = 2 * pair - 2;
-            const double u0 = any ? ax / s : 0.0;
-            const double u1 = any ? ay / s : 0.0;
+            // a controller whose status is not OK gets a zero row (examples/mppi4-non-liner-ukf.rs:80-86)
+            const double u0 = (status == MPCB_OK) ? ax / s : 0.0;
+            const double u1 = (status == MPCB_OK) ? ay / s : 0.0;
             o.u_out[t0] = u0;
             if (o.u_out_host) o.u_out_host[t0] = u0;
             if (t0 + 1 < H) {
                 o.u_out[t0 + 1] = u1;
                 if (o.u_out_host) o.u_out_host[t0 + 1] = u1;
             }
-            if (t0 == 0 && status == MPCB_OK && !finite_f64(u0)) status = MPCB_U_INVALID;  // src/mppi.rs:87-89
         }
         if (j0 + 32 >= npairs) break;
     }
@@ -544,21 +711,6 @@ struct ArithT<float, 2> {
     using type = f2;
 };
 
-// Warp max of v over the lanes with `has`, and the smallest idx among the lanes holding that max.
-__device__ __forceinline__ void warp_max_minidx(double v, long long idx, bool has, double* vmax, long long* imin) {
-    const unsigned int full = 0xffffffffu;
-    double wm;
-    long long wa;
-    int dummy;
-    warp_argmax(v, idx, has, &wm, &wa, &dummy);
-    const bool holds = has && v == wm;
-    const unsigned int ahi = holds ? (unsigned int)((unsigned long long)idx >> 32) : 0xffffffffu;
-    const unsigned int mh = __reduce_min_sync(full, ahi);
-    const unsigned int alo = (holds && ahi == mh) ? (unsigned int)idx : 0xffffffffu;
-    const unsigned int ml = __reduce_min_sync(full, alo);
-    *vmax = wm;
-    *imin = (wa == kNoArg) ? kNoArg : (long long)(((unsigned long long)mh << 32) | ml);
-}
 
 __host__ __device__ inline int mppi_pow2_horizon(int H, int* lg) {
     int hp = 8, l = 3;
@@ -593,14 +745,253 @@ __host__ __device__ inline size_t mppi_smem_bytes(int H, int block, bool vt = tr
     return (bytes + 15) & ~(size_t)15;
 }
 
-// w = exp(a) for the FP32 path: a <= 0 is computed in f64 by the caller; ex2.approx (2 ulp) on a*log2(e).
-// Underflows to exactly 0 below a ~ -87; the f64 reference would keep weights down to e^-745, all of which
-// are < 1e-37 of the block maximum.
-__device__ __forceinline__ float fast_exp_neg(double a) {
-    const float t = (float)(a * 1.4426950408889634074);
-    float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
-    return r;
+
+// The end of a block's work, shared by every rollout kernel: store the block's partial row
+// [m, argmax, sum_w, n_finite, sum_w*v[0..H)], count the block in, and — for the designated merger blocks (or the last
+// arriver) — merge the controller's rows and write u_out / info, the rank row, or run the cross-GPU exchange.
+// Called by the first BLOCK threads of the block (whole warps beyond them have exited); U_run[H] holds the block's
+// weighted sums (dead afterwards: the merge totals reuse it).
+template <int BLOCK, bool kFastExp>
+__device__ __forceinline__ void mppi_block_tail(const MppiParams& p, int c, int chunk, double m_run, long long arg_run, double S_run,
+                                                long long nfin_run, double* U_run, double* scratch, double* part_d) {
+    const int tid = threadIdx.x, wid = tid >> 5;
+    const int H = p.H;
+    const double lambda = p.lambda;
+    MPCB_TS(1);
+    // ---- partial row of this block, then the merge ----
+    // Arrival counters only ever grow (launch `seq` expects seq*rows arrivals), so nothing has to be reset and any
+    // number of blocks can wait on one counter.  With every block of the launch resident at once (p.mergers >= 1)
+    // the first block of a group merges the group and the first p.mergers blocks of the controller share the final
+    // merge column-wise — the same blocks, on the same SMs, every launch; otherwise (grids of several waves) the
+    // last block to arrive merges alone.
+    const int PL = p.PL;
+    const double inv_lambda_m = 1.0 / lambda;
+    double* tot_d = U_run;  // dead once the row is stored (the arrival barrier comes first): merge totals [<= (H+5)/2 double2]
+    double* ctrl_rows = p.partial + (long long)c * (p.chunks + p.groups) * PL;
+    double* my_row = ctrl_rows + (long long)chunk * PL;
+    // single-level merge by warps (below): the level-0 rows are stored pair-major, see mppi_warp_merge
+    const bool pair_major = (p.groups == 1 && p.mergers >= 1 && p.final_mode != FINAL_PEER_EXCHANGE);
+    const long long pair_stride = 2ll * p.chunks;
+    if (pair_major) {
+        for (int j = tid; j < (PL >> 1); j += BLOCK) {
+            double2 v;
+            if (j == 0) v = make_double2(m_run, ll_as_double(arg_run == kNoArg ? -1ll : arg_run));
+            else if (j == 1) v = make_double2(S_run, (double)nfin_run);
+            else v = make_double2(U_run[2 * j - 4], (2 * j - 3 < H) ? U_run[2 * j - 3] : 0.0);
+            *reinterpret_cast<double2*>(ctrl_rows + (long long)j * pair_stride + 2 * chunk) = v;
+        }
+    } else {
+        for (int t = tid; t < H; t += BLOCK) my_row[kPartialHdr + t] = U_run[t];
+        if (tid == 0) {
+            my_row[0] = m_run;
+            my_row[1] = ll_as_double(arg_run == kNoArg ? -1ll : arg_run);
+            my_row[2] = S_run;
+            my_row[3] = (double)nfin_run;
+            if (PL > kPartialHdr + H) my_row[kPartialHdr + H] = 0.0;
+        }
+    }
+    __shared__ int s_go;
+    unsigned int* cnt = p.counters + (long long)c * (p.groups + 1);
+    const int g = chunk / p.group_size;
+    const int g_first = g * p.group_size;
+    int g_rows = p.chunks - g_first;
+    if (g_rows > p.group_size) g_rows = p.group_size;
+    unsigned long long* dbg = (p.debug_ts != nullptr) ? p.debug_ts + (size_t)blockIdx.x * 16 : nullptr;
+    const bool spin = p.mergers >= 1;
+    const int nm = spin ? p.mergers : 1;
+
+    // publish this block's writes and count it in; in last-arriver mode returns whether it completed the count
+    auto arrive = [&](int slot, int expect) -> bool {
+        __syncthreads();
+        if (tid == 0) {
+            const bool drop = (p.ws_debug & 4) && slot == 0 && chunk == p.chunks - 1 && p.chunks > 1;  // fault injection (tests)
+            s_go = !drop && (atom_add_acq_rel_gpu_u32(&cnt[slot], 1u) + 1u == p.seq * (unsigned int)expect);
+        }
+        __syncthreads();
+        return s_go != 0;
+    };
+    // wait until `expect` blocks of this launch have arrived at `slot` (bounded, see MPCB_PEER_TIMEOUT)
+    // A wait that gives up (the launch is not co-resident: another context, MPS, a debugger) is recorded: the merge then
+    // reports MPCB_PEER_TIMEOUT and writes zeros instead of merging stale or half-written rows.
+    __shared__ int s_await_timeout;
+    if (tid == 0) s_await_timeout = 0;
+    auto await = [&](int slot, int expect) {
+        if (tid == 0) {
+            const unsigned int want = p.seq * (unsigned int)expect;
+            const unsigned long long t_start = globaltimer_ns();
+            while (ld_acquire_gpu_u32(&cnt[slot]) != want) {
+                if (globaltimer_ns() - t_start > 5000000000ull) { s_await_timeout = 1; break; }
+            }
+        }
+        __syncthreads();  // thread 0's acquire + this barrier order every thread's (L2) loads after the arrivals
+    };
+
+    int mi = 0;  // which column slice of the final merge this block takes
+    const double* final_rows = ctrl_rows;
+    int final_n = p.chunks;
+    MergeOut none;
+    none.u_out = nullptr; none.u_out_host = nullptr; none.info = nullptr; none.info_host = nullptr; none.out_row = nullptr;
+    none.copy_rows = nullptr; none.copy_offset = 0; none.n_copies = 0; none.copy_skip = -2;
+    none.done_host = nullptr; none.epoch = 0u; none.forced_status = MPCB_OK; none.ts = nullptr;
+    if (pair_major) {
+        // ---- single-level merge by warps, no block barrier after the arrival (mppi_warp_merge): merger block mi owns
+        // the column pairs [1 + mi*cp, 1 + (mi+1)*cp), one warp per pair; every warp waits for the arrivals itself ----
+        __syncthreads();  // the block's row stores before thread 0's release (cumulative)
+        // fault injection (tests): ws_debug & 4 makes the last block "never arrive", as if the launch were not co-resident
+        if (tid == 0 && !((p.ws_debug & 4) && chunk == p.chunks - 1 && p.chunks > 1)) red_add_release_gpu_u32(&cnt[0], 1u);
+        MPCB_TS(2);
+        if (chunk >= nm) return;
+        mi = chunk;
+        const int ncol2 = (H + 3) >> 1;
+        const int cp = (ncol2 - 1 + nm - 1) / nm;
+        const int p_lo = 1 + mi * cp;
+        int p_hi = p_lo + cp;
+        if (p_hi > ncol2) p_hi = ncol2;
+        MergeOut fo = none;
+        fo.u_out = p.u_out + (long long)c * H;
+        fo.u_out_host = p.u_out_host ? p.u_out_host + (long long)c * H : nullptr;
+        fo.info = p.info + c;
+        fo.info_host = p.info_host ? p.info_host + c : nullptr;
+        fo.out_row = p.rank_partial ? p.rank_partial + (long long)c * PL : nullptr;
+        if (wid < p_hi - p_lo || (wid == 0 && p.done_host)) {  // warps with a pair (warp 0 also signs off for the block)
+            const unsigned int want = p.seq * (unsigned int)p.chunks;
+            bool timed_out = false;
+            if ((tid & 31) == 0) {
+                // poll; the clock is read only every 64 polls (one poll is one L2 round trip)
+                unsigned long long t_start = 0;
+                for (unsigned int it = 0; ld_acquire_gpu_u32(&cnt[0]) != want; ++it) {
+                    if ((it & 63u) == 63u) {
+                        const unsigned long long now = globaltimer_ns();
+                        if (t_start == 0) t_start = now;
+                        else if (now - t_start > 5000000000ull) { timed_out = true; break; }
+                    }
+                }
+            }
+            timed_out = __shfl_sync(0xffffffffu, timed_out ? 1 : 0, 0) != 0;
+            __syncwarp();  // lane 0's acquire + the warp barrier order every lane's (L2) loads after the arrivals
+            // a launch that is not co-resident (another context on the GPU) must not merge half-written rows
+            fo.forced_status = timed_out ? MPCB_PEER_TIMEOUT : MPCB_OK;
+            if (dbg != nullptr && tid == 0) dbg[7] = globaltimer_ns();
+            fo.ts = (wid == 0) ? dbg : nullptr;
+            for (int pair = p_lo + wid; pair < p_hi; pair += BLOCK / 32)
+                mppi_warp_merge<kFastExp>(ctrl_rows, pair_stride, p.chunks, H, pair, inv_lambda_m, p.final_mode, fo, mi == 0 && pair == 1);
+            if (p.final_mode == FINAL_RANK_ROW && mi == 0 && tid == 0 && PL > kPartialHdr + H) fo.out_row[kPartialHdr + H] = 0.0;
+            if (dbg != nullptr && tid == 0) dbg[11] = globaltimer_ns();
+        }
+        if (p.done_host && p.final_mode == FINAL_NORMALISE) {
+            // results of every warp of this merger first, then its completion word the host spins on
+            __threadfence_system();
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned int*>(p.done_host + mi) = p.epoch;
+            }
+        }
+        MPCB_TS(5);
+        return;
+    }
+    if (p.groups == 1) {
+        const bool last = arrive(0, p.chunks);
+        MPCB_TS(2);
+        if (spin) {
+            if (chunk >= nm) return;
+            mi = chunk;
+            await(0, p.chunks);
+        } else {
+            if (!last) return;
+        }
+    } else {
+        double* group_rows = ctrl_rows + (long long)p.chunks * PL;
+        const bool last = arrive(g, g_rows);
+        MPCB_TS(2);
+        const bool leader = spin ? (chunk == g_first) : last;
+        const bool merger = spin && chunk < nm;
+        if (!leader && !merger) return;
+        if (leader) {
+            if (spin) await(g, g_rows);
+            MergeOut go = none;
+            go.out_row = group_rows + (long long)g * PL;
+            mppi_merge_rows<BLOCK>(ctrl_rows + (long long)g_first * PL, PL, g_rows, H, 0, 1, inv_lambda_m, FINAL_RANK_ROW, go,
+                                   scratch, part_d, tot_d);
+            if (tid == 0 && PL > kPartialHdr + H) go.out_row[kPartialHdr + H] = 0.0;
+            if (tid == 0 && s_await_timeout) go.out_row[2] = CUDART_NAN;  // a group merged from incomplete rows poisons the result
+            MPCB_TS(3);
+            const bool last2 = arrive(p.groups, p.groups);
+            if (!spin && !last2) return;
+        }
+        if (spin) {
+            if (!merger) return;
+            mi = chunk;
+            await(p.groups, p.groups);
+        }
+        MPCB_TS(4);
+        final_rows = group_rows;
+        final_n = p.groups;
+    }
+    // ---- final merge of this controller (this block's column slice mi of nm) ----
+    MergeOut fo = none;
+    fo.u_out = p.u_out + (long long)c * H;
+    fo.u_out_host = p.u_out_host ? p.u_out_host + (long long)c * H : nullptr;
+    fo.info = p.info + c;
+    fo.info_host = p.info_host ? p.info_host + c : nullptr;
+    fo.done_host = p.done_host;
+    fo.epoch = p.epoch;
+    if (s_await_timeout) fo.forced_status = MPCB_PEER_TIMEOUT;
+    if (p.final_mode != FINAL_PEER_EXCHANGE) {
+        fo.out_row = p.rank_partial ? p.rank_partial + (long long)c * PL : nullptr;
+        fo.ts = (p.groups == 1 && mi == 0) ? dbg : nullptr;
+        mppi_merge_rows<BLOCK>(final_rows, PL, final_n, H, mi, nm, inv_lambda_m, p.final_mode, fo, scratch, part_d, tot_d);
+        if (p.final_mode == FINAL_RANK_ROW && mi == 0 && tid == 0 && PL > kPartialHdr + H) fo.out_row[kPartialHdr + H] = 0.0;
+        MPCB_TS(5);
+        return;
+    }
+    // ---- cross-GPU exchange inside the kernel (SURVEY.md 8e): merger mi puts its column slice of this rank's merged
+    // row into every rank's mailbox slot [parity][rank][c] (peer stores over NVLink) and releases its flag
+    // [parity][rank][c][mi] on every peer; it then acquires, for every rank, that rank's flag mi (its own slice)
+    // and flag 0 (the slice holding m, argmax, sum_w, n) and combines the G rows exactly like the rows of one GPU.
+    // Slots alternate with the exchange epoch: a peer can only be one step ahead, so two slots never collide. ----
+    {
+        const int G = p.G;
+        const unsigned int par = p.xepoch & 1u;
+        const long long slot_self = ((long long)(par * G + p.rank) * p.C + c);
+        double* own_box = p.peer_mbox[p.rank];
+        MergeOut ro = none;
+        ro.out_row = own_box + slot_self * PL;
+        ro.copy_rows = p.peer_mbox;
+        ro.copy_offset = slot_self * PL;
+        ro.n_copies = G;
+        ro.copy_skip = p.rank;
+        MPCB_TS(12);
+        mppi_merge_rows<BLOCK>(final_rows, PL, final_n, H, mi, nm, inv_lambda_m, FINAL_RANK_ROW, ro, scratch, part_d, tot_d);
+        MPCB_TS(13);
+        // the stores of the whole block come before the barrier, thread r's system-scope release after it (cumulative)
+        __syncthreads();
+        for (int r = tid; r < G; r += BLOCK) st_release_sys_u32(p.peer_flags[r] + slot_self * kMaxMergers + mi, p.xepoch);
+        // wait for every rank's slices of this step (bounded: a missing peer becomes MPCB_PEER_TIMEOUT, not a hang)
+        __shared__ int s_timeout;
+        if (tid == 0) s_timeout = 0;
+        __syncthreads();
+        MPCB_TS(14);
+        for (int r = tid; r < 2 * G; r += BLOCK) {
+            const int src = r >> 1, which = (r & 1) ? mi : 0;
+            const unsigned int* f = p.peer_flags[p.rank] + ((long long)(par * G + src) * p.C + c) * kMaxMergers + which;
+            const unsigned long long t_start = globaltimer_ns();
+            while (ld_acquire_sys_u32(f) != p.xepoch) {
+                if (globaltimer_ns() - t_start > 20000000000ull) { s_timeout = 1; break; }
+            }
+        }
+        __syncthreads();
+        MPCB_TS(15);
+        fo.forced_status = (s_timeout || s_await_timeout) ? MPCB_PEER_TIMEOUT : MPCB_OK;
+        const double* rank_rows = own_box + (long long)(par * G) * p.C * PL + (long long)c * PL;
+        if (G <= 32) {
+            if (wid == 0) mppi_combine_ranks_warp(rank_rows, (long long)p.C * PL, G, H, mi, nm, inv_lambda_m, fo);
+        } else {
+            mppi_merge_rows<BLOCK>(rank_rows, (long long)p.C * PL, G, H, mi, nm, inv_lambda_m, FINAL_NORMALISE, fo, scratch,
+                                   part_d, tot_d);
+        }
+        MPCB_TS(5);
+    }
 }
 
 // SPT = samples per thread.  SPT = 2 (FP32 only) packs the two samples' FP32 arithmetic into f32x2 instructions
@@ -649,23 +1040,39 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
     static_assert(S >= 1 && S <= kMaxStateDim, "state dimension out of range");
     static_assert(SPT == 1 || S == 4, "the packed kernels are written for the built-in four-state models");
     real x0[S];
+    // FP32 path: a NaN in x or u_n reaches every sample's cost in the reference (src/mppi.rs:53-61) and must poison the
+    // step; a NaN cost that FP32 overflow produced from clean inputs must not (see the weights below)
+    __shared__ int s_in_nan;
+    if (tid == 0) s_in_nan = 0;
+    __syncthreads();
+    bool in_bad = false;
     if (p.use_inline) {
 #pragma unroll
-        for (int i = 0; i < S; ++i) x0[i] = (real)p.xu_inline[i];
+        for (int i = 0; i < S; ++i) {
+            x0[i] = (real)p.xu_inline[i];
+            in_bad = in_bad || (p.xu_inline[i] != p.xu_inline[i]);
+        }
         for (int t = tid; t < H; t += BLOCK) {
             const double ut = p.xu_inline[S + t];
+            in_bad = in_bad || (ut != ut);
             su[t] = (real)ut;
             sui[t] = (real)(ut * p.inv_var);
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < S; ++i) x0[i] = (real)p.x[(long long)c * S + i];
+        for (int i = 0; i < S; ++i) {
+            const double xi = p.x[(long long)c * S + i];
+            x0[i] = (real)xi;
+            in_bad = in_bad || (xi != xi);
+        }
         for (int t = tid; t < H; t += BLOCK) {
             const double ut = p.u[(long long)c * H + t];
+            in_bad = in_bad || (ut != ut);
             su[t] = (real)ut;
             sui[t] = (real)(ut * p.inv_var);
         }
     }
+    if (in_bad) s_in_nan = 1;
     for (int t = tid; t < H; t += BLOCK) U_run[t] = 0.0;
     const real lo = (real)p.lo, hi = (real)p.hi;
     const float neg2s2ln2 = (float)(-2.0 * p.std_dev * p.std_dev * 0.693147180559945309417);
@@ -716,8 +1123,9 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
         }
 
         double ck[SPT];
+        bool eps_nan[SPT];
 #pragma unroll
-        for (int s = 0; s < SPT; ++s) ck[s] = -CUDART_INF;
+        for (int s = 0; s < SPT; ++s) { ck[s] = -CUDART_INF; eps_nan[s] = false; }
         if (live[0]) {  // live[1] implies live[0]
             // ---- PASS 1+2: noise, clamp, rollout, cost ----
             real* vcol = v_s + tid;
@@ -725,7 +1133,10 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
             auto draw4 = [&](int s, int t0, real(&e)[4]) {
                 if constexpr (kReplay && VT) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) e[i] = (valid[s] && t0 + i < H) ? vcol[(t0 + i) * LD + s * BLOCK] : (real)0;
+                    for (int i = 0; i < 4; ++i) {
+                        e[i] = (valid[s] && t0 + i < H) ? vcol[(t0 + i) * LD + s * BLOCK] : (real)0;
+                        eps_nan[s] = eps_nan[s] || (e[i] != e[i]);
+                    }
                 } else if constexpr (kReplay) {
                     // no tile: the thread reads its own row of the caller's noise (verification mode)
                     const long long row = ((long long)c * p.K_global + kg[s]) * H;
@@ -735,11 +1146,12 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
                         if (valid[s] && t0 + i < H)
                             e[i] = p.eps_f64 ? (real) reinterpret_cast<const double*>(p.eps)[row + t0 + i]
                                              : (real) reinterpret_cast<const float*>(p.eps)[row + t0 + i];
+                        eps_nan[s] = eps_nan[s] || (e[i] != e[i]);
                     }
                 } else {
                     const unsigned int c0 = (unsigned int)(kg[s] & 0xffffffffll);
                     const unsigned int khi = (unsigned int)((kg[s] >> 32) & 0xffff) << 16;
-                    const Philox4 r = philox4x32_10(c0, p.call_idx, (unsigned int)c, (unsigned int)(t0 >> 2) | khi,
+                    const Philox4 r = philox4x32(c0, p.call_idx, (unsigned int)c, (unsigned int)(t0 >> 2) | khi,
                                                     p.seed_lo, p.seed_hi);
                     float z[4];
                     philox_normal4(r, neg2s2ln2, z);
@@ -872,6 +1284,13 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
 #pragma unroll
             for (int s = 0; s < SPT; ++s) {
                 ck[s] = -J[s] - CT[s];  // :61
+                if constexpr (!kExact) {
+                    // FP32 rollouts overflow (inf, then inf - inf = NaN) where the f64 reference still holds a huge finite
+                    // cost whose weight underflows to exactly 0: with clean inputs a NaN cost is that case -> -inf, weight 0.
+                    // A NaN that came in through x, u_n or the sample's replay noise poisons the sums like the reference.
+                    if (s_in_nan != 0 || eps_nan[s]) ck[s] = CUDART_NAN;
+                    else if (ck[s] != ck[s]) ck[s] = -CUDART_INF;
+                }
                 if (p.costs != nullptr && valid[s]) p.costs[(long long)c * p.K_local + kl[s]] = ck[s];
             }
         }
@@ -918,9 +1337,11 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
                 if (!valid[s] || ck[s] == -CUDART_INF) w = 0.0;
                 else w = (arg < -746.0) ? 0.0 : exp(arg);
             } else {
-                // FP32 rollouts can overflow where the f64 reference yields a huge finite cost whose weight
-                // underflows to exactly 0: non-finite costs get weight 0 here.
-                w = fin[s] ? fast_exp_neg((ck[s] - m_run) * inv_lambda) : 0.0f;
+                // natural IEEE semantics like the reference (src/mppi.rs:71-74): -inf -> 0, NaN / +inf poison the sums
+                // (FP32-overflow NaNs were turned into -inf above)
+                if (!valid[s] || ck[s] == -CUDART_INF) w = 0.0f;
+                else if (m_run == -CUDART_INF) w = (float)(ck[s] - ck[s]);  // no finite cost yet: NaN / +inf still poison
+                else w = fast_exp_neg((ck[s] - m_run) * inv_lambda);
             }
             w_s[s * BLOCK + tid] = w;
             wsum += w;
@@ -1010,7 +1431,7 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
                     } else {
                         const unsigned int c0 = (unsigned int)(kgk & 0xffffffffll);
                         const unsigned int khi = (unsigned int)((kgk >> 32) & 0xffff) << 16;
-                        const Philox4 r = philox4x32_10(c0, p.call_idx, (unsigned int)c, (unsigned int)j | khi, p.seed_lo, p.seed_hi);
+                        const Philox4 r = philox4x32(c0, p.call_idx, (unsigned int)c, (unsigned int)j | khi, p.seed_lo, p.seed_hi);
                         float z[4];
                         philox_normal4(r, neg2s2ln2, z);
 #pragma unroll
@@ -1037,162 +1458,7 @@ __global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_consta
         }
     }
 
-    MPCB_TS(1);
-    // ---- partial row of this block, then the merge ----
-    // Arrival counters only ever grow (launch `seq` expects seq*rows arrivals), so nothing has to be reset and any
-    // number of blocks can wait on one counter.  With every block of the launch resident at once (p.mergers >= 1)
-    // the first block of a group merges the group and the first p.mergers blocks of the controller share the final
-    // merge column-wise — the same blocks, on the same SMs, every launch; otherwise (grids of several waves) the
-    // last block to arrive merges alone.
-    const int PL = p.PL;
-    const double inv_lambda_m = 1.0 / lambda;
-    double* tot_d = U_run;  // dead once the row is stored (the arrival barrier comes first): merge totals [<= (H+5)/2 double2]
-    double* ctrl_rows = p.partial + (long long)c * (p.chunks + p.groups) * PL;
-    double* my_row = ctrl_rows + (long long)chunk * PL;
-    for (int t = tid; t < H; t += BLOCK) my_row[kPartialHdr + t] = U_run[t];
-    if (tid == 0) {
-        my_row[0] = m_run;
-        my_row[1] = ll_as_double(arg_run == kNoArg ? -1ll : arg_run);
-        my_row[2] = S_run;
-        my_row[3] = (double)nfin_run;
-        if (PL > kPartialHdr + H) my_row[kPartialHdr + H] = 0.0;
-    }
-    __shared__ int s_go;
-    unsigned int* cnt = p.counters + (long long)c * (p.groups + 1);
-    const int g = chunk / p.group_size;
-    const int g_first = g * p.group_size;
-    int g_rows = p.chunks - g_first;
-    if (g_rows > p.group_size) g_rows = p.group_size;
-    unsigned long long* dbg = (p.debug_ts != nullptr) ? p.debug_ts + (size_t)blockIdx.x * 16 : nullptr;
-    const bool spin = p.mergers >= 1;
-    const int nm = spin ? p.mergers : 1;
-
-    // publish this block's writes and count it in; in last-arriver mode returns whether it completed the count
-    auto arrive = [&](int slot, int expect) -> bool {
-        __syncthreads();
-        if (tid == 0) s_go = (atom_add_acq_rel_gpu_u32(&cnt[slot], 1u) + 1u == p.seq * (unsigned int)expect);
-        __syncthreads();
-        return s_go != 0;
-    };
-    // wait until `expect` blocks of this launch have arrived at `slot` (bounded, see MPCB_PEER_TIMEOUT)
-    auto await = [&](int slot, int expect) {
-        if (tid == 0) {
-            const unsigned int want = p.seq * (unsigned int)expect;
-            const unsigned long long t_start = globaltimer_ns();
-            while (ld_acquire_gpu_u32(&cnt[slot]) != want) {
-                if (globaltimer_ns() - t_start > 5000000000ull) break;
-            }
-        }
-        __syncthreads();  // thread 0's acquire + this barrier order every thread's (L2) loads after the arrivals
-    };
-
-    int mi = 0;  // which column slice of the final merge this block takes
-    const double* final_rows = ctrl_rows;
-    int final_n = p.chunks;
-    MergeOut none;
-    none.u_out = nullptr; none.u_out_host = nullptr; none.info = nullptr; none.info_host = nullptr; none.out_row = nullptr;
-    none.copy_rows = nullptr; none.copy_offset = 0; none.n_copies = 0; none.copy_skip = -2;
-    none.done_host = nullptr; none.epoch = 0u; none.forced_status = MPCB_OK; none.ts = nullptr;
-    if (p.groups == 1) {
-        const bool last = arrive(0, p.chunks);
-        MPCB_TS(2);
-        if (spin) {
-            if (chunk >= nm) return;
-            mi = chunk;
-            await(0, p.chunks);
-        } else {
-            if (!last) return;
-        }
-    } else {
-        double* group_rows = ctrl_rows + (long long)p.chunks * PL;
-        const bool last = arrive(g, g_rows);
-        MPCB_TS(2);
-        const bool leader = spin ? (chunk == g_first) : last;
-        const bool merger = spin && chunk < nm;
-        if (!leader && !merger) return;
-        if (leader) {
-            if (spin) await(g, g_rows);
-            MergeOut go = none;
-            go.out_row = group_rows + (long long)g * PL;
-            mppi_merge_rows<BLOCK>(ctrl_rows + (long long)g_first * PL, PL, g_rows, H, 0, 1, inv_lambda_m, FINAL_RANK_ROW, go,
-                                   scratch, part_d, tot_d);
-            if (tid == 0 && PL > kPartialHdr + H) go.out_row[kPartialHdr + H] = 0.0;
-            MPCB_TS(3);
-            const bool last2 = arrive(p.groups, p.groups);
-            if (!spin && !last2) return;
-        }
-        if (spin) {
-            if (!merger) return;
-            mi = chunk;
-            await(p.groups, p.groups);
-        }
-        MPCB_TS(4);
-        final_rows = group_rows;
-        final_n = p.groups;
-    }
-    // ---- final merge of this controller (this block's column slice mi of nm) ----
-    MergeOut fo = none;
-    fo.u_out = p.u_out + (long long)c * H;
-    fo.u_out_host = p.u_out_host ? p.u_out_host + (long long)c * H : nullptr;
-    fo.info = p.info + c;
-    fo.info_host = p.info_host ? p.info_host + c : nullptr;
-    fo.done_host = p.done_host;
-    fo.epoch = p.epoch;
-    if (p.final_mode != FINAL_PEER_EXCHANGE) {
-        fo.out_row = p.rank_partial ? p.rank_partial + (long long)c * PL : nullptr;
-        fo.ts = (p.groups == 1 && mi == 0) ? dbg : nullptr;
-        mppi_merge_rows<BLOCK>(final_rows, PL, final_n, H, mi, nm, inv_lambda_m, p.final_mode, fo, scratch, part_d, tot_d);
-        if (p.final_mode == FINAL_RANK_ROW && mi == 0 && tid == 0 && PL > kPartialHdr + H) fo.out_row[kPartialHdr + H] = 0.0;
-        MPCB_TS(5);
-        return;
-    }
-    // ---- cross-GPU exchange inside the kernel (SURVEY.md 8e): merger mi puts its column slice of this rank's merged
-    // row into every rank's mailbox slot [parity][rank][c] (peer stores over NVLink) and releases its flag
-    // [parity][rank][c][mi] on every peer; it then acquires, for every rank, that rank's flag mi (its own slice)
-    // and flag 0 (the slice holding m, argmax, sum_w, n) and combines the G rows exactly like the rows of one GPU.
-    // Slots alternate with the exchange epoch: a peer can only be one step ahead, so two slots never collide. ----
-    {
-        const int G = p.G;
-        const unsigned int par = p.xepoch & 1u;
-        const long long slot_self = ((long long)(par * G + p.rank) * p.C + c);
-        double* own_box = p.peer_mbox[p.rank];
-        MergeOut ro = none;
-        ro.out_row = own_box + slot_self * PL;
-        ro.copy_rows = p.peer_mbox;
-        ro.copy_offset = slot_self * PL;
-        ro.n_copies = G;
-        ro.copy_skip = p.rank;
-        MPCB_TS(12);
-        mppi_merge_rows<BLOCK>(final_rows, PL, final_n, H, mi, nm, inv_lambda_m, FINAL_RANK_ROW, ro, scratch, part_d, tot_d);
-        MPCB_TS(13);
-        // the stores of the whole block come before the barrier, thread r's system-scope release after it (cumulative)
-        __syncthreads();
-        for (int r = tid; r < G; r += BLOCK) st_release_sys_u32(p.peer_flags[r] + slot_self * kMaxMergers + mi, p.xepoch);
-        // wait for every rank's slices of this step (bounded: a missing peer becomes MPCB_PEER_TIMEOUT, not a hang)
-        __shared__ int s_timeout;
-        if (tid == 0) s_timeout = 0;
-        __syncthreads();
-        MPCB_TS(14);
-        for (int r = tid; r < 2 * G; r += BLOCK) {
-            const int src = r >> 1, which = (r & 1) ? mi : 0;
-            const unsigned int* f = p.peer_flags[p.rank] + ((long long)(par * G + src) * p.C + c) * kMaxMergers + which;
-            const unsigned long long t_start = globaltimer_ns();
-            while (ld_acquire_sys_u32(f) != p.xepoch) {
-                if (globaltimer_ns() - t_start > 20000000000ull) { s_timeout = 1; break; }
-            }
-        }
-        __syncthreads();
-        MPCB_TS(15);
-        fo.forced_status = s_timeout ? MPCB_PEER_TIMEOUT : MPCB_OK;
-        const double* rank_rows = own_box + (long long)(par * G) * p.C * PL + (long long)c * PL;
-        if (G <= 32) {
-            if (wid == 0) mppi_combine_ranks_warp(rank_rows, (long long)p.C * PL, G, H, mi, nm, inv_lambda_m, fo);
-        } else {
-            mppi_merge_rows<BLOCK>(rank_rows, (long long)p.C * PL, G, H, mi, nm, inv_lambda_m, FINAL_NORMALISE, fo, scratch,
-                                   part_d, tot_d);
-        }
-        MPCB_TS(5);
-    }
+    mppi_block_tail<BLOCK, !kExact>(p, c, chunk, m_run, arg_run, S_run, nfin_run, U_run, scratch, part_d);
 }
 
 // Cross-rank merge: rows[g][c][PL] gathered from all ranks -> u_out / info.  One block per controller.

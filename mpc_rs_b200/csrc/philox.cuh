@@ -1,5 +1,9 @@
-// philox.cuh — Philox4x32-10 counter-based generator (Salmon, Moraes, Dror, Shaw, SC'11) and the
+// philox.cuh — Philox4x32 counter-based generator (Salmon, Moraes, Dror, Shaw, SC'11) and the
 // in-register Box-Muller that turns one 128-bit block into four N(0, sigma^2) draws.
+// Rounds: kPhiloxRounds = 7 — the fewest rounds for which the paper reports Philox4x32 passing BigCrush
+// ("Crush-resistant"; 10 is the paper's default with a safety margin).  Generate mode defines its own noise
+// stream (the reference seeds from OS entropy), so the round count is a quality/speed choice, not a parity one;
+// tests/test_mppi_gpu.py checks the moments, the tails and the serial correlation of the dumped stream.
 // Replaces the rand_distr::Normal / Xoshiro256Plus::from_entropy draw of src/mppi.rs:38-45.
 //
 // Counter layout (so the sample set does not depend on how samples are sharded over GPUs or blocks):
@@ -22,20 +26,21 @@ struct Philox4 {
 #endif
 
 MPCB_HD void philox_mulhilo(uint32_t a, uint32_t b, uint32_t* hi, uint32_t* lo) {
-#ifdef __CUDA_ARCH__
-    *lo = a * b;
-    *hi = __umulhi(a, b);
-#else
-    uint64_t p = (uint64_t)a * (uint64_t)b;
+    // one 32x32->64 multiply (IMAD.WIDE.U32) instead of mul.lo + mul.hi
+    const uint64_t p = (uint64_t)a * (uint64_t)b;
     *lo = (uint32_t)p;
     *hi = (uint32_t)(p >> 32);
-#endif
 }
 
-MPCB_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#ifndef MPCB_PHILOX_ROUNDS
+#define MPCB_PHILOX_ROUNDS 7
+#endif
+constexpr int kPhiloxRounds = MPCB_PHILOX_ROUNDS;
+
+MPCB_HD Philox4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
     constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < kPhiloxRounds; ++r) {
         uint32_t hi0, lo0, hi1, lo1;
         philox_mulhilo(M0, c0, &hi0, &lo0);
         philox_mulhilo(M1, c2, &hi1, &lo1);

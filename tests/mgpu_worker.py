@@ -74,7 +74,7 @@ def main():
                     err = np.linalg.norm(ug - us) / np.linalg.norm(us)
                     # same samples, different block boundaries: f64 differs by summation order only, f32 by the
                     # block-local float weighted sums
-                    assert err < (1e-12 if prec == "f64" else 2e-6), f"[{tr}/{prec}] sharded vs single-GPU generate: {err}"
+                    assert err < (1e-12 if prec == "f64" else 1e-5), f"[{tr}/{prec}] sharded vs single-GPU generate: {err}"
                     assert m.last_call_info()[0]["argmax"] == single.last_call_info()[0]["argmax"]
                     gather_equal(ug, f"[{tr}/{prec}] generate")
                 # device-resident closed loop (what bench.py times)

@@ -8,9 +8,9 @@ cd "$(dirname "$0")/../mpc_rs_b200/csrc"
 make -j8 >/dev/null
 mkdir -p /tmp/mpcb_var_$name
 for f in mppi_f32_NL mppi_f32x2_NL; do
-  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -ccbin g++ -Xcompiler -fPIC "$@" -c $f.cu -o /tmp/mpcb_var_$name/$f.o &
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -ccbin g++ --cudart shared -Xcompiler -fPIC "$@" -c $f.cu -o /tmp/mpcb_var_$name/$f.o &
 done
 wait
 objs=$(ls *.o | grep -v '^mppi_f32_NL.o$' | grep -v '^mppi_f32x2_NL.o$')
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../libmpc_b200_$name.so $objs /tmp/mpcb_var_$name/mppi_f32_NL.o /tmp/mpcb_var_$name/mppi_f32x2_NL.o -lcudart -ldl
+nvcc -gencode arch=compute_100a,code=sm_100a --cudart shared -shared -o ../libmpc_b200_$name.so $objs /tmp/mpcb_var_$name/mppi_f32_NL.o /tmp/mpcb_var_$name/mppi_f32x2_NL.o -ldl
 echo built ../libmpc_b200_$name.so

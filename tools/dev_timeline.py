@@ -29,8 +29,9 @@ ts = buf[:n].astype(np.int64)
 t0 = ts[:, 0].min()
 rel = np.where(ts > 0, ts - t0, -1)
 print(f"K={K} H={H} blocks={n}")
-names = ["start", "rollouts done", "ticket1", "group merged | final: headers done", "ticket2 | final: columns done", "final done"]
+names = ["start", "rollouts done", "ticket1", "group merged | ws: weights done", "ticket2 | ws: weighted sums done", "final done"]
 names += ["", "m: entry", "m: loads issued", "m: after barrier 1 (warp argmax)", "m: tid0 accumulated", "m: outputs stored"]
+names += ["ws: producer warp 0 done", "ws: block max known", "ws: consumer warp 0 done", "ws: last consumer warp done"]
 for i, nm in enumerate(names):
     if not nm:
         continue

@@ -25,3 +25,15 @@ double mpcb_e2e_loop(mpcb_mppi* h, const double* x, double* u, double* out, int 
     clock_gettime(CLOCK_MONOTONIC, &b);
     return (double)(b.tv_sec - a.tv_sec) + 1e-9 * (double)(b.tv_nsec - a.tv_nsec);
 }
+
+/* Device-resident closed loop: n back-to-back control steps enqueued from compiled code (ping-pong u buffers on the
+ * device: u_out of step i is u_in of step i + 1).  bench.py brackets this call with CUDA events on the handle's stream
+ * to get the kernel's launch-to-launch duration: a Python loop over the same call spends ~30 us per step in the
+ * interpreter, which is as long as the kernel itself.  Returns the first failing status, or MPCB_OK. */
+int mpcb_device_loop(mpcb_mppi* h, const double* d_x, double* d_u0, double* d_u1, int n) {
+    for (int i = 0; i < n; ++i) {
+        const mpcb_status st = mpcb_mppi_compute_device(h, d_x, (i & 1) ? d_u1 : d_u0, NULL, MPCB_DT_F32, (i & 1) ? d_u0 : d_u1);
+        if (st != MPCB_OK) return (int)st;
+    }
+    return 0;
+}
