@@ -68,7 +68,7 @@ def workload(n_gpus: int) -> dict:
         "workload": "BASELINE configs[1]: examples/mppi4-non-liner.rs MPPI, model NL, "
                     f"K={K_PER_GPU} samples/GPU x H={H}, DT={DT}, lambda={LAMBDA}, sigma={SIGMA}, limit=+-20",
         "samples_per_gpu": K_PER_GPU, "samples_total": K_PER_GPU * n_gpus, "horizon": H, "controllers": 1,
-        "noise": "philox4x32-10 in-register (generate mode)", "precision": "f32 rollout, f64 accumulation/softmax",
+        "noise": "philox4x32-7 in-register (generate mode)", "precision": "f32 rollout, f64 accumulation/softmax",
         "sharding": f"samples x{n_gpus}, {exchange}" if n_gpus > 1 else "none",
         "l2": "flushed between timed steps (256 MiB write); inputs are O(H) bytes",
     }

@@ -26,7 +26,7 @@ struct mpcb_mppi {
     int Hp = 8, lgHp = 3;
     int spt = 1;            // samples per thread (2: packed f32x2 kernels)
     int ws_variant = -1;    // >= 0: warp-specialised kernel, index into kWsVariants (mppi_ws_kernel.cuh)
-    int ws_cq = 2;          // its producer->consumer chunk, in 4-step groups
+    int ws_cq = 5;          // its producer->consumer chunk, in 4-step groups (20 steps: measured best of 1/2/5)
     int ws_debug = 0;       // MPCB_MPPI_WS_DEBUG: 1 = producers idle, 2 = consumers idle (timing decomposition only)
     int block_samples = 0;  // samples per block and batch = block * spt
     int mergers = 0;        // blocks sharing the final merge (0: last arriver merges alone)
@@ -274,12 +274,11 @@ mpcb_status pick_kernels(mpcb_mppi* h) {
         if (want >= 0) {
             if (ws_fits(want)) pick = want;
         } else if (want == -2) {
-            for (int v : {6, 0, 4}) {  // 8 / 14 / 16 sample-warps per batch, scalar consumers
-                if (wpc <= kWsVariants[v].ncw * kWsVariants[v].spt && ws_fits(v)) {
-                    pick = v;
-                    break;
-                }
-            }
+            // Measured on B200 (tools/dev_events.py, model NL, H = 100): with 13-14 sample-warps per SM the packed
+            // consumers + producer queue (variant 1: 7 + 9 warps) beat the one-thread-per-sample kernels by ~1.2 us per
+            // step; with fewer sample-warps per SM the consumer warps are half empty and the fused kernels win, with
+            // 15-16 both tie.  Several batches per block (large K) stay with the fused kernels too.
+            if ((wpc == 13 || wpc == 14) && h->C == 1 && ws_fits(1)) pick = 1;
         }
         if (pick >= 0) {
             const MppiWsVariant& wv = kWsVariants[pick];

@@ -1002,7 +1002,7 @@ __device__ __forceinline__ void mppi_block_tail(const MppiParams& p, int c, int 
 // of shared memory per resident sample, which is what limits the occupancy of long horizons (H = 200: 2 blocks of
 // 128 per SM) — the multi-batch shapes use it, so that the packed kernels keep >= 8 warps per SM at any horizon.
 template <template <typename> class ModelT, typename real, int BLOCK, int NOISE, int SPT, bool VT>
-__global__ void __launch_bounds__(BLOCK) mppi_rollout_kernel(const __grid_constant__ MppiParams p) {
+__global__ void __launch_bounds__(BLOCK, (512 / BLOCK > 0 ? 512 / BLOCK : 1)) mppi_rollout_kernel(const __grid_constant__ MppiParams p) {
     static_assert(SPT == 1 || (SPT == 2 && sizeof(real) == 4), "two samples per thread is an FP32 layout");
     constexpr int NW = BLOCK / 32;
     constexpr int SB = BLOCK * SPT;  // samples per batch

@@ -91,6 +91,7 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) mppi_ws_kernel(const __gr
     extern __shared__ __align__(32) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long full_bar[kWsMaxChunks];
     __shared__ int s_poison;
+    __shared__ unsigned int nz_s[32];  // per sample-warp of the batch: which samples have a non-zero weight
     __shared__ int s_next;  // producers' work queue: next item (chunk-major: all unit-warps of chunk 0, then chunk 1, ...)
 
     const int H = p.H;
@@ -416,6 +417,9 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) mppi_ws_kernel(const __gr
                 else w = fast_exp_neg((cv - m_run) * inv_lambda);
                 w_s[k] = w;
                 wsum += w;
+                // which samples of this sample-warp carry weight (NaN counts): PASS 6 walks the set bits only
+                const unsigned int nz = __ballot_sync(0xffffffffu, w != 0.0f);
+                if (lane == 0) nz_s[k >> 5] = nz;
             }
             const double wd = warp_sum_f64((double)wsum);
             if (lane == 0) red_s[wid] = wd;
@@ -430,10 +434,10 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) mppi_ws_kernel(const __gr
 
         // ---- PASS 6: sum_k w_k v[k][t].  Thread item (row, q): one tile row — four steps of every sample (SPT = 1) or two
         // steps of every sample pair (SPT = 2) — over the unit partition q, one 128-bit load per cell (the rows are padded
-        // by one cell, so the eight lanes of a quarter warp hit all 32 banks), weights broadcast; cells whose weights
-        // are zero — samples far from the best, warps beyond the range — are skipped, which leaves the sums unchanged
-        // (and keeps never-written cells out: 0 * NaN would poison).  FP32 sums of <= kper terms, added up in FP64
-        // over the partitions in order: nothing depends on timing. ----
+        // by one cell, so the eight lanes of a quarter warp hit all 32 banks), weights broadcast; only the cells whose
+        // weights are not zero are visited (nz_s: one bit per sample, set in PASS 4-5) — samples far from the best and warps
+        // beyond the range cost nothing, which leaves the sums unchanged (and keeps never-written cells out: 0 * NaN).
+        // FP32 sums of <= kper terms, added up in FP64 over the partitions in order: nothing depends on timing. ----
         constexpr int TPR = 4 / SPT;       // steps per tile row
         const int rows = Hq * SPT;
         int nq = NT / rows;
@@ -449,21 +453,26 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) mppi_ws_kernel(const __gr
             float acc[TPR];
 #pragma unroll
             for (int i = 0; i < TPR; ++i) acc[i] = 0.0f;
-#pragma unroll 4
-            for (int k = k_lo; k < k_hi; ++k) {
-                if constexpr (SPT == 1) {
-                    const float wk = w_s[k];
-                    if (wk != 0.0f) {
-                        const float4 v4 = cp[k];
+            // the units of [k_lo, k_hi) that carry weight, in ascending order (one mask word per 32 units)
+            for (int wd = k_lo >> 5; k_lo < k_hi && wd <= (k_hi - 1) >> 5; ++wd) {
+                unsigned int mk = nz_s[wd];
+                if constexpr (SPT == 2) mk |= nz_s[wd + NCW];
+                const int b_lo = k_lo - 32 * wd, b_hi = k_hi - 32 * wd;  // partition bounds relative to this word
+                if (b_lo > 0) mk &= 0xffffffffu << b_lo;
+                if (b_hi < 32) mk &= (1u << b_hi) - 1u;
+                while (mk != 0u) {
+                    const int k = 32 * wd + __ffs(mk) - 1;
+                    mk &= mk - 1u;
+                    const float4 v4 = cp[k];
+                    if constexpr (SPT == 1) {
+                        const float wk = w_s[k];
                         acc[0] = fmaf(wk, v4.x, acc[0]);
                         acc[1] = fmaf(wk, v4.y, acc[1]);
                         acc[2] = fmaf(wk, v4.z, acc[2]);
                         acc[3] = fmaf(wk, v4.w, acc[3]);
-                    }
-                } else {
-                    const float wa = w_s[k], wb2 = w_s[k + U];
-                    if (wa != 0.0f || wb2 != 0.0f) {
-                        const float4 v4 = cp[k];  // (a[t], b[t], a[t+1], b[t+1])
+                    } else {
+                        // v4 = (a[t], b[t], a[t+1], b[t+1]); a zero weight must not touch its value (0 * NaN)
+                        const float wa = w_s[k], wb2 = w_s[k + U];
                         if (wa != 0.0f) {
                             acc[0] = fmaf(wa, v4.x, acc[0]);
                             acc[1] = fmaf(wa, v4.z, acc[1]);

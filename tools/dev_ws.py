@@ -40,6 +40,9 @@ def device_loop(m, d_x, d_u0, d_u1, n):
 
 def main():
     shape = sys.argv[1] if len(sys.argv) > 1 else "c1"
+    if shape.startswith("K"):  # K<samples>xH<horizon>
+        ks, hs = shape[1:].split("xH")
+        SHAPES[shape] = (int(hs), int(ks), 0.8 / int(hs), 200)
     H, K, dt, reps = SHAPES[shape]
     variants = [int(v) for v in sys.argv[2:]] or [-1, 0, 1, 2, 3]
     cqs = [int(v) for v in os.environ.get("CQS", "2").split(",")]

@@ -37,3 +37,26 @@ int mpcb_device_loop(mpcb_mppi* h, const double* d_x, double* d_u0, double* d_u1
     }
     return 0;
 }
+
+/* The same loop with a CUDA event between consecutive launches (on the handle's stream): ms[i] = time from event i to
+ * event i + 1, i.e. the launch-to-launch interval of step i as the GPU saw it.  Returns 0 or the failing status; -1 if
+ * CUDA events fail.  n <= 4096. */
+#include <cuda_runtime_api.h>
+int mpcb_device_loop_events(mpcb_mppi* h, void* stream, const double* d_x, double* d_u0, double* d_u1, int n, float* ms) {
+    static cudaEvent_t ev[4097];
+    static int made = 0;
+    if (n > 4096) n = 4096;
+    for (; made <= 4096; ++made)
+        if (cudaEventCreate(&ev[made]) != cudaSuccess) return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int i = 0; i < n; ++i) {
+        cudaEventRecord(ev[i], s);
+        const mpcb_status st = mpcb_mppi_compute_device(h, d_x, (i & 1) ? d_u1 : d_u0, NULL, MPCB_DT_F32, (i & 1) ? d_u0 : d_u1);
+        if (st != MPCB_OK) return (int)st;
+    }
+    cudaEventRecord(ev[n], s);
+    if (cudaEventSynchronize(ev[n]) != cudaSuccess) return -1;
+    for (int i = 0; i < n; ++i)
+        if (cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]) != cudaSuccess) return -1;
+    return 0;
+}
