@@ -69,7 +69,8 @@ struct mpcb_mppi {
     void* comm = nullptr;
     // fused peer exchange: own mailbox + flags, the peers' mappings, device tables of both
     void* d_mailbox = nullptr;  // [flags: 2*G*C*kMaxMergers u32, padded][mailbox: 2*G*C*PL doubles]
-    size_t mailbox_bytes = 0, mailbox_flag_bytes = 0;
+    size_t mailbox_bytes = 0, mailbox_flag_bytes = 0, mailbox_ll_offset = 0;
+    int peer_ll = 0;  // 1: tagged-cell (LL) exchange inside the warp merge; 0: rows + flags (mergers must match across ranks)
     void* peer_base[kMergeFan] = {};
     bool peer_ipc[kMergeFan] = {};
     double** d_peer_mbox = nullptr;
@@ -99,7 +100,9 @@ struct PeerBlob {
     uint64_t flag_bytes;
     int32_t world, controllers, horizon, pad;
     cudaIpcMemHandle_t ipc;  // 64 bytes
-    char reserved[MPCB_PEER_HANDLE_BYTES - 56 - 64];
+    int32_t protocol;        // 1: tagged cells (LL), 0: rows + flags — every rank must use the same one
+    int32_t mergers;         // flag protocol: flags are indexed by merger, so the merger count must match too
+    char reserved[MPCB_PEER_HANDLE_BYTES - 56 - 64 - 8];
 };
 static_assert(sizeof(PeerBlob) == MPCB_PEER_HANDLE_BYTES, "peer blob must be 128 bytes");
 constexpr uint32_t kPeerMagic = 0x4d504258u;  // "MPBX"
@@ -338,7 +341,8 @@ mpcb_status pick_kernels(mpcb_mppi* h) {
         int nq = tail_threads / Hpm;
         if (nq < 1) nq = 1;
         if (nq > kMergeMaxPart) nq = kMergeMaxPart;
-        if (h->chunks <= kMergeFan && h->chunks <= 2 * kMergeBatch * nq) {
+        // (with designated mergers the single level is the barrier-free warp merge, which takes any row count <= kMergeFan)
+        if (h->chunks <= kMergeFan && (h->mergers >= 1 || h->chunks <= 2 * kMergeBatch * nq)) {
             h->group_size = h->chunks;
             h->groups = 1;
         } else {
@@ -468,6 +472,7 @@ void set_peer_params(mpcb_mppi* h, MppiParams& p) {
     p.G = h->cfg.world_size;
     p.rank = h->cfg.rank;
     p.xepoch = h->xepoch;
+    p.peer_ll_offset = h->peer_ll ? (long long)h->mailbox_ll_offset : 0;
 }
 
 mpcb_status compute_host(mpcb_mppi* h, const double* x, const double* u_in, const void* d_eps, int eps_dtype,
@@ -613,7 +618,7 @@ static mpcb_status create_impl(mpcb_mppi** out, const mpcb_mppi_cfg* cfg, const 
     MPCB_REQUIRE(cfg->samples >= 1, "samples must be >= 1");
     MPCB_REQUIRE(cfg->controllers >= 1, "controllers must be >= 1");
     MPCB_REQUIRE(cfg->world_size >= 1 && cfg->world_size <= kMergeFan && cfg->rank >= 0 && cfg->rank < cfg->world_size,
-                 "bad rank/world_size (1..64 ranks)");
+                 "bad rank/world_size (1..256 ranks)");
     MPCB_REQUIRE(cfg->precision == MPCB_F32 || cfg->precision == MPCB_F64, "bad precision");
     MPCB_REQUIRE(cfg->std_dev > 0.0 && cfg->lambda > 0.0, "std_dev and lambda must be positive");
     MPCB_REQUIRE(cfg->limit_lo <= cfg->limit_hi, "limit.0 > limit.1");
@@ -931,7 +936,11 @@ mpcb_status ensure_mailbox(mpcb_mppi* h) {
     if (h->d_mailbox) return MPCB_OK;
     const size_t G = h->cfg.world_size, C = h->C;
     h->mailbox_flag_bytes = ((2 * G * C * kMaxMergers * sizeof(unsigned int)) + 255) & ~(size_t)255;
-    h->mailbox_bytes = h->mailbox_flag_bytes + 2 * G * C * (size_t)h->PL * sizeof(double);
+    // [flags][2 parity x G x C rows of PL doubles: flag protocol][2 x G x C x ncell tagged 16-byte cells: LL protocol]
+    h->mailbox_ll_offset = 2 * G * C * (size_t)h->PL * sizeof(double);  // from the end of the flags
+    h->mailbox_bytes = h->mailbox_flag_bytes + h->mailbox_ll_offset + 2 * G * C * (size_t)mppi_ll_cells(h->H) * 16;
+    // the tagged-cell exchange runs inside the single-level warp merge (one resident wave, <= kMergeFan rows) with lane r = rank r
+    h->peer_ll = (h->groups == 1 && h->mergers >= 1 && G <= 32 && !getenv("MPCB_MPPI_PEER_FLAGS")) ? 1 : 0;
     MPCB_CUDA_TRY(cudaMalloc(&h->d_mailbox, h->mailbox_bytes));
     MPCB_CUDA_TRY(cudaMemset(h->d_mailbox, 0, h->mailbox_bytes));
     MPCB_CUDA_TRY(cudaDeviceSynchronize());  // zeroed before anyone can learn the handle
@@ -956,6 +965,8 @@ mpcb_status mpcb_mppi_peer_handle(mpcb_mppi* h, char out[MPCB_PEER_HANDLE_BYTES]
     b.world = h->cfg.world_size;
     b.controllers = h->C;
     b.horizon = h->H;
+    b.protocol = h->peer_ll;
+    b.mergers = h->mergers;
     MPCB_CUDA_TRY(cudaIpcGetMemHandle(&b.ipc, h->d_mailbox));
     memcpy(out, &b, sizeof(b));
     return MPCB_OK;
@@ -976,6 +987,10 @@ mpcb_status mpcb_mppi_attach_peers(mpcb_mppi* h, const char* handles) {
         MPCB_REQUIRE(b.magic == kPeerMagic && b.rank == r, "handles must be the mpcb_mppi_peer_handle blobs in rank order");
         MPCB_REQUIRE(b.world == G && b.controllers == h->C && b.horizon == h->H && b.bytes == h->mailbox_bytes,
                      "peer handle was made by a controller of a different shape");
+        // the exchange protocol (and, for the flag protocol, the number of merger blocks the flags are indexed by) follows from
+        // each rank's own kernel plan: a mismatch would end in MPCB_PEER_TIMEOUT on every step, so it is refused here
+        MPCB_REQUIRE(b.protocol == h->peer_ll && (h->peer_ll || b.mergers == h->mergers),
+                     "ranks planned different exchange protocols / merger counts (different shard sizes or MPCB_MPPI_* overrides?)");
         void* base = nullptr;
         if (r == h->cfg.rank) {
             base = h->d_mailbox;

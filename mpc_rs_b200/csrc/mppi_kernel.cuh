@@ -85,6 +85,7 @@ struct MppiParams {
     int G, rank;
     unsigned int xepoch, pad2;     // exchange epoch (same on every rank), parity = xepoch & 1
     unsigned long long* debug_ts;  // optional [blocks][8] %globaltimer stamps (diagnostics)
+    long long peer_ll_offset;      // FINAL_PEER_EXCHANGE: bytes from a mailbox base to its tagged-cell region; 0 = flag protocol
     int ws_cq, ws_debug;           // warp-specialised kernels: 4-step groups per producer->consumer chunk; diagnostics bits
     ModelConsts mc;
     double xu_inline[8 + kInlineHorizon];  // x[S] (S <= kMaxStateDim = 8) then u_n[H]
@@ -447,6 +448,33 @@ __device__ __forceinline__ float fast_exp_neg(double a) {
     return r;
 }
 
+// ---- cross-GPU exchange of the warp merge: data that carries its own tag (NCCL's "LL" idea) ----
+// A value travels as ONE 16-byte store {lo32, tag, hi32, tag}: each 8-byte half is written atomically and validates
+// itself, so the receiver needs neither a flag nor the sender an acknowledged release (the round-1 exchange spent
+// 2.5 us per step in st.release.sys waiting for its row stores to be acknowledged over NVLink).  tag = the exchange
+// epoch (the same on every rank); slots alternate with its parity, a peer can be at most one step ahead.
+// Record of (source rank, controller): cells [0..5) = m, argmax, sum_w, n_finite, sum_w*v[0] — written once per rank
+// by the warp of pair 1 in merger 0 — then two cells (the pair's two sums) per column pair 1 .. ncol2-1.
+struct PeerLL {
+    double* const* peer_base;  // device table [G]: every rank's mailbox base (own entry included)
+    long long ll_offset;       // bytes from the base to the LL region [2 parity][G source ranks][C][ncell] cells
+    int G, rank, C, ncell;
+    unsigned int epoch;
+};
+__host__ __device__ inline int mppi_ll_cells(int H) { return 3 + 2 * ((H + 3) >> 1); }  // 5 + 2 * (ncol2 - 1)
+__device__ __forceinline__ void ll_store(uint4* cell, double v, unsigned int tag) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(cell), "r"((unsigned int)b), "r"(tag),
+                 "r"((unsigned int)(b >> 32)), "r"(tag)
+                 : "memory");
+}
+__device__ __forceinline__ bool ll_load(const uint4* cell, unsigned int tag, double* v) {
+    unsigned int a, ta, b, tb;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(ta), "=r"(b), "=r"(tb) : "l"(cell) : "memory");
+    *v = __longlong_as_double((long long)(((unsigned long long)b << 32) | a));
+    return ta == tag && tb == tag;
+}
+
 // Single-level merge without block barriers: ONE WARP merges one column pair of the n_rows (<= kMergeFan) rows.
 // Lane l takes rows l, l + 32, ...: every load of the warp — the rows' headers (m, argmax), pair 0 (sum_w, n_finite),
 // pair 1 (it holds u[0], the element src/mppi.rs:87 checks) and the warp's own pair — is issued before anything is
@@ -463,9 +491,13 @@ __device__ __forceinline__ float fast_exp_neg(double a) {
 // The rows are stored PAIR-MAJOR here (slot q of row r at rows + q * pair_stride + 2 r; q = 0: header (m, argmax),
 // q = 1: pair 0, q = j + 1: pair j): the rows a warp reads for one slot are consecutive 16-byte cells, i.e. coalesced
 // loads (row-major rows made every load of the warp touch 32 different 128-byte lines: 2.9 us for the 20 loads).
+// ll != nullptr (FINAL_PEER_EXCHANGE): the warp's un-normalised sums go to every rank's mailbox as tagged cells, the warp
+// collects the G ranks' records of its pair (lane r = rank r) and combines them exactly like rows of one GPU — every
+// rank does the same arithmetic on the same records, so the ranks' results agree bitwise.
 template <bool kFastExp>
 static __device__ __forceinline__ int mppi_warp_merge(const double* rows, long long pair_stride, int n_rows, int H, int pair,
-                                                      double inv_lambda, int final_mode, const MergeOut& o, bool write_info) {
+                                                      double inv_lambda, int final_mode, const MergeOut& o, bool write_info,
+                                                      const PeerLL* ll = nullptr, int ctrl = 0) {
     constexpr int RPL = kMergeFan / 32;  // rows per lane
     const unsigned int full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -529,6 +561,69 @@ static __device__ __forceinline__ int mppi_warp_merge(const double* rows, long l
         ay += __hiloint2double(__shfl_xor_sync(full, __double2hiint(ay), off), __shfl_xor_sync(full, __double2loint(ay), off));
     }
     if (o.ts != nullptr && lane == 0 && s == s) o.ts[10] = globaltimer_ns();  // (diagnostics) sums reduced
+    bool any_r = any;
+    int forced = o.forced_status;
+    if (ll != nullptr) {
+        // ---- send: lane r writes this rank's record of the pair (and, once per rank, the header) into rank r's mailbox ----
+        const unsigned int tag = ll->epoch, par = ll->epoch & 1u;
+        const long long slot_out = ((long long)(par * ll->G + ll->rank) * ll->C + ctrl) * ll->ncell;
+        if (lane < ll->G) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(ll->peer_base[lane]) + ll->ll_offset) + slot_out;
+            ll_store(dst + 5 + 2 * (pair - 1), ax, tag);
+            ll_store(dst + 6 + 2 * (pair - 1), ay, tag);
+            if (write_info) {  // the header travels once per rank
+                ll_store(dst + 0, any ? wm : -CUDART_INF, tag);
+                ll_store(dst + 1, ll_as_double(any ? wa : -1ll), tag);
+                ll_store(dst + 2, s, tag);
+                ll_store(dst + 3, nf, tag);
+                ll_store(dst + 4, a0, tag);
+            }
+        }
+        // ---- receive: lane r polls rank r's record in this rank's own mailbox until every cell carries this step's tag ----
+        double rm = -CUDART_INF, rarg = ll_as_double(-1ll), rs = 0.0, rnf = 0.0, ra0 = 0.0, rax = 0.0, ray = 0.0;
+        bool timed_out = false;
+        if (lane < ll->G) {
+            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(ll->peer_base[ll->rank]) + ll->ll_offset) +
+                               ((long long)(par * ll->G + lane) * ll->C + ctrl) * ll->ncell;
+            unsigned long long t_start = 0;
+            for (unsigned int it = 0;; ++it) {
+                bool ok = ll_load(src + 0, tag, &rm);
+                ok = ll_load(src + 1, tag, &rarg) && ok;
+                ok = ll_load(src + 2, tag, &rs) && ok;
+                ok = ll_load(src + 3, tag, &rnf) && ok;
+                ok = ll_load(src + 4, tag, &ra0) && ok;
+                ok = ll_load(src + 5 + 2 * (pair - 1), tag, &rax) && ok;
+                ok = ll_load(src + 6 + 2 * (pair - 1), tag, &ray) && ok;
+                if (ok) break;
+                if ((it & 63u) == 63u) {  // bounded: a missing peer becomes MPCB_PEER_TIMEOUT, not a hang
+                    const unsigned long long now = globaltimer_ns();
+                    if (t_start == 0) t_start = now;
+                    else if (now - t_start > 20000000000ull) { timed_out = true; break; }
+                }
+            }
+        }
+        if (__any_sync(full, timed_out)) forced = MPCB_PEER_TIMEOUT;
+        // ---- combine the ranks like rows: max, lowest sample index among equal maxima, scales, fixed xor tree ----
+        long long ra = double_as_ll(rarg);
+        if (ra < 0) ra = kNoArg;
+        warp_max_minidx(rm, ra, lane < ll->G && ra != kNoArg, &wm, &wa);
+        any_r = (wa != kNoArg);
+        double arg = (rm - wm) * inv_lambda;
+        arg = (arg > -746.0) ? arg : -746.0;
+        double f;
+        if constexpr (kFastExp) f = (double)fast_exp_neg(arg);
+        else f = exp(arg);
+        if (lane >= ll->G) f = 0.0;
+        s = f * rs; nf = rnf; a0 = f * ra0; ax = f * rax; ay = f * ray;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            s += __hiloint2double(__shfl_xor_sync(full, __double2hiint(s), off), __shfl_xor_sync(full, __double2loint(s), off));
+            nf += __hiloint2double(__shfl_xor_sync(full, __double2hiint(nf), off), __shfl_xor_sync(full, __double2loint(nf), off));
+            a0 += __hiloint2double(__shfl_xor_sync(full, __double2hiint(a0), off), __shfl_xor_sync(full, __double2loint(a0), off));
+            ax += __hiloint2double(__shfl_xor_sync(full, __double2hiint(ax), off), __shfl_xor_sync(full, __double2loint(ax), off));
+            ay += __hiloint2double(__shfl_xor_sync(full, __double2hiint(ay), off), __shfl_xor_sync(full, __double2loint(ay), off));
+        }
+    }
     if (final_mode == FINAL_RANK_ROW) {
         if (lane == 0) {
             for (int r = -1; r < o.n_copies; ++r) {
@@ -544,8 +639,8 @@ static __device__ __forceinline__ int mppi_warp_merge(const double* rows, long l
         return MPCB_OK;
     }
     // src/mppi.rs:69 no finite cost, :76-78 sum is zero, :87-89 u[0] not finite (element 0 only)
-    int status = o.forced_status;
-    if (status == MPCB_OK) status = !any ? MPCB_NO_FINITE_COST : (s == 0.0 ? MPCB_SUM_ZERO : (!finite_f64(a0 / s) ? MPCB_U_INVALID : MPCB_OK));
+    int status = forced;
+    if (status == MPCB_OK) status = !any_r ? MPCB_NO_FINITE_COST : (s == 0.0 ? MPCB_SUM_ZERO : (!finite_f64(a0 / s) ? MPCB_U_INVALID : MPCB_OK));
     if (lane == 0) {
         const int t0 = 2 * pair - 2;
         const double u0 = (status == MPCB_OK) ? ax / s : 0.0;
@@ -560,8 +655,8 @@ static __device__ __forceinline__ int mppi_warp_merge(const double* rows, long l
             mpcb_mppi_info out;
             out.status = status;
             out.reserved = 0;
-            out.argmax = any ? wa : -1ll;
-            out.max = any ? wm : 0.0;
+            out.argmax = any_r ? wa : -1ll;
+            out.max = any_r ? wm : 0.0;
             out.sum = s;
             out.n_finite = (long long)nf;
             *o.info = out;
@@ -770,7 +865,8 @@ __device__ __forceinline__ void mppi_block_tail(const MppiParams& p, int c, int 
     double* ctrl_rows = p.partial + (long long)c * (p.chunks + p.groups) * PL;
     double* my_row = ctrl_rows + (long long)chunk * PL;
     // single-level merge by warps (below): the level-0 rows are stored pair-major, see mppi_warp_merge
-    const bool pair_major = (p.groups == 1 && p.mergers >= 1 && p.final_mode != FINAL_PEER_EXCHANGE);
+    const bool peer_ll = (p.final_mode == FINAL_PEER_EXCHANGE && p.peer_ll_offset != 0);
+    const bool pair_major = (p.groups == 1 && p.mergers >= 1 && (p.final_mode != FINAL_PEER_EXCHANGE || peer_ll));
     const long long pair_stride = 2ll * p.chunks;
     if (pair_major) {
         for (int j = tid; j < (PL >> 1); j += BLOCK) {
@@ -873,12 +969,18 @@ __device__ __forceinline__ void mppi_block_tail(const MppiParams& p, int c, int 
             fo.forced_status = timed_out ? MPCB_PEER_TIMEOUT : MPCB_OK;
             if (dbg != nullptr && tid == 0) dbg[7] = globaltimer_ns();
             fo.ts = (wid == 0) ? dbg : nullptr;
+            PeerLL pll;
+            pll.peer_base = p.peer_mbox;
+            pll.ll_offset = p.peer_ll_offset;
+            pll.G = p.G; pll.rank = p.rank; pll.C = p.C; pll.ncell = mppi_ll_cells(H);
+            pll.epoch = p.xepoch;
             for (int pair = p_lo + wid; pair < p_hi; pair += BLOCK / 32)
-                mppi_warp_merge<kFastExp>(ctrl_rows, pair_stride, p.chunks, H, pair, inv_lambda_m, p.final_mode, fo, mi == 0 && pair == 1);
+                mppi_warp_merge<kFastExp>(ctrl_rows, pair_stride, p.chunks, H, pair, inv_lambda_m, peer_ll ? FINAL_NORMALISE : p.final_mode, fo,
+                                          mi == 0 && pair == 1, peer_ll ? &pll : nullptr, c);
             if (p.final_mode == FINAL_RANK_ROW && mi == 0 && tid == 0 && PL > kPartialHdr + H) fo.out_row[kPartialHdr + H] = 0.0;
             if (dbg != nullptr && tid == 0) dbg[11] = globaltimer_ns();
         }
-        if (p.done_host && p.final_mode == FINAL_NORMALISE) {
+        if (p.done_host && p.final_mode != FINAL_RANK_ROW) {
             // results of every warp of this merger first, then its completion word the host spins on
             __threadfence_system();
             __syncthreads();
