@@ -6,8 +6,9 @@
 One "step" is one MPPI control step (src/mppi.rs:33-92: noise -> K x H rollout -> softmax-weighted update) on
 BASELINE.json configs[1]: examples/mppi4-non-liner.rs model NL, K = 65536 samples, H = 100 (DT = 0.8/100), FP32
 fast path, Philox noise generated in-register.  With N > 1 (torchrun, one rank per GPU) every rank rolls out its
-own 65536-sample shard of a K = 65536*N controller (weak scaling) and the partial rows meet in ONE ncclAllGather
-per control step inside the library.
+own 65536-sample shard of a K = 65536*N controller (weak scaling); the ranks' partial sums meet INSIDE the rollout kernel
+(tagged 16-byte cells written into every peer's mailbox over NVLink; MPCB_BENCH_TRANSPORT=nccl selects one ncclAllGather
+per control step instead).
 
     value     device-resident closed loop (u_out of step i is u_in of step i+1), CUDA events per step on the
               handle's stream, L2 flushed between timed steps, max over ranks
@@ -18,7 +19,12 @@ per control step inside the library.
     roofline  algorithmic FP32 flops (60 per rollout-step) / kernel time vs the FFMA peak measured
               live by tools/peak_bench (MEASURED_PEAKS.json has no FP32 vector number)
     ukf       BASELINE configs[2] on the side: 2^20 independent examples/ukf-pen.rs filters per GPU, FP64,
-              336 algorithmic bytes per filter-update vs the measured HBM copy bandwidth
+              336 algorithmic bytes per filter-update vs the measured HBM copy bandwidth; its own cpu_baseline (the
+              oracle looped over filters with OpenMP on all host cores)
+    closed_loop  BASELINE configs[3]: 4096 robots x 8192 samples x H = 8 of examples/mppi4-non-liner-ukf.rs through
+              mpcb_closed_loop_tick (plant, sensor, UKF, MPPI all on the device), robots sharded over the N ranks
+    sweep     BASELINE configs[4]: K = 2^16 .. 2^24, H = 200, samples sharded over the N ranks
+    parity_check  (N > 1) untimed: the sharded controller against a single-GPU controller of the same K and seed
     cpu_baseline / --impl reference
               the C restatement of the reference's nalgebra/rayon CPU path (oracle/, kind "port": no Rust
               toolchain exists here or on the GPU box) on all host cores
@@ -47,7 +53,7 @@ LAMBDA, SIGMA, LIMIT = 0.5, 3.0, (-20.0, 20.0)
 X0 = np.array([0.5, 0.0, 0.1, 0.0])  # examples/mppi4-non-liner.rs:30
 FLOPS_PER_STEP = 60.0  # model NL 58 + 2 epilogue flops per rollout-step
 UKF_B = 1 << 20
-UKF_T = 50
+UKF_T = 100  # T = 100 steps, as examples/ukf-pen.rs:154-178 runs
 UKF_BYTES = 336.0  # 8*(2n + 2n^2 + o), n=4, o=2
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures of these kernels
 # (profiles/mppi_r1_final2_ncu_full_summary.txt, profiles/ukf_r1_pipe_ncu_full_summary.txt)
@@ -62,8 +68,8 @@ UNIT = "rollout-steps/s"
 def workload(n_gpus: int) -> dict:
     transport = os.environ.get("MPCB_BENCH_TRANSPORT", "peer")
     exchange = (f"one ncclAllGather of {H + 4} doubles per rank per step" if transport == "nccl" else
-                f"in-kernel exchange: each rank's final blocks store its {H + 4}-double partial row into the peers' mailboxes "
-                "over NVLink and combine the rows they receive (no collective call)")
+                "in-kernel peer exchange (no collective call): every merger warp stores its column pair's sums into all ranks' "
+                "mailboxes over NVLink as self-validating tagged 16-byte cells and combines the ranks' cells itself")
     return {
         "workload": "BASELINE configs[1]: examples/mppi4-non-liner.rs MPPI, model NL, "
                     f"K={K_PER_GPU} samples/GPU x H={H}, DT={DT}, lambda={LAMBDA}, sigma={SIGMA}, limit=+-20",
@@ -75,7 +81,7 @@ def workload(n_gpus: int) -> dict:
 
 
 # ---- reference arm / cpu baseline ---------------------------------------------------------------------------
-def cpu_baseline(steps, warmup: int, budget_s: float = 12.0):
+def cpu_baseline(steps, warmup: int, budget_s: float = 12.0, n_gpus: int = 1):
     """Times the CPU restatement (oracle/) of src/mppi.rs:38-91 on all host cores: full-size control steps of the bench
     workload (K = 65536, H = 100), closed loop.  steps=None runs as many as fit in about budget_s seconds of CPU work
     (the bounded sample); an explicit step count is capped by the same budget.  Returns (rollout-steps/s, info)."""
@@ -84,7 +90,7 @@ def cpu_baseline(steps, warmup: int, budget_s: float = 12.0):
     # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every core this process may run on
     threads = max(O.max_threads(), len(os.sched_getaffinity(0)))
     p = O.model_defaults(O.MODEL_NL, dt=DT)
-    K = K_PER_GPU
+    K = K_PER_GPU * n_gpus  # the GPU arm's whole-job workload (weak scaling: K_PER_GPU samples per GPU)
     u = np.zeros(H)
     t0 = time.perf_counter()
     O.mppi_compute_cpu(O.MODEL_NL, p, K, H, LAMBDA, SIGMA, LIMIT[0], LIMIT[1], X0, u, seed=1, threads=threads)
@@ -111,11 +117,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    val, info = cpu_baseline(args.steps, min(args.warmup, 3), budget_s=120.0)  # every step is a full-size control step
+    val, info = cpu_baseline(args.steps, args.warmup, budget_s=120.0, n_gpus=args.gpus)  # every step is a full-size control step
     steps = info["steps"]
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 3), "ms_per_step": info["ms_per_step"], "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload(args.gpus),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -205,6 +211,85 @@ def upload(A, dev, dptr, arr):
     arr = np.ascontiguousarray(arr)
     A.check(A.lib().mpcb_device_upload(dev, dptr, arr.ctypes.data_as(C.c_void_p), arr.nbytes))
 
+
+
+# ---- BASELINE configs[3]: the batched closed loop, robots sharded over the ranks (no exchange) ----------------------
+CL_C, CL_K, CL_TICKS = 4096, 8192, 50
+
+
+def closed_loop_leg(dev, rank, world, barrier, max_over_ranks):
+    from mpc_rs_b200.closed_loop import ClosedLoopBatch
+    lo, hi = CL_C * rank // world, CL_C * (rank + 1) // world
+    rng = np.random.default_rng(20240004)
+    x0 = np.zeros((CL_C, 6))
+    x0[:, 3] = rng.uniform(-0.1, 0.1, CL_C)  # theta0 ~ U(-0.1, 0.1)
+    out = {"config": {"workload": f"BASELINE configs[3]: examples/mppi4-non-liner-ukf.rs closed loop, C={CL_C} robots (sharded x{world}) x "
+                                  f"K={CL_K} samples x H=8 (model NL6 + UKF NL6_UKF), fixed tick 0.01 s, MPPI fed the UKF estimate, "
+                                  f"{CL_TICKS} ticks through mpcb_closed_loop_tick", "controllers": CL_C, "samples": CL_K, "horizon": 8}}
+    for prec in ("f64", "f32"):
+        with ClosedLoopBatch(hi - lo, CL_K, x0=x0[lo:hi], seed=20240004, precision=prec, device=dev, controller_offset=lo) as loop:
+            loop.tick(5)
+            loop.sync()
+            barrier()
+            l0, t0 = loop.launches, time.perf_counter()
+            loop.tick(CL_TICKS)
+            loop.sync()
+            el = max_over_ranks(time.perf_counter() - t0)
+            up = int(loop.upright().sum())
+            bad = int((loop.mppi_status() != 0).sum())
+            out[prec] = {"value": CL_C * CL_K * 8 * CL_TICKS / el, "unit": UNIT, "ms_per_tick": el / CL_TICKS * 1e3,
+                         "filter_updates_per_sec": CL_C * CL_TICKS / el, "gpu_launches": int(loop.launches - l0),
+                         "upright_on_rank0": f"{up}/{hi - lo}", "mppi_failures_on_rank0": bad}
+    out["f64"]["note"] = "the default precision for model NL6 (FP64 rollouts reproduce the f64 reference to 1e-9)"
+    out["f32"]["note"] = ("FP32 rollouts: on model NL6 at its shipped DT = 0.15 the FP32 controls are 1e-4..1e-3 from the f64 "
+                          "reference (the model is chaotic inside its horizon, DESIGN.md 4.1) - reported, not the parity path")
+    out["f32"]["roofline"] = {"bound": "fp32", "flops_per_rollout_step": 72.0,
+                              "achieved": out["f32"]["value"] / world * 72.0 / 1e12, "unit": "TFLOP/s",
+                              "note": "72 algorithmic flops per NL6 rollout-step (SURVEY.md 8d); whole tick incl. plant, sensor and UKF"}
+    return out
+
+
+# ---- BASELINE configs[4]: K = 2^16 .. 2^24, H = 200, samples sharded over the ranks ----------------------------------
+def sweep_leg(dev, rank, world, barrier, max_over_ranks, A, Mppi, models, torch, dev_loop):
+    from mpc_rs_b200.distributed import attach_mppi_peers
+    Hs, rows = 200, []
+    for lg in (16, 18, 20, 22, 24):
+        K = 1 << lg
+        m = Mppi(Hs, K, model=models.NL, lam=LAMBDA, std_dev=SIGMA, limit=LIMIT, precision="f32", dt=0.8 / Hs, device=dev, rank=rank,
+                 world_size=world, seed=20240005)
+        if world > 1:
+            attach_mppi_peers(m)
+        d_x, d_a, d_b = dev_alloc(A, dev, 32), dev_alloc(A, dev, 8 * Hs), dev_alloc(A, dev, 8 * Hs)
+        upload(A, dev, d_x, X0)
+        upload(A, dev, d_a, np.zeros(Hs))
+        stream = torch.cuda.ExternalStream(m.stream, device=dev)
+        steps = 20 if lg <= 20 else 8
+
+        def run(n):
+            if dev_loop is not None:
+                if dev_loop(m._h, d_x, d_a, d_b, n) != 0:
+                    raise SystemExit("sweep: mpcb_mppi_compute_device failed")
+            else:
+                for i in range(n):
+                    m.compute_device(d_x, d_a if i % 2 == 0 else d_b, d_b if i % 2 == 0 else d_a)
+        run(4)
+        m.sync()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        run(steps)
+        e1.record(stream)
+        m.sync()
+        ms = max_over_ranks(e0.elapsed_time(e1) / steps)
+        info = m.last_info()[0]
+        rows.append({"K": K, "ms_per_step": ms, "value": K * Hs / (ms * 1e-3), "status": int(info["status"]),
+                     "frac_fp32_roofline_per_gpu": K * Hs / (ms * 1e-3) / world * FLOPS_PER_STEP / 1e12})
+        for q in (d_x, d_a, d_b):
+            A.lib().mpcb_device_free(dev, q)
+        m.close()
+    return {"config": {"workload": f"BASELINE configs[4]: MPPI sweep K=2^16..2^24 (global), H={Hs}, model NL, DT={0.8 / Hs}, FP32, generate "
+                                   f"mode, samples sharded x{world}" + (", in-kernel peer exchange" if world > 1 else ""), "horizon": Hs},
+            "unit": UNIT, "points": rows}
 
 # ---- GPU arm --------------------------------------------------------------------------------------------------
 def run_gpu(args):
@@ -412,6 +497,73 @@ def run_gpu(args):
     except Exception as e:  # the MPPI line is still valid; say what happened
         ukf_out = {"error": repr(e)}
 
+    # ---- UKF CPU baseline (rank 0, N = 1): the oracle's examples/ukf-pen.rs step looped over filters with OpenMP ----
+    if world == 1 and ukf_out and "value" in ukf_out:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_lib as O
+            threads = max(O.max_threads(), len(os.sched_getaffinity(0)))
+            Bc, Tc = 1 << 16, 10
+            pu = O.model_defaults(O.MODEL_PEN_LIN)
+            Qc, Rc, P0c = O.ukf_default_noise(O.MODEL_PEN_LIN, 0.0)
+            xc, Pc = np.zeros((Bc, 4)), np.tile(P0c, (Bc, 1, 1))
+            zc = 0.7 * np.random.default_rng(3).standard_normal((Tc, Bc, 2))
+            xc, Pc, _ = O.ukf_step_batch(O.MODEL_PEN_LIN, pu, xc, Pc, Qc, Rc, 0.0015, zc[0], 0.0, O.SQRT_CHOLESKY, O.ORDER_INTERLEAVED,
+                                         threads=threads)
+            t0 = time.perf_counter()
+            for t in range(1, Tc):
+                xc, Pc, _ = O.ukf_step_batch(O.MODEL_PEN_LIN, pu, xc, Pc, Qc, Rc, 0.0015, zc[t], 0.0, O.SQRT_CHOLESKY,
+                                             O.ORDER_INTERLEAVED, threads=threads)
+            el_c = time.perf_counter() - t0
+            ukf_out["cpu_baseline"] = {
+                "value": Bc * (Tc - 1) / el_c, "unit": "filter-updates/s", "cores": threads, "kind": "port",
+                "sample": f"{Tc - 1} steps of {Bc} filters ({el_c:.1f} s on {threads} threads) through oracle/ orc_ukf_step_batch "
+                          "(examples/ukf-pen.rs:93-141 per filter, OpenMP over filters, f64, incl. the ctypes array copies); the "
+                          "reference itself runs one filter on one thread"}
+        except Exception as e:  # noqa: BLE001
+            ukf_out["cpu_baseline"] = {"error": repr(e)}
+
+    # ---- BASELINE configs[3] and configs[4] as sub-objects (every rank takes part) ----
+    try:
+        closed_loop = closed_loop_leg(dev, rank, world, barrier, max_over_ranks)
+    except Exception as e:  # noqa: BLE001
+        closed_loop = {"error": repr(e)}
+    try:
+        sweep = sweep_leg(dev, rank, world, barrier, max_over_ranks, A, Mppi, models, torch, dev_loop)
+    except Exception as e:  # noqa: BLE001
+        sweep = {"error": repr(e)}
+
+    # ---- N > 1: correctness of the sharded path, untimed — a fresh sharded controller against a fresh single-GPU one
+    # with the same K and seed (same Philox counters => same samples), and the ranks' results against each other ----
+    parity = None
+    if world > 1:
+        try:
+            from mpc_rs_b200.distributed import attach_mppi, attach_mppi_peers
+            kw = dict(model=models.NL, lam=LAMBDA, std_dev=SIGMA, limit=LIMIT, precision="f32", dt=DT, device=dev, seed=20240001)
+            sh = Mppi(H, K_PER_GPU * world, rank=rank, world_size=world, **kw)
+            (attach_mppi if transport == "nccl" else attach_mppi_peers)(sh)
+            u_test = np.linspace(-1.0, 1.0, H)
+            upload(A, dev, d_u[0], u_test)
+            sh.compute_device(d_x, d_u[0], d_u[1])
+            sh.sync()
+            u_sh = np.empty(H)
+            A.check(A.lib().mpcb_device_download(dev, u_sh.ctypes.data_as(C.c_void_p), d_u[1], 8 * H))
+            arg_sh = sh.last_info()[0]["argmax"]
+            t_all = [torch.zeros(H, dtype=torch.float64, device="cuda") for _ in range(world)]
+            dist.all_gather(t_all, torch.from_numpy(u_sh).cuda())
+            bitwise = all(bool(torch.equal(t_all[0], t)) for t in t_all)
+            sh.close()
+            if rank == 0:
+                with Mppi(H, K_PER_GPU * world, **kw) as one:
+                    u_one = one.compute(X0, u_test)
+                    arg_one = one.last_call_info()[0]["argmax"]
+                parity = {"rel_err": float(np.linalg.norm(u_sh - u_one) / np.linalg.norm(u_one)), "argmax_equal": bool(arg_sh == arg_one),
+                          "ranks_bitwise_equal": bool(bitwise),
+                          "what": f"one untimed step: K={K_PER_GPU * world} sharded x{world} vs the same K on one GPU (same seed: the "
+                                  "Philox counter is the global sample index)"}
+        except Exception as e:  # noqa: BLE001
+            parity = {"error": repr(e)}
+
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -452,8 +604,10 @@ def run_gpu(args):
                 "d2h_bytes_per_step": (8 * H + 40) * world, "ms_per_step": e2e_s / args.steps * 1e3, "caller": e2e_caller,
                 "python_loop_value": steps_total / e2e_py_s, "python_loop_ms_per_step": e2e_py_s / args.steps * 1e3},
         "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
-        "state_updates_per_sec": value * 4, "ukf": ukf_out,
+        "state_updates_per_sec": value * 4, "ukf": ukf_out, "closed_loop": closed_loop, "sweep": sweep,
     }
+    if parity is not None:
+        line["parity_check"] = parity
     if cpu_val is not None:
         line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": cpu_info["cores"], "kind": cpu_info["kind"],
                                 "sample": cpu_info["sample"]}

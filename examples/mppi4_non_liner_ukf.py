@@ -25,20 +25,21 @@ def run(controllers=4096, samples=8192, seconds=3.0, truth=False, csv="logs/mppi
     with ClosedLoopBatch(controllers, samples, use_estimate=not truth, seed=seed, x0=x0, precision=precision) as loop, \
             MppiUkfLog(csv) as log:
         next_log = 0.0
-        loop.mppi.sync()
+        loop.sync()
         t0 = time.perf_counter()  # the loop itself: construction (CUDA context, buffers) is not part of a tick
         while loop.t < seconds:
             loop.tick()
             if loop.t >= next_log:  # the logging thread writes every 30 ms (:404)
                 next_log += 0.03
-                x_est, _ = loop.ukf.get_state(0, 1)
+                x_est, _ = loop.estimate_range(0, 1)
                 u_n = loop.controls()[0]
                 x_pred = x_est[0].copy()
                 for i in range(loop.H):  # :418-421
                     x_pred = loop.plant.dynamics_short(x_pred, u_n[i], loop.DT, 0.0)
-                log.write(loop.t, u_n[0], loop.x[0], x_est[0], x_pred)
+                x_true = loop.x
+                log.write(loop.t, u_n[0], x_true[0], x_est[0], x_pred)
                 if not quiet:
-                    e, x = x_est[0], loop.x[0]
+                    e, x = x_est[0], x_true[0]
                     print(f"t:{loop.t:6.2f} u:{u_n[0]:6.2f} e:[{e[0]:6.2f},{e[1]:6.2f},{np.degrees(e[3]):5.0f},{np.degrees(e[4]):5.0f}] "
                           f"x:[{x[0]:6.2f},{x[1]:6.2f},{np.degrees(x[3]):5.0f},{np.degrees(x[4]):5.0f}] upright {int(loop.upright().sum())}/{controllers}")
         dt = time.perf_counter() - t0

@@ -198,6 +198,9 @@ mpcb_status mpcb_mppi_first_control_device(mpcb_mppi* h, const double* d_u_out, 
 mpcb_status mpcb_mppi_sync(mpcb_mppi* h);
 mpcb_status mpcb_mppi_last_info(mpcb_mppi* h, mpcb_mppi_info* info /*[C]*/);
 void* mpcb_mppi_stream(mpcb_mppi* h);    /* cudaStream_t */
+/* Global index of this handle's first controller (default 0): controllers sharded over GPUs draw the noise of their global
+ * index, so a sharded batch reproduces the unsharded one. */
+mpcb_status mpcb_mppi_set_controller_offset(mpcb_mppi* h, int64_t first_controller);
 int64_t mpcb_mppi_launches(mpcb_mppi* h); /* kernels launched by this handle so far */
 int64_t mpcb_mppi_local_samples(mpcb_mppi* h);
 
@@ -332,6 +335,48 @@ mpcb_status mpcb_device_alloc(int32_t device, uint64_t bytes, void** out);
 mpcb_status mpcb_device_free(int32_t device, void* p);
 mpcb_status mpcb_device_upload(int32_t device, void* dst, const void* src, uint64_t bytes);
 mpcb_status mpcb_device_download(int32_t device, void* dst, const void* src, uint64_t bytes);
+
+/* ---- batched closed loop (BASELINE config #4): examples/mppi4-non-liner-ukf.rs:38-103,224-288 ------------------------
+ * C independent robots, each with its own MPPI controller (model NL6, the constants of :13-24) and its own UKF (model
+ * NL6_UKF, :161-221), on a fixed tick instead of the reference's four wall-clock threads.  One tick = plant
+ * (dynamics_short with the 2 N push of :236-241) + sensor (hx + R*N(0,1), :169-190) + UKF predict/update (:272-283) +
+ * MPPI compute on the estimate's [x0, x1, x3, x4] (:55-87) — five launches on the device, no host round trip; a robot
+ * whose MPPI step fails gets a zero control sequence like `Err(e) => zeros` (:81-86).  Controllers shard over GPUs
+ * without any exchange: give every rank its own handle with controller_offset = its first global robot index (the
+ * noise counters use the global index, so trajectories do not depend on the sharding). */
+typedef struct mpcb_closed_loop mpcb_closed_loop;
+typedef struct mpcb_closed_loop_cfg {
+    int64_t controllers;       /* robots on this handle */
+    int64_t samples;           /* K per controller (the example ships 500000; BASELINE config #4 uses 8192) */
+    int64_t controller_offset; /* global index of this handle's first robot */
+    double tick_dt;            /* fixed tick, seconds (0.01: the example's sensor period, :267-268) */
+    uint64_t seed;
+    int32_t use_estimate;      /* 1: MPPI is fed the UKF estimate; 0: the truth (DEBUG_UKF = true, :31,55-57) */
+    int32_t precision;         /* MPCB_F32 / MPCB_F64 for the MPPI rollouts; anything else = the model's default */
+    int32_t exact_ukf;         /* mpcb_ukf_cfg.exact */
+    int32_t device;
+} mpcb_closed_loop_cfg;
+mpcb_status mpcb_closed_loop_default_cfg(mpcb_closed_loop_cfg* out); /* C = 4096, K = 8192, tick 0.01 s */
+mpcb_status mpcb_closed_loop_create(mpcb_closed_loop** out, const mpcb_closed_loop_cfg* cfg);
+void mpcb_closed_loop_destroy(mpcb_closed_loop* h);
+/* truth and estimate of every robot, host x6[C][6] (init_ukf(&init_x), :40,161-167); P[C][6][6] or NULL to keep P0 */
+mpcb_status mpcb_closed_loop_set_state(mpcb_closed_loop* h, const double* x6, const double* P);
+mpcb_status mpcb_closed_loop_set_truth(mpcb_closed_loop* h, const double* x6);       /* the plant's state only */
+mpcb_status mpcb_closed_loop_set_controls(mpcb_closed_loop* h, const double* u_seq); /* u_n[C][H] (and u_n[0]) */
+/* n ticks, asynchronous (all launches are enqueued; read back with mpcb_closed_loop_get) */
+mpcb_status mpcb_closed_loop_tick(mpcb_closed_loop* h, int32_t n_ticks);
+/* one tick with the sensor readings z[C][5] and/or the MPPI noise eps[C][K][H] supplied by the caller (host pointers,
+ * either may be NULL) — verification against a CPU restatement of the same schedule; synchronous */
+mpcb_status mpcb_closed_loop_tick_replay(mpcb_closed_loop* h, const double* z, const void* eps, int32_t eps_dtype);
+mpcb_status mpcb_closed_loop_sync(mpcb_closed_loop* h);
+/* host copies after a sync; any pointer may be NULL: truth x6[C][6], estimate x_est[C][6], last readings z[C][5], applied
+ * control u0[C], control sequences u_seq[C][H], per-controller mpcb_status of the last MPPI step */
+mpcb_status mpcb_closed_loop_get(mpcb_closed_loop* h, double* x6, double* x_est, double* z, double* u0, double* u_seq,
+                                 int32_t* mppi_status);
+mpcb_mppi* mpcb_closed_loop_mppi(mpcb_closed_loop* h); /* the handles inside (owned by the loop) */
+mpcb_ukf* mpcb_closed_loop_ukf(mpcb_closed_loop* h);
+int64_t mpcb_closed_loop_ticks(mpcb_closed_loop* h);
+int64_t mpcb_closed_loop_launches(mpcb_closed_loop* h);
 
 #ifdef __cplusplus
 }

@@ -82,6 +82,13 @@ _vp = C.c_void_p
 _H = C.c_void_p  # opaque handles
 
 # name -> (restype, argtypes); every symbol include/mpc_b200.h declares
+class ClosedLoopCfg(C.Structure):
+    """mpcb_closed_loop_cfg (include/mpc_b200.h)."""
+    _fields_ = [("controllers", C.c_int64), ("samples", C.c_int64), ("controller_offset", C.c_int64), ("tick_dt", C.c_double),
+                ("seed", C.c_uint64), ("use_estimate", C.c_int32), ("precision", C.c_int32), ("exact_ukf", C.c_int32),
+                ("device", C.c_int32)]
+
+
 SYMBOLS = {
     "mpcb_status_string": (C.c_char_p, [C.c_int]),
     "mpcb_last_error_string": (C.c_char_p, []),
@@ -137,6 +144,21 @@ SYMBOLS = {
     "mpcb_ukf_launches": (C.c_int64, [_H]),
     "mpcb_ukf_device_x": (C.c_void_p, [_H]),
     "mpcb_ukf_device_p": (C.c_void_p, [_H]),
+    "mpcb_mppi_set_controller_offset": (C.c_int, [_H, C.c_int64]),
+    "mpcb_closed_loop_default_cfg": (C.c_int, [C.POINTER(ClosedLoopCfg)]),
+    "mpcb_closed_loop_create": (C.c_int, [C.POINTER(_H), C.POINTER(ClosedLoopCfg)]),
+    "mpcb_closed_loop_destroy": (None, [_H]),
+    "mpcb_closed_loop_set_state": (C.c_int, [_H, _dp, _dp]),
+    "mpcb_closed_loop_set_truth": (C.c_int, [_H, _dp]),
+    "mpcb_closed_loop_set_controls": (C.c_int, [_H, _dp]),
+    "mpcb_closed_loop_tick": (C.c_int, [_H, C.c_int32]),
+    "mpcb_closed_loop_tick_replay": (C.c_int, [_H, _dp, _vp, C.c_int32]),
+    "mpcb_closed_loop_sync": (C.c_int, [_H]),
+    "mpcb_closed_loop_get": (C.c_int, [_H, _dp, _dp, _dp, _dp, _dp, C.POINTER(C.c_int32)]),
+    "mpcb_closed_loop_mppi": (C.c_void_p, [_H]),
+    "mpcb_closed_loop_ukf": (C.c_void_p, [_H]),
+    "mpcb_closed_loop_ticks": (C.c_int64, [_H]),
+    "mpcb_closed_loop_launches": (C.c_int64, [_H]),
     "mpcb_device_alloc": (C.c_int, [C.c_int32, C.c_uint64, C.POINTER(C.c_void_p)]),
     "mpcb_device_free": (C.c_int, [C.c_int32, _vp]),
     "mpcb_device_upload": (C.c_int, [C.c_int32, _vp, _vp, C.c_uint64]),

@@ -25,6 +25,7 @@ struct mpcb_mppi {
     int block = 0, chunks = 0, group_size = 0, groups = 0;
     int Hp = 8, lgHp = 3;
     int spt = 1;            // samples per thread (2: packed f32x2 kernels)
+    unsigned int c_offset = 0;  // mpcb_mppi_set_controller_offset
     int ws_variant = -1;    // >= 0: warp-specialised kernel, index into kWsVariants (mppi_ws_kernel.cuh)
     int ws_cq = 5;          // its producer->consumer chunk, in 4-step groups (20 steps: measured best of 1/2/5)
     int ws_debug = 0;       // MPCB_MPPI_WS_DEBUG: 1 = producers idle, 2 = consumers idle (timing decomposition only)
@@ -374,6 +375,7 @@ void fill_params(const mpcb_mppi* h, MppiParams* p) {
     p->seed_lo = (unsigned int)(h->cfg.seed & 0xffffffffull);
     p->seed_hi = (unsigned int)(h->cfg.seed >> 32);
     p->call_idx = h->call_idx;
+    p->c_offset = h->c_offset;
     p->lambda = h->cfg.lambda;
     p->inv_var = 1.0 / (h->cfg.std_dev * h->cfg.std_dev);  // std_dev.powi(-2), src/mppi.rs:48
     p->lo = h->cfg.limit_lo;
@@ -883,6 +885,12 @@ int64_t mpcb_mppi_debug_timeline(mpcb_mppi* h, unsigned long long* out, int64_t 
     if (n > max_blocks) n = max_blocks;
     cudaMemcpy(out, h->d_ts, (size_t)n * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     return n;
+}
+
+mpcb_status mpcb_mppi_set_controller_offset(mpcb_mppi* h, int64_t first_controller) {
+    MPCB_REQUIRE(h && first_controller >= 0 && first_controller <= 0x7fffffffll, "bad controller offset");
+    h->c_offset = (unsigned int)first_controller;
+    return MPCB_OK;
 }
 
 void* mpcb_mppi_stream(mpcb_mppi* h) { return h ? (void*)h->stream : nullptr; }

@@ -67,7 +67,8 @@ struct MppiParams {
     int final_mode;  // MppiFinal
     void* eps_dump;  // generate+dump: [C][K_local][H] of real
     double* costs;   // optional [C][K_local]
-    unsigned int seed_lo, seed_hi, call_idx, pad0;
+    unsigned int seed_lo, seed_hi, call_idx;
+    unsigned int c_offset;  // global index of this handle's controller 0 (part of the Philox counter)
     double lambda, inv_var, lo, hi, std_dev;
     double* partial;         // [C][chunks + groups][kPartialHdr + H]: level-0 rows, then group rows
     unsigned int* counters;  // [C][groups + 1]
@@ -1253,7 +1254,7 @@ __global__ void __launch_bounds__(BLOCK, (512 / BLOCK > 0 ? 512 / BLOCK : 1)) mp
                 } else {
                     const unsigned int c0 = (unsigned int)(kg[s] & 0xffffffffll);
                     const unsigned int khi = (unsigned int)((kg[s] >> 32) & 0xffff) << 16;
-                    const Philox4 r = philox4x32(c0, p.call_idx, (unsigned int)c, (unsigned int)(t0 >> 2) | khi,
+                    const Philox4 r = philox4x32(c0, p.call_idx, (unsigned int)c + p.c_offset, (unsigned int)(t0 >> 2) | khi,
                                                     p.seed_lo, p.seed_hi);
                     float z[4];
                     philox_normal4(r, neg2s2ln2, z);
@@ -1533,7 +1534,7 @@ __global__ void __launch_bounds__(BLOCK, (512 / BLOCK > 0 ? 512 / BLOCK : 1)) mp
                     } else {
                         const unsigned int c0 = (unsigned int)(kgk & 0xffffffffll);
                         const unsigned int khi = (unsigned int)((kgk >> 32) & 0xffff) << 16;
-                        const Philox4 r = philox4x32(c0, p.call_idx, (unsigned int)c, (unsigned int)j | khi, p.seed_lo, p.seed_hi);
+                        const Philox4 r = philox4x32(c0, p.call_idx, (unsigned int)c + p.c_offset, (unsigned int)j | khi, p.seed_lo, p.seed_hi);
                         float z[4];
                         philox_normal4(r, neg2s2ln2, z);
 #pragma unroll

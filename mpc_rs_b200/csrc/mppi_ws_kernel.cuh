@@ -206,7 +206,7 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) mppi_ws_kernel(const __gr
                 } else {
                     const unsigned int c0 = (unsigned int)(kg & 0xffffffffll);
                     const unsigned int khi = (unsigned int)((kg >> 32) & 0xffff) << 16;
-                    const Philox4 r = philox4x32(c0, p.call_idx, (unsigned int)c, (unsigned int)g | khi, p.seed_lo, p.seed_hi);
+                    const Philox4 r = philox4x32(c0, p.call_idx, (unsigned int)c + p.c_offset, (unsigned int)g | khi, p.seed_lo, p.seed_hi);
                     philox_normal4(r, neg2s2ln2, e);
                     if constexpr (NOISE == NOISE_GENERATE_DUMP) {
                         if (kl < p.K_local) {

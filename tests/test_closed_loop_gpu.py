@@ -44,36 +44,45 @@ def test_sensor_gating_parity(gpu_required, name, oid):
         assert rel(xg, xo) < 1e-8 and rel(Pg, Po) < 1e-8, (name, bin(enable), rel(xg, xo), rel(Pg, Po))
 
 
+def _oracle_tick(loop, pm, pu, Q, R, x_true, x_est, P_est, u_seq, u0, k, eps, z=None, noise=None):
+    """The CPU restatement of one tick (same order as csrc/closed_loop.cu): returns the new (x_true, z, x_est, P_est, u_seq, u0)."""
+    C, H, dt = loop.C, loop.H, loop.tick_dt
+    f = loop.plant.push(k * dt)
+    x_true = np.stack([O.dynamics_short(pu, x_true[c], u0[c], dt, f) for c in range(C)])
+    if z is None:
+        z = np.stack([O.hx(O.MODEL_NL6_UKF, pu, x_true[c]) for c in range(C)]) + noise * PlantR
+    x_est, P_est, st = O.ukf_step_batch(O.MODEL_NL6_UKF, pu, x_est, P_est, Q, R, u0, z, dt, O.SQRT_EIG, O.ORDER_LIBRARY)
+    assert not st.any()
+    u_seq = u_seq.copy()
+    for c in range(C):
+        s, u_new, info, _ = O.mppi_compute(O.MODEL_NL6, pm, loop.K, H, loop.LAMBDA, loop.R_U, loop.LIMIT[0], loop.LIMIT[1],
+                                           x_est[c][[0, 1, 3, 4]], u_seq[c], eps[c])
+        u_seq[c] = u_new if s == 0 else 0.0
+    return x_true, z, x_est, P_est, u_seq, u_seq[:, 0].copy()
+
+
 def test_closed_loop_matches_the_oracle_schedule(gpu_required):
-    """C robots, MPPI noise replayed: every tick the GPU loop and an oracle loop (same plant, same sensor readings,
-    same noise) must agree on the applied control, the control sequence and the estimate."""
+    """C robots through mpcb_closed_loop_tick_replay (MPPI noise and sensor readings supplied): every tick the GPU loop and
+    an oracle loop (same plant, same readings, same noise) must agree on the true state, the applied control, the
+    control sequence and the estimate."""
     C, K, ticks = 3, 2048, 5
     rng = np.random.default_rng(99)
     x0 = np.zeros((C, 6))
     x0[:, 3] = [0.05, -0.08, 0.02]
     pm, pu = O.model_defaults(O.MODEL_NL6), O.model_defaults(O.MODEL_NL6_UKF)
     with ClosedLoopBatch(C, K, precision="f64", exact_ukf=True, x0=x0, seed=5) as loop:
-        H, DT, dt = loop.H, loop.DT, loop.tick_dt
+        H, dt = loop.H, loop.tick_dt
         Q, R, P0 = O.ukf_default_noise(O.MODEL_NL6_UKF, dt)
         x_true, x_est, P_est = x0.copy(), x0.copy(), np.tile(P0, (C, 1, 1))
         u_seq, u0 = np.zeros((C, H)), np.zeros(C)
         for k in range(ticks):
             eps = loop.R_U * rng.standard_normal((C, K, H))
-            # oracle side of the tick (same order as ClosedLoopBatch.tick)
-            f = loop.plant.push(k * dt)
-            x_true = np.stack([O.dynamics_short(pu, x_true[c], u0[c], dt, f) for c in range(C)])
-            z = np.stack([O.hx(O.MODEL_NL6_UKF, pu, x_true[c]) for c in range(C)]) + rng.normal(0, 1, (C, 5)) * PlantR
-            x_est, P_est, st = O.ukf_step_batch(O.MODEL_NL6_UKF, pu, x_est, P_est, Q, R, u0, z, dt, O.SQRT_EIG, O.ORDER_LIBRARY)
-            assert not st.any()
-            for c in range(C):
-                s, u_new, info, _ = O.mppi_compute(O.MODEL_NL6, pm, K, H, loop.LAMBDA, loop.R_U, loop.LIMIT[0], loop.LIMIT[1],
-                                                   x_est[c][[0, 1, 3, 4]], u_seq[c], eps[c])
-                u_seq[c] = u_new if s == 0 else 0.0
-            u0 = u_seq[:, 0].copy()
+            x_true, z, x_est, P_est, u_seq, u0 = _oracle_tick(loop, pm, pu, Q, R, x_true, x_est, P_est, u_seq, u0, k, eps,
+                                                              noise=rng.normal(0, 1, (C, 5)))
             # GPU side, fed the same sensor readings and noise
             u0_g = loop.tick(eps=eps, z=z)
             xg, Pg = loop.estimate()
-            assert np.allclose(loop.x, x_true, rtol=1e-12, atol=1e-14)  # numpy plant == oracle plant
+            assert np.allclose(loop.x, x_true, rtol=1e-12, atol=1e-14)  # device plant == oracle plant
             # per-tick parity of the coupled parts: UKF 1e-6 on this ill-conditioned n = 6 filter (the sigma weights
             # amplify rounding 1.7e5 x per step, SURVEY.md 7.2), MPPI 1e-6 on the estimate it was given
             assert rel(xg, x_est) < 1e-7 and rel(Pg, P_est) < 1e-6, (k, rel(xg, x_est), rel(Pg, P_est))
@@ -81,13 +90,65 @@ def test_closed_loop_matches_the_oracle_schedule(gpu_required):
             assert rel(u0_g, u0) < 1e-6
             # the filter multiplies any difference ~200 x per tick, so both sides continue from the oracle's state:
             # every tick is then a fresh per-step comparison of the whole coupled tick
-            loop.x = x_true.copy()
-            loop.ukf.set_state(x_est, P_est)
-            from mpc_rs_b200.closed_loop import _upload
-            _upload(loop.dev, loop.d_u[loop.cur], u_seq)
-            _upload(loop.dev, loop.d_u0, u0)
-            loop.u0 = u0.copy()
+            loop.set_truth(x_true)
+            loop.set_estimate(x_est, P_est)
+            loop.set_controls(u_seq)
             assert not loop.mppi_status().any()
+
+
+def test_closed_loop_device_sensor_and_sharding(gpu_required):
+    """Generate mode (device plant, device sensor noise, Philox MPPI noise): the readings the device sensor produced are
+    the oracle's hx of the device's true state plus noise of the right scale, and a batch sharded over two handles by
+    controller_offset reproduces the unsharded batch bit for bit (the noise counters use the global robot index)."""
+    C, K, ticks = 8, 1024, 4
+    rng = np.random.default_rng(3)
+    x0 = np.zeros((C, 6))
+    x0[:, 3] = rng.uniform(-0.1, 0.1, C)
+    pu = O.model_defaults(O.MODEL_NL6_UKF)
+    with ClosedLoopBatch(C, K, x0=x0, seed=11) as whole, ClosedLoopBatch(3, K, x0=x0[:3], seed=11) as lo, \
+            ClosedLoopBatch(5, K, x0=x0[3:], seed=11, controller_offset=3) as hi:
+        for k in range(ticks):
+            for loop in (whole, lo, hi):
+                loop.tick()
+            xw, zw = whole.x, whole.readings()
+            hx = np.stack([O.hx(O.MODEL_NL6_UKF, pu, xw[c]) for c in range(C)])
+            noise = (zw - hx) / PlantR
+            assert np.all(np.abs(noise) < 6.0) and np.any(np.abs(noise) > 0.05), noise
+            assert np.array_equal(np.vstack([lo.x, hi.x]), xw)
+            assert np.array_equal(np.vstack([lo.readings(), hi.readings()]), zw)
+            assert np.array_equal(np.vstack([lo.controls(), hi.controls()]), whole.controls())
+        assert whole.launches == ticks * 5  # plant+sensor, UKF, gather, MPPI, first control
+
+
+def test_closed_loop_config4_subset_parity(gpu_required):
+    """BASELINE config #4 at its named size — C = 4096 robots x K = 8192 samples — against the oracle on a subset: the first
+    64 robots of the big batch and a 64-robot batch (same seed, same initial states) walk the same trajectories (their
+    kernels split the samples differently, so sums differ at rounding level), and the 64-robot batch's tick, replayed
+    with the noise it drew, matches the oracle schedule."""
+    Cbig, Csub, K, ticks = 4096, 64, 8192, 3
+    rng = np.random.default_rng(20240004)
+    x0 = np.zeros((Cbig, 6))
+    x0[:, 3] = rng.uniform(-0.1, 0.1, Cbig)
+    pm, pu = O.model_defaults(O.MODEL_NL6), O.model_defaults(O.MODEL_NL6_UKF)
+    with ClosedLoopBatch(Cbig, K, x0=x0, seed=7, precision="f64") as big, ClosedLoopBatch(Csub, K, x0=x0[:Csub], seed=7, precision="f64") as sub:
+        big.tick(ticks)
+        sub.tick(ticks)
+        xb, xs = big.x[:Csub], sub.x
+        ub, us = big.controls()[:Csub], sub.controls()
+        eb, es = big.estimate()[0][:Csub], sub.estimate()[0]
+        assert not big.mppi_status().any() and not sub.mppi_status().any()
+        assert rel(xb, xs) < 1e-9 and rel(eb, es) < 1e-5 and rel(ub, us) < 1e-5, (rel(xb, xs), rel(eb, es), rel(ub, us))
+        # one more tick of the subset against the oracle, with the noise the MPPI kernel draws (dumped) and the device's readings
+        H, dt = sub.H, sub.tick_dt
+        Q, R, P0 = O.ukf_default_noise(O.MODEL_NL6_UKF, dt)
+        x_true, (x_est, P_est), u_seq, u0 = sub.x, sub.estimate(), sub.controls(), sub.applied()
+        eps = sub.R_U * rng.standard_normal((Csub, K, H))
+        z = np.stack([O.hx(O.MODEL_NL6_UKF, pu, O.dynamics_short(pu, x_true[c], u0[c], dt, sub.plant.push(sub.t))) for c in range(Csub)])
+        z = z + rng.normal(0, 1, (Csub, 5)) * PlantR
+        xt, z, xe, Pe, useq, u0n = _oracle_tick(sub, pm, pu, Q, R, x_true, x_est, P_est, u_seq, u0, sub.ticks, eps, z=z)
+        u0_g = sub.tick(eps=eps, z=z)
+        assert np.allclose(sub.x, xt, rtol=1e-12, atol=1e-14)
+        assert rel(sub.estimate()[0], xe) < 1e-6 and rel(sub.controls(), useq) < 1e-6 and rel(u0_g, u0n) < 1e-6
 
 
 PlantR = np.array([200.0, 200.0, 10.0, 0.05, 0.05])
