@@ -503,7 +503,7 @@ def run_gpu(args):
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             import oracle_lib as O
             threads = max(O.max_threads(), len(os.sched_getaffinity(0)))
-            Bc, Tc = 1 << 16, 10
+            Bc, Tc = 1 << 18, 41  # ~10 s of CPU work
             pu = O.model_defaults(O.MODEL_PEN_LIN)
             Qc, Rc, P0c = O.ukf_default_noise(O.MODEL_PEN_LIN, 0.0)
             xc, Pc = np.zeros((Bc, 4)), np.tile(P0c, (Bc, 1, 1))

@@ -324,7 +324,9 @@ mpcb_status mpcb_ukf_sync(mpcb_ukf* h);
 mpcb_status mpcb_ukf_get_status(mpcb_ukf* h, int32_t* s);
 void* mpcb_ukf_stream(mpcb_ukf* h);
 int64_t mpcb_ukf_launches(mpcb_ukf* h);
-/* raw SoA device pointers (x: [n][B], P: [n*n][B]) for zero-copy coupling with other device code */
+/* raw SoA device pointers (x: [n][B], P: [n*n][B]) for zero-copy coupling with other device code.  After a fused step
+ * (mpcb_ukf_step / mpcb_ukf_run_device) P is exactly symmetric and only its LOWER triangle (rows r >= columns c, entry
+ * r*n + c) is current in device memory; mpcb_ukf_get_state mirrors it. */
 double* mpcb_ukf_device_x(mpcb_ukf* h);
 double* mpcb_ukf_device_p(mpcb_ukf* h);
 

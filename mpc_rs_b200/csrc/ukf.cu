@@ -55,6 +55,7 @@ struct mpcb_ukf {
     double* d_z = nullptr;
     int* d_status = nullptr;
     bool predicted = false;
+    bool p_lower_only = false;  // the last fused step stored only the lower triangle of P: read-outs mirror it
     unsigned int enable = 0xffffffffu;  // sensor mask of the next update (examples/mppi4-ukf-commu.rs:279-293)
     int64_t launches = 0;
 };
@@ -422,6 +423,7 @@ mpcb_status mpcb_ukf_init(mpcb_ukf* h, const double* x, const double* P, const d
     MPCB_CUDA_TRY(cudaStreamSynchronize(h->stream));
     h->launches += 2;
     h->predicted = false;  // sigma_f starts as NaN in the reference (src/ukf.rs:32)
+    h->p_lower_only = false;
     return MPCB_OK;
 }
 
@@ -437,6 +439,7 @@ mpcb_status mpcb_ukf_set_state(mpcb_ukf* h, const double* x, const double* P) {
     if (P) {
         st = upload_aos(h, P, h->n * h->n, h->d_P);
         if (st != MPCB_OK) return st;
+        h->p_lower_only = false;
     }
     MPCB_CUDA_TRY(cudaMemsetAsync(h->d_status, 0, (size_t)h->B * sizeof(int), h->stream));
     MPCB_CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -462,6 +465,13 @@ mpcb_status mpcb_ukf_get_state_range(mpcb_ukf* h, int64_t first, int64_t count, 
         MPCB_CUDA_TRY(cudaMemcpyAsync(P, h->d_stage, (size_t)count * W * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         MPCB_CUDA_TRY(cudaStreamSynchronize(h->stream));
         h->launches += 1;
+        if (h->p_lower_only) {
+            // the fused kernels store only the lower triangle of the exactly symmetric P: mirror it for the caller
+            const int n = h->n;
+            for (int64_t b = 0; b < count; ++b)
+                for (int r = 0; r < n; ++r)
+                    for (int c = r + 1; c < n; ++c) P[(b * n + r) * n + c] = P[(b * n + c) * n + r];
+        }
     }
     return MPCB_OK;
 }
@@ -528,6 +538,7 @@ mpcb_status mpcb_ukf_predict(mpcb_ukf* h, const double* u, double u_scalar, doub
     st = stage_u(h, u, u_scalar, &p);
     if (st != MPCB_OK) return st;
     st = launch(h, h->k_predict, p);
+    h->p_lower_only = false;  // predict writes the whole (not exactly symmetric) P
     if (st != MPCB_OK) return st;
     MPCB_CUDA_TRY(cudaStreamSynchronize(h->stream));
     h->predicted = true;
@@ -561,6 +572,9 @@ mpcb_status mpcb_ukf_step(mpcb_ukf* h, const double* u, double u_scalar, double 
     if (st != MPCB_OK) return st;
     st = stage_z(h, z, &p);
     if (st != MPCB_OK) return st;
+    p.lower_only = getenv("MPCB_UKF_FULL_P") ? 0 : 1;
+    p.use_tma = (h->B % 4 == 0 && ((uintptr_t)p.z % 16) == 0 && (!p.has_u || ((uintptr_t)p.u % 8) == 0) && !getenv("MPCB_UKF_NO_TMA")) ? 1 : 0;
+    if (p.lower_only) h->p_lower_only = true;
     st = launch(h, h->k_fused, p);
     if (st != MPCB_OK) return st;
     MPCB_CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -583,6 +597,11 @@ mpcb_status mpcb_ukf_run_device(mpcb_ukf* h, int32_t steps, const double* d_u, d
     p.u_scalar = u_scalar;
     p.z = d_z;
     h->predicted = false;
+    // fused step: P comes out exactly symmetric, only its lower triangle goes back to memory; the tile rows are staged with
+    // TMA bulk copies when every row start is 16-byte aligned
+    p.lower_only = getenv("MPCB_UKF_FULL_P") ? 0 : 1;
+    p.use_tma = (h->B % 4 == 0 && ((uintptr_t)d_z % 16) == 0 && !getenv("MPCB_UKF_NO_TMA")) ? 1 : 0;
+    if (p.lower_only) h->p_lower_only = true;
     return launch(h, h->k_fused, p);
 }
 

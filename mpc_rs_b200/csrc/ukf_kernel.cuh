@@ -36,6 +36,8 @@ struct UkfParams {
     double u_scalar;
     double dt;
     unsigned int enable;  // sensor bit mask: hx rows of cleared bits read 0 (examples/mppi4-ukf-commu.rs:279-293)
+    int use_tma;           // fused n = 4 kernels: stage the tile rows with cp.async.bulk (needs B % 4 == 0 and 16-byte aligned x, P, z, status)
+    int lower_only;        // fused kernels: store only the lower triangle of the (exactly symmetric) P; readers mirror it
     unsigned int reverse;  // 1: walk the tiles from the end (alternates per launch: the tiles the previous launch wrote last are still in L2)
     double wm0, wc0, wi, cC;  // sigma_weight (src/ukf.rs:112-118), C = alpha^2 (n + kappa)
     double Q[36];
@@ -510,6 +512,33 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int KEEP>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(KEEP) : "memory"); }
 
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) + mbarrier: ONE thread stages a whole SoA row of the tile ----
+__device__ __forceinline__ void ukf_mbar_init(unsigned long long* bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ukf_mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ukf_mbar_wait(unsigned long long* bar, unsigned int parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "UW_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra UD_%=;\n"
+        "bra UW_%=;\n"
+        "UD_%=:\n"
+        "}\n" ::"r"(addr), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void ukf_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned int bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
 constexpr int kUkfThreads = 128;
 
 // One thread per filter, a block walks tiles of 128 filters (grid-stride).  The fused predict+update kernel of the
@@ -526,8 +555,9 @@ __global__ void __launch_bounds__(kUkfThreads) ukf_kernel(const __grid_constant_
     constexpr int NTRI = N * (N + 1) / 2;
     constexpr int ROWS = N + NTRI + O;
     constexpr bool PIPE = (MODE == UKF_FUSED) && (2 * ROWS * kUkfThreads * 8 + 2 * kUkfThreads * 4 <= 48 * 1024);
-    __shared__ double s_in[PIPE ? 2 : 1][PIPE ? ROWS : 1][PIPE ? kUkfThreads : 1];
-    __shared__ int s_st[PIPE ? 2 : 1][PIPE ? kUkfThreads : 1];
+    __shared__ __align__(128) double s_in[PIPE ? 2 : 1][PIPE ? ROWS : 1][PIPE ? kUkfThreads : 1];
+    __shared__ __align__(128) int s_st[PIPE ? 2 : 1][PIPE ? kUkfThreads : 1];
+    __shared__ __align__(8) unsigned long long s_bar[2];
     const long long B = p.B;
     const int tid = threadIdx.x;
     const long long ntiles = (B + kUkfThreads - 1) / kUkfThreads;
@@ -547,9 +577,37 @@ __global__ void __launch_bounds__(kUkfThreads) ukf_kernel(const __grid_constant_
             cp_async4(&s_st[slot][tid], p.status + bb);
         }
     };
+    // the same with TMA: thread 0 issues one bulk copy per SoA row of the tile (1 KB each, 512 B for the status row) that
+    // complete on the slot's mbarrier — 18 instructions of one thread instead of 18 LDGSTS of every thread
+    const bool tma = PIPE && p.use_tma != 0;
+    auto prefetch_tma = [&](long long tile, int slot) {
+        const long long b0 = (p.reverse ? ntiles - 1 - tile : tile) * kUkfThreads;
+        const unsigned int cnt = (unsigned int)((B - b0 < kUkfThreads) ? (B - b0) : kUkfThreads);
+        ukf_mbar_expect_tx(&s_bar[slot], cnt * 8u * ROWS + cnt * 4u);
+#pragma unroll
+        for (int r = 0; r < N; ++r) ukf_bulk_g2s(&s_in[slot][r][0], p.x + (long long)r * B + b0, cnt * 8u, &s_bar[slot]);
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+#pragma unroll
+            for (int c = 0; c <= r; ++c)
+                ukf_bulk_g2s(&s_in[slot][N + r * (r + 1) / 2 + c][0], p.P + (long long)(r * N + c) * B + b0, cnt * 8u, &s_bar[slot]);
+#pragma unroll
+        for (int c = 0; c < O; ++c) ukf_bulk_g2s(&s_in[slot][N + NTRI + c][0], p.z + (long long)c * B + b0, cnt * 8u, &s_bar[slot]);
+        ukf_bulk_g2s(&s_st[slot][0], p.status + b0, cnt * 4u, &s_bar[slot]);
+    };
     if constexpr (PIPE) {
-        if ((long long)blockIdx.x < ntiles) prefetch(blockIdx.x, 0);
-        cp_async_commit();
+        if (tma) {
+            if (tid == 0) {
+                ukf_mbar_init(&s_bar[0], 1);
+                ukf_mbar_init(&s_bar[1], 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncthreads();
+            if (tid == 0 && (long long)blockIdx.x < ntiles) prefetch_tma(blockIdx.x, 0);
+        } else {
+            if ((long long)blockIdx.x < ntiles) prefetch(blockIdx.x, 0);
+            cp_async_commit();
+        }
     }
 
   int it = 0;
@@ -560,9 +618,13 @@ __global__ void __launch_bounds__(kUkfThreads) ukf_kernel(const __grid_constant_
     int st = MPCB_OK;
     if constexpr (PIPE) {
         const int slot = it & 1;
-        if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x, slot ^ 1);
-        cp_async_commit();   // one group per iteration (possibly empty): wait<1> always means "this tile has landed"
-        cp_async_wait<1>();
+        if (tma) {
+            ukf_mbar_wait(&s_bar[slot], (unsigned int)(it >> 1) & 1u);  // use number it/2 of this slot
+        } else {
+            if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x, slot ^ 1);
+            cp_async_commit();   // one group per iteration (possibly empty): wait<1> always means "this tile has landed"
+            cp_async_wait<1>();
+        }
         if (live) {
             st = s_st[slot][tid];
 #pragma unroll
@@ -573,6 +635,12 @@ __global__ void __launch_bounds__(kUkfThreads) ukf_kernel(const __grid_constant_
                 for (int c = 0; c < N; ++c) P[r][c] = (c <= r) ? s_in[slot][N + r * (r + 1) / 2 + c][tid] : 0.0;
 #pragma unroll
             for (int c = 0; c < O; ++c) z0[c] = s_in[slot][N + NTRI + c][tid];
+        }
+        if (tma) {
+            // every thread has taken its values out of `slot` (and, one iteration ago, out of the other buffer): only now may
+            // thread 0 let the TMA overwrite the other buffer with the tile after this one
+            __syncthreads();
+            if (tid == 0 && tile + gridDim.x < ntiles) prefetch_tma(tile + gridDim.x, slot ^ 1);
         }
     } else if (live) {
         st = p.status[b];
@@ -779,10 +847,13 @@ __global__ void __launch_bounds__(kUkfThreads) ukf_kernel(const __grid_constant_
     if (p_full) {
 #pragma unroll
         for (int r = 0; r < N; ++r) p.x[(long long)r * B + b] = x[r];
+        // after an update P is exactly symmetric (src/ukf.rs:73 symmetrises it): with lower_only the strictly-upper
+        // triangle stays in memory as it was — predict never reads it, and the read-out calls mirror the lower one
 #pragma unroll
         for (int r = 0; r < N; ++r)
 #pragma unroll
-            for (int c = 0; c < N; ++c) p.P[(long long)(r * N + c) * B + b] = P[r][c];
+            for (int c = 0; c < N; ++c)
+                if (c <= r || !(MODE == UKF_FUSED && p.lower_only)) p.P[(long long)(r * N + c) * B + b] = P[r][c];
     }
     if constexpr (MODE == UKF_PREDICT) {
 #pragma unroll
