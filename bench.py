@@ -55,10 +55,11 @@ FLOPS_PER_STEP = 60.0  # model NL 58 + 2 epilogue flops per roll
 UKF_B = 1 << 20
 UKF_T = 100  # T = 100 steps, as examples/ukf-pen.rs:154-178 runs
 UKF_BYTES = 336.0  # 8*(2n + 2n^2 + o), n=4, o=2
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures of these kernels
-# (profiles/mppi_r1_final2_ncu_full_summary.txt, profiles/ukf_r1_pipe_ncu_full_summary.txt)
-MPPI_DRAM_TRAFFIC_BYTES = 87_296 + 0
-UKF_DRAM_TRAFFIC_BYTES = 138_434_048 + 114_366_976
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from this round's ncu --set full captures of these kernels
+# (profiles/mppi_r2_ncu_full_summary.txt, profiles/ukf_r2_ncu_full_summary.txt; tools/prof_round.sh) — the one roofline
+# field that cannot be measured inside this run
+MPPI_DRAM_TRAFFIC_BYTES = 73_728 + 0
+UKF_DRAM_TRAFFIC_BYTES = 138_444_032 + 63_853_568
 FP32_FALLBACK_TFLOPS = 69.5  # tools/peak_bench on this pool's B200 (profiles/peaks_r1.json)
 FP64_FALLBACK_TFLOPS = 33.9
 METRIC = "mppi_rollout_steps_per_sec"
@@ -574,25 +575,21 @@ def run_gpu(args):
     peaks = measured_peaks()
     ach_tflops = K_PER_GPU * H * FLOPS_PER_STEP / (kern_ms * 1e-3) / 1e12
     roof = {
-        "bound": "fp32", "kernel": "mppi_rollout_kernel<ModelNL,float,256 threads x 2 samples (packed f32x2),generate,v tile>",
+        "bound": "fp32", "kernel": "mppi_ws_kernel<ModelNL, 7 packed consumer warps + 9 producer warps, generate> (csrc/mppi_ws_kernel.cuh)",
         "achieved": ach_tflops, "peak": peaks["fp32_tflops"], "unit": "TFLOP/s", "frac": ach_tflops / peaks["fp32_tflops"],
-        "traffic": MPPI_DRAM_TRAFFIC_BYTES, "kernel_ms": kern_ms,
-        # instruction-level view of the same kernel from the committed ncu --set full capture (not measured in this run)
-        "ncu": {"fma_pipe_cycles_active_pct": 46.4, "alu_pipe_inst_pct": 34.0, "xu_pipe_inst_pct": 22.2, "issue_active_pct": 50.7,
-                "registers": 122, "source": "profiles/mppi_r1_final2_ncu_full_summary.txt"},
+        "traffic": MPPI_DRAM_TRAFFIC_BYTES, "kernel_ms": kern_ms, "kernel_ms_with_l2_flush": total_ms / args.steps,
         "note": f"{FLOPS_PER_STEP:.0f} algorithmic FP32 flops per rollout-step (SURVEY.md 8d) x {K_PER_GPU * H} steps per launch; "
-                f"peak = {peaks['fp32_source']}; neither 'hbm' nor 'tensor' bounds this kernel: it issues FP32/MUFU "
-                "instructions and moves 87 KB of DRAM per launch (traffic, bytes, ncu); kernel_ms = back-to-back launches "
-                "without the L2 flush" + ("; at N > 1 it includes the in-kernel cross-GPU exchange" if world > 1 else ""),
+                f"peak = {peaks['fp32_source']}; neither 'hbm' nor 'tensor' bounds this kernel: it is bound by the SM's instruction "
+                "dispatch (66 issued instructions per rollout-step, DESIGN.md 4.1) and moves 74 KB of DRAM per launch (traffic: bytes, "
+                "this round's ncu capture); kernel_ms = back-to-back launches enqueued from compiled code, no L2 flush"
+                + ("; at N > 1 it includes the in-kernel cross-GPU exchange" if world > 1 else ""),
     }
     if ukf_out and "value" in ukf_out:
         gbs = ukf_out["value"] / world * UKF_BYTES / 1e9
         ukf_out["roofline"] = {"bound": "hbm", "kernel": "ukf_kernel<4,2,PEN_LIN,cholesky,interleaved,fused>", "achieved": gbs,
                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": UKF_DRAM_TRAFFIC_BYTES,
-                               "ncu": {"fp64_pipe_cycles_active_pct": 59.8, "dram_throughput_pct": 50.7, "issue_active_pct": 52.6,
-                                       "registers": 162, "source": "profiles/ukf_r1_pipe_ncu_full_summary.txt"},
                                "note": f"{UKF_BYTES:.0f} algorithmic bytes per filter-update (x, full P in and out, z: SURVEY.md 8d); the "
-                                       "kernel does not read the strictly-upper triangle of P (predict never uses it), so the DRAM "
+                                       "kernel neither reads nor writes the strictly-upper triangle of the exactly symmetric P, so the DRAM "
                                        f"traffic is lower than the algorithmic figure; peak = {peaks['hbm_source']}; "
                                        f"FP64 pipe peak {peaks['fp64_tflops']:.1f} TFLOP/s ({peaks['fp32_source']})"}
     cpu_val, cpu_info = cpu_baseline(None, 2, budget_s=12.0) if world == 1 else (None, None)

@@ -409,3 +409,29 @@ def test_svd_square_root_three_ways():
         spread.append(worst)
     assert spread[0] < 1e-6, spread  # one step: rounding x the 1.7e5 weight amplification
     assert all(s < 1.0 for s in spread)  # and it grows: per-step comparison is the only meaningful one (finding 5)
+
+
+def test_fp32_twin_bounds_what_fp32_can_reach():
+    """The precision policy, shown with the oracle's FP32 twin — the reference's own formula order evaluated
+    in IEEE FP32 without FMA: on models L and NL (shipped horizon, random start angles, K = 8192) it stays within ~2e-5 of the
+    f64 controls (the CUDA FP32 path, with host-folded constants and FMA, is held to 1e-5 on the reference's shapes by the
+    GPU suite); on model NL6 at its shipped DT = 0.15 (the pendulum's error doubles every step of that horizon) it is
+    3e-5 .. 9e-4 on half of the seeds — an order of magnitude worse, so no FP32 kernel can be held to 1e-5 there and
+    BASELINE config #4 is reported in FP64 (the default for NL6)."""
+    def twin_err(oid, dt, K, H, lam, sig, lim, seeds):
+        p = O.model_defaults(oid, dt=dt)
+        errs = []
+        for seed in seeds:
+            rng = np.random.default_rng(seed)
+            x = np.array([0.0, 0.0, rng.uniform(-0.1, 0.1), 0.0])
+            u = rng.uniform(-2, 2, H) if seed % 2 else np.zeros(H)
+            eps = (sig * rng.standard_normal((K, H))).astype(np.float32).astype(np.float64)
+            _, u64, i64, _ = O.mppi_compute(oid, p, K, H, lam, sig, lim[0], lim[1], x, u, eps)
+            _, u32, i32, _ = O.mppi_compute(oid, p, K, H, lam, sig, lim[0], lim[1], x, u, eps, f32=True)
+            errs.append(np.linalg.norm(u32 - u64) / np.linalg.norm(u64))
+        return np.array(errs)
+    e_l = twin_err(O.MODEL_L, 0.1, 8192, 8, 0.5, 3.0, (-20.0, 20.0), range(6))
+    e_nl = twin_err(O.MODEL_NL, 0.1, 8192, 8, 0.5, 3.0, (-20.0, 20.0), range(6))
+    e_nl6 = twin_err(O.MODEL_NL6, 0.15, 8192, 8, 1.4, 4.0, (-10.0, 10.0), range(12))
+    assert e_l.max() < 5e-5 and e_nl.max() < 5e-5, (e_l, e_nl)
+    assert e_nl6.max() > 1e-4 and np.sum(e_nl6 > 1e-5) >= 4 and e_nl6.max() < 5e-3, e_nl6
