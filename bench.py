@@ -227,7 +227,7 @@ def closed_loop_leg(dev, rank, world, barrier, max_over_ranks):
     out = {"config": {"workload": f"BASELINE configs[3]: examples/mppi4-non-liner-ukf.rs closed loop, C={CL_C} robots (sharded x{world}) x "
                                   f"K={CL_K} samples x H=8 (model NL6 + UKF NL6_UKF), fixed tick 0.01 s, MPPI fed the UKF estimate, "
                                   f"{CL_TICKS} ticks through mpcb_closed_loop_tick", "controllers": CL_C, "samples": CL_K, "horizon": 8}}
-    for prec in ("f64", "f32"):
+    for prec in ("f64fast", "f64", "f32"):
         with ClosedLoopBatch(hi - lo, CL_K, x0=x0[lo:hi], seed=20240004, precision=prec, device=dev, controller_offset=lo) as loop:
             loop.tick(5)
             loop.sync()
@@ -241,7 +241,13 @@ def closed_loop_leg(dev, rank, world, barrier, max_over_ranks):
             out[prec] = {"value": CL_C * CL_K * 8 * CL_TICKS / el, "unit": UNIT, "ms_per_tick": el / CL_TICKS * 1e3,
                          "filter_updates_per_sec": CL_C * CL_TICKS / el, "gpu_launches": int(loop.launches - l0),
                          "upright_on_rank0": f"{up}/{hi - lo}", "mppi_failures_on_rank0": bad}
-    out["f64"]["note"] = "the default precision for model NL6 (FP64 rollouts reproduce the f64 reference to 1e-9)"
+    out["f64fast"]["note"] = ("the default precision for model NL6 (MPCB_F64_FAST): every operation FP64, the FP32 kernels' folded "
+                              "formulas with one reciprocal per step and FMA; controls within 1e-9 of the f64 reference, same argmin "
+                              "(tests/test_mppi_gpu.py::test_replay_parity_f64_fast)")
+    out["f64fast"]["roofline"] = {"bound": "fp64", "flops_per_rollout_step": 72.0,
+                                  "achieved": out["f64fast"]["value"] / world * 72.0 / 1e12, "unit": "TFLOP/s",
+                                  "note": "72 algorithmic flops per NL6 rollout-step (SURVEY.md 8d), FP64; whole tick incl. plant, sensor and UKF"}
+    out["f64"]["note"] = "MPCB_F64: the reference's operation order without FMA contraction (bit-level twin of the f64 oracle up to libm)"
     out["f32"]["note"] = ("FP32 rollouts: on model NL6 at its shipped DT = 0.15 the FP32 controls are 1e-4..1e-3 from the f64 "
                           "reference (the model is chaotic inside its horizon, DESIGN.md 4.1) - reported, not the parity path")
     out["f32"]["roofline"] = {"bound": "fp32", "flops_per_rollout_step": 72.0,
@@ -284,7 +290,7 @@ def sweep_leg(dev, rank, world, barrier, max_over_ranks, A, Mppi, models, torch,
         ms = max_over_ranks(e0.elapsed_time(e1) / steps)
         info = m.last_info()[0]
         rows.append({"K": K, "ms_per_step": ms, "value": K * Hs / (ms * 1e-3), "status": int(info["status"]),
-                     "frac_fp32_roofline_per_gpu": K * Hs / (ms * 1e-3) / world * FLOPS_PER_STEP / 1e12})
+                     "tflops_fp32_algorithmic_per_gpu": K * Hs / (ms * 1e-3) / world * FLOPS_PER_STEP / 1e12})
         for q in (d_x, d_a, d_b):
             A.lib().mpcb_device_free(dev, q)
         m.close()
@@ -573,6 +579,9 @@ def run_gpu(args):
         return 0
 
     peaks = measured_peaks()
+    if isinstance(sweep, dict):
+        for row in sweep.get("points", []):  # the same FP32 roofline as the headline kernel, per sweep point
+            row["frac_fp32_roofline_per_gpu"] = row["tflops_fp32_algorithmic_per_gpu"] / peaks["fp32_tflops"]
     ach_tflops = K_PER_GPU * H * FLOPS_PER_STEP / (kern_ms * 1e-3) / 1e12
     roof = {
         "bound": "fp32", "kernel": "mppi_ws_kernel<ModelNL, 7 packed consumer warps + 9 producer warps, generate> (csrc/mppi_ws_kernel.cuh)",

@@ -58,7 +58,7 @@ if __name__ == "__main__":
     ap.add_argument("--seconds", type=float, default=3.0)
     ap.add_argument("--truth", action="store_true", help="DEBUG_UKF = true: feed the controller the true state")
     ap.add_argument("--csv", default="logs/mppi/mppi.csv")
-    ap.add_argument("--precision", choices=["f32", "f64"], default=None,
-                    help="MPPI arithmetic; default f64 for this model (DESIGN.md 4.1 precision policy), f32 is ~20x faster")
+    ap.add_argument("--precision", choices=["f32", "f64", "f64fast"], default=None,
+                    help="MPPI arithmetic; default f64fast for this model (DESIGN.md 4.1 precision policy): FP64 folded form, 1e-9 from the reference; f64 = reference order (2x slower), f32 (2x faster) misses 1e-5 on this model")
     a = ap.parse_args()
     run(a.controllers, a.samples, a.seconds, a.truth, a.csv, precision=a.precision)

@@ -95,7 +95,12 @@ mpcb_status mpcb_model_defaults(int32_t model_id, mpcb_model_params* out);
 
 typedef enum mpcb_precision {
     MPCB_F32 = 0, /* FP32 dynamics/cost/noise, FP64 cost accumulation + softmax + weighted mean */
-    MPCB_F64 = 1  /* everything FP64, no FMA contraction: reference arithmetic */
+    MPCB_F64 = 1, /* everything FP64, no FMA contraction: reference arithmetic */
+    /* Everything FP64 in the folded form of the FP32 kernels: host-folded constants, one reciprocal per step instead of
+     * the reference's divisions, sincos(), FMA contraction.  Differs from the reference order by FP64 rounding times
+     * the model's error growth (model NL6 at its shipped DT: ~1e-11 on the controls); about half the FP64 instructions
+     * of MPCB_F64.  Built-in models only; replay / dump noise is f64 like MPCB_F64. */
+    MPCB_F64_FAST = 2
 } mpcb_precision;
 
 typedef enum mpcb_dtype { MPCB_DT_F32 = 0, MPCB_DT_F64 = 1 } mpcb_dtype;
@@ -354,7 +359,7 @@ typedef struct mpcb_closed_loop_cfg {
     double tick_dt;            /* fixed tick, seconds (0.01: the example's sensor period, :267-268) */
     uint64_t seed;
     int32_t use_estimate;      /* 1: MPPI is fed the UKF estimate; 0: the truth (DEBUG_UKF = true, :31,55-57) */
-    int32_t precision;         /* MPCB_F32 / MPCB_F64 for the MPPI rollouts; anything else = the model's default */
+    int32_t precision;         /* MPCB_F32 / MPCB_F64 / MPCB_F64_FAST for the MPPI rollouts; anything else = the model's default */
     int32_t exact_ukf;         /* mpcb_ukf_cfg.exact */
     int32_t device;
 } mpcb_closed_loop_cfg;

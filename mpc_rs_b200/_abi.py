@@ -17,7 +17,8 @@ OK, NO_FINITE_COST, SUM_ZERO, U_INVALID, INVERSE_FAIL, CHOLESKY_FAIL, BAD_ARG, C
 MODEL_L, MODEL_NL, MODEL_NL6, MODEL_USER = 0, 1, 2, 3
 USER_PARAMS = 24
 MODEL_PEN_LIN, MODEL_PEN_NL, MODEL_PEN6, MODEL_NL6_UKF, MODEL_USER_UKF = 16, 17, 18, 19, 20
-F32, F64 = 0, 1
+F32, F64, F64_FAST = 0, 1, 2
+PRECISIONS = {"f32": F32, "f64": F64, "f64fast": F64_FAST}
 DT_F32, DT_F64 = 0, 1
 SQRT_CHOLESKY, SQRT_EIG = 0, 1
 ORDER_LIBRARY, ORDER_INTERLEAVED = 0, 1

@@ -46,7 +46,7 @@ class ClosedLoopBatch:
         A.check(L.mpcb_closed_loop_default_cfg(C.byref(cfg)))
         cfg.controllers, cfg.samples, cfg.controller_offset = self.C, self.K, int(controller_offset)
         cfg.tick_dt, cfg.seed, cfg.use_estimate = self.tick_dt, int(seed), int(self.use_estimate)
-        cfg.precision = {"f32": A.F32, "f64": A.F64}.get(precision, -1)
+        cfg.precision = A.PRECISIONS.get(precision, -1)
         cfg.exact_ukf, cfg.device = int(bool(exact_ukf)), self.dev
         self._h = A._H()
         A.check(L.mpcb_closed_loop_create(C.byref(self._h), C.byref(cfg)))

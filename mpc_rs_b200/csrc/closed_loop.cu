@@ -245,7 +245,7 @@ mpcb_status mpcb_closed_loop_create(mpcb_closed_loop** out, const mpcb_closed_lo
     mc.controllers = cfg->controllers;
     mc.seed = cfg->seed;
     mc.device = cfg->device;
-    if (cfg->precision == MPCB_F32 || cfg->precision == MPCB_F64) mc.precision = cfg->precision;
+    if (cfg->precision == MPCB_F32 || cfg->precision == MPCB_F64 || cfg->precision == MPCB_F64_FAST) mc.precision = cfg->precision;
     h->H = mc.horizon;
     st = mpcb_mppi_create(&h->mppi, &mc);
     if (st != MPCB_OK) return fail(st);

@@ -1608,5 +1608,6 @@ using MppiKernelFn = void (*)(const MppiParams);
 MppiKernelFn mppi_kernel_f32(int model_id, int block, int noise, int vt);
 MppiKernelFn mppi_kernel_f32x2(int model_id, int block, int noise, int vt);  // two samples per thread (block threads = 2*block samples)
 MppiKernelFn mppi_kernel_f64(int model_id, int block, int noise, int vt);
+MppiKernelFn mppi_kernel_f64fast(int model_id, int block, int noise, int vt);  // MPCB_F64_FAST (models.cuh, Model*F)
 
 }  // namespace mpcb

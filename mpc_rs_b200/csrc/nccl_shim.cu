@@ -24,42 +24,51 @@ struct Api {
     AllGatherFn all_gather = nullptr;
     CommDestroyFn comm_destroy = nullptr;
     GetErrorStringFn get_error_string = nullptr;
-    bool tried = false;
+    const char* why = nullptr;  // set when the library is unusable
 };
-Api g_api;
 
-mpcb_status load() {
-    if (g_api.lib) return MPCB_OK;
-    if (g_api.tried) {
-        set_error("NCCL library not available");
-        return MPCB_NCCL_ERROR;
-    }
-    g_api.tried = true;
+// Resolved once, by the first caller, behind the C++11 function-local-static guard: handles are Send and two
+// threads may reach NCCL at the same time (like nvrtc_api() / library_api()).
+Api load_api() {
+    Api a;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* n : names) {
-        g_api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
-        if (g_api.lib) break;
+        a.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (a.lib) break;
     }
-    if (!g_api.lib) {
-        set_error("dlopen(libnccl.so.2) failed: %s", dlerror());
-        return MPCB_NCCL_ERROR;
+    if (!a.lib) {
+        a.why = "dlopen(libnccl.so.2) failed";
+        return a;
     }
-    g_api.get_unique_id = (GetUniqueIdFn)dlsym(g_api.lib, "ncclGetUniqueId");
-    g_api.comm_init_rank = (CommInitRankFn)dlsym(g_api.lib, "ncclCommInitRank");
-    g_api.all_gather = (AllGatherFn)dlsym(g_api.lib, "ncclAllGather");
-    g_api.comm_destroy = (CommDestroyFn)dlsym(g_api.lib, "ncclCommDestroy");
-    g_api.get_error_string = (GetErrorStringFn)dlsym(g_api.lib, "ncclGetErrorString");
-    if (!g_api.get_unique_id || !g_api.comm_init_rank || !g_api.all_gather || !g_api.comm_destroy) {
-        set_error("NCCL symbols missing");
-        g_api.lib = nullptr;
-        return MPCB_NCCL_ERROR;
+    a.get_unique_id = (GetUniqueIdFn)dlsym(a.lib, "ncclGetUniqueId");
+    a.comm_init_rank = (CommInitRankFn)dlsym(a.lib, "ncclCommInitRank");
+    a.all_gather = (AllGatherFn)dlsym(a.lib, "ncclAllGather");
+    a.comm_destroy = (CommDestroyFn)dlsym(a.lib, "ncclCommDestroy");
+    a.get_error_string = (GetErrorStringFn)dlsym(a.lib, "ncclGetErrorString");
+    if (!a.get_unique_id || !a.comm_init_rank || !a.all_gather || !a.comm_destroy) {
+        a.why = "NCCL symbols missing";
+        a.lib = nullptr;
+        a.all_gather = nullptr;
+        a.comm_destroy = nullptr;
     }
-    return MPCB_OK;
+    return a;
+}
+
+const Api& api() {
+    static const Api a = load_api();
+    return a;
+}
+
+mpcb_status load() {
+    const Api& a = api();
+    if (a.lib) return MPCB_OK;
+    set_error("NCCL library not available: %s", a.why ? a.why : "unknown");
+    return MPCB_NCCL_ERROR;
 }
 
 mpcb_status check(int rc, const char* what) {
     if (rc == 0) return MPCB_OK;
-    set_error("%s failed: %s", what, g_api.get_error_string ? g_api.get_error_string(rc) : "nccl error");
+    set_error("%s failed: %s", what, api().get_error_string ? api().get_error_string(rc) : "nccl error");
     return MPCB_NCCL_ERROR;
 }
 
@@ -69,7 +78,7 @@ mpcb_status nccl_unique_id(char id[128]) {
     mpcb_status st = load();
     if (st != MPCB_OK) return st;
     UniqueId u;
-    st = check(g_api.get_unique_id(&u), "ncclGetUniqueId");
+    st = check(api().get_unique_id(&u), "ncclGetUniqueId");
     if (st != MPCB_OK) return st;
     memcpy(id, u.internal, 128);
     return MPCB_OK;
@@ -80,19 +89,19 @@ mpcb_status nccl_init_rank(void** comm, const char id[128], int rank, int world)
     if (st != MPCB_OK) return st;
     UniqueId u;
     memcpy(u.internal, id, 128);
-    return check(g_api.comm_init_rank(comm, world, u, rank), "ncclCommInitRank");
+    return check(api().comm_init_rank(comm, world, u, rank), "ncclCommInitRank");
 }
 
 mpcb_status nccl_all_gather(void* comm, const double* send, double* recv, size_t count, cudaStream_t stream) {
-    if (!comm || !g_api.all_gather) {
+    if (!comm || !api().all_gather) {
         set_error("no NCCL communicator attached");
         return MPCB_NCCL_ERROR;
     }
-    return check(g_api.all_gather(send, recv, count, /*ncclFloat64*/ 8, comm, stream), "ncclAllGather");
+    return check(api().all_gather(send, recv, count, /*ncclFloat64*/ 8, comm, stream), "ncclAllGather");
 }
 
 void nccl_destroy(void* comm) {
-    if (comm && g_api.comm_destroy) g_api.comm_destroy(comm);
+    if (comm && api().comm_destroy) api().comm_destroy(comm);
 }
 
 }  // namespace mpcb

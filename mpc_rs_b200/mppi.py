@@ -76,8 +76,8 @@ class Mppi:
         cfg = A.MppiCfg()
         A.check(L.mpcb_mppi_default_cfg(model.model_id, C.byref(cfg)))
         if precision is not None:  # default: f32 for L/NL, f64 for NL6 (mpcb_mppi_default_cfg)
-            cfg.precision = {"f32": A.F32, "f64": A.F64}[precision]
-        precision = "f64" if cfg.precision == A.F64 else "f32"
+            cfg.precision = A.PRECISIONS[precision]
+        precision = {A.F32: "f32", A.F64: "f64", A.F64_FAST: "f64fast"}[cfg.precision]
         cfg.horizon, cfg.samples, cfg.state_dim = int(N), int(K), int(S)
         cfg.controllers, cfg.device, cfg.rank, cfg.world_size = int(controllers), int(device), int(rank), int(world_size)
         cfg.lambda_, cfg.std_dev = float(lam), float(std_dev)
@@ -203,7 +203,7 @@ class Mppi:
         x, u_n = self._inputs(x, u_n)
         u_out = np.empty((self.C, self.N))
         infos = (A.MppiInfo * self.C)()
-        eps = np.empty((self.C, self.K_local, self.N), dtype=np.float64 if self.precision == "f64" else np.float32)
+        eps = np.empty((self.C, self.K_local, self.N), dtype=np.float32 if self.precision == "f32" else np.float64)
         st = A.lib().mpcb_mppi_compute_dump(self._h, _dp(x), _dp(u_n), eps.ctypes.data_as(C.c_void_p), _dp(u_out), infos)
         u = self._finish(st, u_out, infos, squeeze)
         return u, (eps[0] if squeeze else eps)

@@ -43,8 +43,8 @@ def test_defaults_match_the_examples():
     assert (cfg.horizon, cfg.samples, cfg.lambda_, cfg.std_dev, cfg.limit_lo, cfg.limit_hi) == (8, 800000, 0.5, 3.0, -20.0, 20.0)
     assert cfg.model.dt == pytest.approx(0.1) and cfg.model.m2 == 2.3 - 2.0 * 150e-3 + 2.0 and cfg.precision == A.F32
     assert L.mpcb_mppi_default_cfg(A.MODEL_NL6, C.byref(cfg)) == 0
-    # examples/mppi4-non-liner-ukf.rs:13-24; FP64 by default (DESIGN.md precision policy)
-    assert (cfg.samples, cfg.lambda_, cfg.std_dev, cfg.limit_hi, cfg.precision) == (500000, 1.4, 4.0, 10.0, A.F64)
+    # examples/mppi4-non-liner-ukf.rs:13-24; FP64 (fast form) by default (DESIGN.md precision policy)
+    assert (cfg.samples, cfg.lambda_, cfg.std_dev, cfg.limit_hi, cfg.precision) == (500000, 1.4, 4.0, 10.0, A.F64_FAST)
     assert list(cfg.model.cost)[:4] == [0.1, 0.1, 1.0, 0.5]
     assert L.mpcb_mppi_default_cfg(A.MODEL_PEN_LIN, C.byref(cfg)) == A.BAD_ARG  # not an MPPI model
     # product defaults == oracle defaults, field by field

@@ -65,6 +65,21 @@ def test_replay_parity_f64(gpu_required, case):
 
 
 @pytest.mark.parametrize("case", list(CASES))
+def test_replay_parity_f64_fast(gpu_required, case):
+    """MPCB_F64_FAST: the folded formulas in double (one reciprocal per step, sincos, FMA).  Every operation is FP64, so the
+    distance to the reference order is rounding times the model's error growth: 1e-9 on the controls everywhere — far inside
+    the north star's 1e-5, which FP32 misses on model NL6 — with the same argmin and the same set of finite samples."""
+    for u_g, u_o, ig, io, c_g, c_o in closed_loop(case, 16384, "f64fast"):
+        assert ig["argmax"] == io["argmax"]
+        assert ig["n_finite"] == io["n_finite"]
+        near = c_o > io["max"] - 1e4
+        np.testing.assert_allclose(c_g[near], c_o[near], rtol=1e-6, atol=1e-8)
+        assert abs(ig["max"] - io["max"]) <= 1e-8 * abs(io["max"]) + 1e-11
+        assert abs(ig["sum"] - io["sum"]) <= 1e-8 * io["sum"]
+        assert rel_err(u_g, u_o) < 1e-9
+
+
+@pytest.mark.parametrize("case", list(CASES))
 def test_replay_parity_f32(gpu_required, case):
     # NL6 at DT = 0.15 moves theta by radians per step: the rollout is chaotic inside the 8-step horizon and
     # amplifies FP32 rounding ~1e3x.  The reference's own formula order evaluated in FP32 (oracle f32 twin) is
