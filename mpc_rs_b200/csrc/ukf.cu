@@ -300,6 +300,7 @@ static mpcb_status ukf_create_impl(mpcb_ukf** out, const mpcb_ukf_cfg* cfg, cons
         const mpcb_model_params& mp = cfg->model;
         double* k = h->mc.k;
         k[uslot::G] = mp.g;
+        k[uslot::IG] = 1.0 / mp.g;
         k[uslot::L] = mp.l;
         k[uslot::DEG] = 180.0 / PI;  // f64::to_degrees
         k[uslot::M2G] = mp.m2 * mp.g;

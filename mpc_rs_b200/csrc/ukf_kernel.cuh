@@ -21,6 +21,7 @@ namespace mpcb {
 
 namespace uslot {  // hx constants, disjoint from the dynamics slots of models.cuh
 constexpr int G = 12, L = 13, RPM = 14, NRPM = 15, DEG = 17, M2G = 18, M2 = 19, M2L = 20;
+constexpr int IG = 29;  // 1 / g (fast arithmetic: the accelerometer rows multiply instead of dividing)
 }
 
 struct UkfParams {
@@ -67,7 +68,21 @@ __device__ __forceinline__ void nl6_ddot(const ModelConsts& mc, double th, doubl
     *ddth = t1 + t2 + t3 + 0.0;
 }
 
-template <int MODEL, int N>
+// The same accelerations in the folded form of ModelNL6F (models.cuh): one sincos, ONE reciprocal instead of five IEEE
+// divisions, FMA — the fast-arithmetic kernels (rounding-level differences from the reference order)
+__device__ __forceinline__ void nl6_ddot_fast(const ModelConsts& mc, double th, double thd, double u, double* ddx, double* ddth) {
+    double s2, c2;
+    sincos(th, &s2, &c2);
+    const double mlc = mc.k[slot::N6_ML] * c2;
+    const double id = 1.0 / fma(-mlc, mlc, mc.k[slot::N6_D1]);
+    const double ws = (thd * thd) * s2;
+    const double numx = fma(mc.k[slot::N6_BML], ws, fma(mc.k[slot::N6_NML2G] * s2, c2, mc.k[slot::N6_C3] * u));
+    const double numt = fma(c2, fma(mc.k[slot::N6_NML2], ws, -mc.k[slot::N6_C6] * u), mc.k[slot::N6_C5] * s2);
+    *ddx = numx * id;
+    *ddth = numt * id;
+}
+
+template <int MODEL, int N, bool FAST = false>
 __device__ __forceinline__ void ukf_fx(const ModelConsts& mc, double (&x)[N], double u, double dt) {
 #ifdef MPCB_UKF_USER
     // run-time compiled user model (mpcb_ukf_create_user): ::fx is declared by the user source ahead of this header
@@ -81,6 +96,19 @@ __device__ __forceinline__ void ukf_fx(const ModelConsts& mc, double (&x)[N], do
         x[2] += x[3] * dt;
         x[1] += (mc.k[slot::L_A2] * x[2] + mc.k[slot::L_B2] * u) * dt;
         x[0] += x[1] * dt;
+    } else if constexpr (MODEL == MPCB_MODEL_PEN_NL && FAST) {
+        // the folded form of ModelNLF (models.cuh): one sincos, one reciprocal, FMA
+        double s, c;
+        sincos(x[2], &s, &c);
+        const double rd = 1.0 / fma(-mc.k[slot::NL_E2], c * c, mc.k[slot::NL_D]);
+        const double qq = fma(mc.k[slot::NL_KU], u, (x[3] * x[3]) * s);
+        const double n3 = fma(-mc.k[slot::NL_K3], qq * c, s);
+        const double n1 = fma(mc.k[slot::NL_K1], qq, s * c);
+        const double r3 = fma(n3, rd * (dt * mc.k[slot::NL_T1]), x[3]);
+        const double r2 = fma(x[3], dt, x[2]);
+        const double r1 = fma(n1, rd * (dt * mc.k[slot::NL_T4]), x[1]);
+        const double r0 = fma(x[1], dt, x[0]);
+        x[0] = r0; x[1] = r1; x[2] = r2; x[3] = r3;
     } else if constexpr (MODEL == MPCB_MODEL_PEN_NL) {
         // examples/ukf-pen2.rs:31-44
         const double s = sin(x[2]), c = cos(x[2]);
@@ -95,6 +123,20 @@ __device__ __forceinline__ void ukf_fx(const ModelConsts& mc, double (&x)[N], do
         const double r1 = x[1] + (term3 + term4) / d * dt;
         const double r0 = x[0] + x[1] * dt;
         x[0] = r0; x[1] = r1; x[2] = r2; x[3] = r3;
+    } else if constexpr (MODEL == MPCB_MODEL_PEN6 && FAST) {
+        // same formulas, one sincos and one reciprocal (d still comes from x[2].cos(), as the reference writes it)
+        const double mlc = mc.k[slot::NL_ML] * cos(x[2]);
+        const double id = 1.0 / fma(-mlc, mlc, mc.k[slot::NL_D]);
+        double s3, c3;
+        sincos(x[3], &s3, &c3);
+        const double q = fma(mc.k[slot::NL_ML] * (x[4] * x[4]), s3, mc.k[slot::NL_KTR] * u);
+        const double r0 = fma(x[1], dt, x[0]);
+        const double r1 = fma(x[2], dt, x[1]);
+        const double r2 = fma(mc.k[slot::NL_JML], q, mc.k[slot::NL_T4] * s3 * c3) * id;
+        const double r3 = fma(x[4], dt, x[3]);
+        const double r4 = fma(x[5], dt, x[4]);
+        const double r5 = fma(-(mc.k[slot::NL_M2] * mc.k[slot::NL_L]) * q, c3, mc.k[slot::NL_T1] * s3) * id;
+        x[0] = r0; x[1] = r1; x[2] = r2; x[3] = r3; x[4] = r4; x[5] = r5;
     } else if constexpr (MODEL == MPCB_MODEL_PEN6) {
         // examples/ukf-pen3.rs:35-50 — d from x[2].cos() as written (theta is x[3] in this layout)
         const double mlc = mc.k[slot::NL_ML] * cos(x[2]);
@@ -115,7 +157,8 @@ __device__ __forceinline__ void ukf_fx(const ModelConsts& mc, double (&x)[N], do
     } else {
         // MPCB_MODEL_NL6_UKF: dynamics_short(x, u, dt, 0) — examples/mppi4-non-liner-ukf.rs:149-159
         double ddx, ddth;
-        nl6_ddot(mc, x[3], x[4], u, &ddx, &ddth);
+        if constexpr (FAST) nl6_ddot_fast(mc, x[3], x[4], u, &ddx, &ddth);
+        else nl6_ddot(mc, x[3], x[4], u, &ddx, &ddth);
         x[5] = ddth;
         x[4] += x[5] * dt;
         x[3] += x[4] * dt;
@@ -125,7 +168,7 @@ __device__ __forceinline__ void ukf_fx(const ModelConsts& mc, double (&x)[N], do
     }
 }
 
-template <int MODEL, int N, int O>
+template <int MODEL, int N, int O, bool FAST = false>
 __device__ __forceinline__ void ukf_hx(const ModelConsts& mc, const double (&x)[N], double (&z)[O]) {
 #ifdef MPCB_UKF_USER
     if constexpr (MODEL == MPCB_MODEL_USER_UKF) {
@@ -139,6 +182,17 @@ __device__ __forceinline__ void ukf_hx(const ModelConsts& mc, const double (&x)[
         z[0] = mc.k[uslot::RPM] * x[1];  // examples/ukf-pen2.rs:47-53
         z[1] = mc.k[uslot::RPM] * x[1];
         z[2] = x[3] * mc.k[uslot::DEG];
+    } else if constexpr (MODEL == MPCB_MODEL_PEN6 && FAST) {
+        double s3, c3;
+        sincos(x[3], &s3, &c3);
+        const double m2a = mc.k[uslot::M2] * x[2];
+        const double v = fma(mc.k[uslot::M2G], c3, fma(m2a, s3, -mc.k[uslot::M2L] * (x[4] * x[4])));
+        const double h = fma(-mc.k[uslot::M2G], s3, fma(m2a, c3, mc.k[uslot::M2L] * x[5]));
+        z[0] = mc.k[uslot::RPM] * x[1];
+        z[1] = z[0];
+        z[2] = x[3] * mc.k[uslot::DEG];
+        z[3] = v * mc.k[uslot::IG];
+        z[4] = h * mc.k[uslot::IG];
     } else if constexpr (MODEL == MPCB_MODEL_PEN6) {
         // examples/ukf-pen3.rs:53-63
         const double s3 = sin(x[3]), c3 = cos(x[3]);
@@ -149,6 +203,16 @@ __device__ __forceinline__ void ukf_hx(const ModelConsts& mc, const double (&x)[
         z[2] = x[3] * mc.k[uslot::DEG];
         z[3] = v / mc.k[uslot::G];
         z[4] = h / mc.k[uslot::G];
+    } else if constexpr (FAST) {
+        double s3, c3;
+        sincos(x[3], &s3, &c3);
+        const double ax = fma(mc.k[uslot::G], s3, fma(x[2], c3, mc.k[uslot::L] * x[5]));
+        const double az = fma(mc.k[uslot::G], c3, fma(-x[2], s3, mc.k[uslot::L] * (x[4] * x[4])));
+        z[0] = mc.k[uslot::RPM] * x[1];
+        z[1] = mc.k[uslot::NRPM] * x[1];
+        z[2] = x[4] * mc.k[uslot::DEG];
+        z[3] = az * mc.k[uslot::IG];
+        z[4] = ax * mc.k[uslot::IG];
     } else {
         // examples/mppi4-non-liner-ukf.rs:169-179
         const double s3 = sin(x[3]), c3 = cos(x[3]);
@@ -165,13 +229,13 @@ __device__ __forceinline__ void ukf_hx(const ModelConsts& mc, const double (&x)[
 // Out-of-line calls for the six-state models: their fx/hx carry FP64 sin/cos expansions, and inlining them at all
 // 2n+1 = 13 sigma points made the fused kernel 220 KB of straight-line code — ncu: "no_instruction" was the top
 // stall (2.8 cycles per issue), the FP64 pipe 23 % busy.  The four-state kernels stay inlined (their code fits).
-template <int MODEL, int N>
+template <int MODEL, int N, bool FAST>
 __device__ __noinline__ void ukf_fx_call(const ModelConsts& mc, double (&x)[N], double u, double dt) {
-    ukf_fx<MODEL, N>(mc, x, u, dt);
+    ukf_fx<MODEL, N, FAST>(mc, x, u, dt);
 }
-template <int MODEL, int N, int O>
+template <int MODEL, int N, int O, bool FAST>
 __device__ __noinline__ void ukf_hx_call(const ModelConsts& mc, const double (&x)[N], double (&z)[O]) {
-    ukf_hx<MODEL, N, O>(mc, x, z);
+    ukf_hx<MODEL, N, O, FAST>(mc, x, z);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -274,24 +338,36 @@ __device__ __forceinline__ void sym_eig_sqrt(double (&A)[N][N], double (&Lo)[N][
                             V[k][q] = s * vkp + c * vkq;
                         }
                     } else {
-                        // same rotation with reciprocals / reciprocal square roots (MUFU seed + Newton instead of the
-                        // IEEE division and sqrt sequences) and the symmetric update: only rows/columns p and q of the
-                        // other indices change, the 2x2 block in closed form (a_pp -= t a_pq, a_qq += t a_pq, a_pq = 0)
-                        const double diff = A[q][q] - A[p][p];
-                        // equal diagonal entries rotate by 45 degrees (tau = 0) whatever the size of a_pq, like the
-                        // division does; a_pq so small that tau overflows means t = 1/(2 tau) (and 0 * inf never forms)
-                        const double tau = (diff == 0.0) ? 0.0 : diff * (0.5 * __drcp_rn(apq));
-                        const double at = fabs(tau);
-                        double t;
-                        if (at < 1e150) {
-                            const double w = fma(tau, tau, 1.0);
-                            const double rt = w * rsqrt(w);  // sqrt(1 + tau^2)
-                            t = copysign(__drcp_rn(at + rt), tau);
+                        // same rotation, symmetric update (only rows/columns p and q of the other indices change, the 2x2 block
+                        // in closed form: a_pp -= t a_pq, a_qq += t a_pq, a_pq = 0), and the angle from TWO reciprocal square
+                        // roots and no division: with theta = (a_qq - a_pp)/2 and h = hypot(theta, a_pq),
+                        //   cos 2phi = |theta|/h,  cos^2 phi = (1 + cos 2phi)/2,  sin phi = (|a_pq|/h) / (2 cos phi),  t = sin/cos
+                        // — the same phi as t = sign(tau)/(|tau| + sqrt(1 + tau^2)), tau = theta/a_pq.  Equal diagonal entries
+                        // rotate by +45 degrees whatever the sign of a_pq, like the division form does.
+                        const double th = 0.5 * (A[q][q] - A[p][p]);
+                        const double h2 = fma(th, th, apq * apq);
+                        double c, s, t;
+                        if (h2 > 1e-280 && h2 < 1e280) {
+                            const double rh = rsqrt(h2);
+                            const double c2 = fma(0.5, fabs(th) * rh, 0.5);  // in [0.5, 1]
+                            const double rc = rsqrt(c2);
+                            c = c2 * rc;
+                            const double sa = (0.5 * rc) * (fabs(apq) * rh);
+                            s = (th != 0.0 && ((th < 0.0) != (apq < 0.0))) ? -sa : sa;
+                            t = s * rc;
                         } else {
-                            t = 0.5 * __drcp_rn(tau);
+                            // h^2 under- or overflows (entries around 1e-140 or 1e140): the division form
+                            const double tau = (th == 0.0) ? 0.0 : th * __drcp_rn(apq);
+                            const double at = fabs(tau);
+                            if (at < 1e150) {
+                                const double w = fma(tau, tau, 1.0);
+                                t = copysign(__drcp_rn(at + w * rsqrt(w)), tau);
+                            } else {
+                                t = 0.5 * __drcp_rn(tau);
+                            }
+                            c = rsqrt(fma(t, t, 1.0));
+                            s = t * c;
                         }
-                        const double c = rsqrt(fma(t, t, 1.0));
-                        const double s = t * c;
 #pragma unroll
                         for (int k = 0; k < N; ++k) {
                             if (k != p && k != q) {
@@ -709,8 +785,8 @@ __global__ void __launch_bounds__(kUkfThreads) ukf_kernel(const __grid_constant_
                 double col[N];
 #pragma unroll
                 for (int r = 0; r < N; ++r) col[r] = sig[r][i];
-                if constexpr (N >= 6) ukf_fx_call<MODEL, N>(p.mc, col, u, p.dt);
-                else ukf_fx<MODEL, N>(p.mc, col, u, p.dt);
+                if constexpr (N >= 6) ukf_fx_call<MODEL, N, FAST>(p.mc, col, u, p.dt);
+                else ukf_fx<MODEL, N, FAST>(p.mc, col, u, p.dt);
 #pragma unroll
                 for (int r = 0; r < N; ++r) sig[r][i] = col[r];
             }
@@ -725,8 +801,8 @@ __global__ void __launch_bounds__(kUkfThreads) ukf_kernel(const __grid_constant_
                 double col[N], zz[O];
 #pragma unroll
                 for (int r = 0; r < N; ++r) col[r] = sig[r][i];
-                if constexpr (N >= 6) ukf_hx_call<MODEL, N, O>(p.mc, col, zz);
-                else ukf_hx<MODEL, N, O>(p.mc, col, zz);
+                if constexpr (N >= 6) ukf_hx_call<MODEL, N, O, FAST>(p.mc, col, zz);
+                else ukf_hx<MODEL, N, O, FAST>(p.mc, col, zz);
 #pragma unroll
                 for (int r = 0; r < O; ++r) zs[r][i] = ((p.enable >> r) & 1u) ? zz[r] : 0.0;
             }
