@@ -72,9 +72,9 @@ __device__ __forceinline__ void nl6_ddot(const ModelConsts& mc, double th, doubl
 // divisions, FMA — the fast-arithmetic kernels (rounding-level differences from the reference order)
 __device__ __forceinline__ void nl6_ddot_fast(const ModelConsts& mc, double th, double thd, double u, double* ddx, double* ddth) {
     double s2, c2;
-    sincos(th, &s2, &c2);
+    sincos_f64_fast(th, &s2, &c2);
     const double mlc = mc.k[slot::N6_ML] * c2;
-    const double id = 1.0 / fma(-mlc, mlc, mc.k[slot::N6_D1]);
+    const double id = rcp_f64_fast(fma(-mlc, mlc, mc.k[slot::N6_D1]));
     const double ws = (thd * thd) * s2;
     const double numx = fma(mc.k[slot::N6_BML], ws, fma(mc.k[slot::N6_NML2G] * s2, c2, mc.k[slot::N6_C3] * u));
     const double numt = fma(c2, fma(mc.k[slot::N6_NML2], ws, -mc.k[slot::N6_C6] * u), mc.k[slot::N6_C5] * s2);
@@ -99,8 +99,8 @@ __device__ __forceinline__ void ukf_fx(const ModelConsts& mc, double (&x)[N], do
     } else if constexpr (MODEL == MPCB_MODEL_PEN_NL && FAST) {
         // the folded form of ModelNLF (models.cuh): one sincos, one reciprocal, FMA
         double s, c;
-        sincos(x[2], &s, &c);
-        const double rd = 1.0 / fma(-mc.k[slot::NL_E2], c * c, mc.k[slot::NL_D]);
+        sincos_f64_fast(x[2], &s, &c);
+        const double rd = rcp_f64_fast(fma(-mc.k[slot::NL_E2], c * c, mc.k[slot::NL_D]));
         const double qq = fma(mc.k[slot::NL_KU], u, (x[3] * x[3]) * s);
         const double n3 = fma(-mc.k[slot::NL_K3], qq * c, s);
         const double n1 = fma(mc.k[slot::NL_K1], qq, s * c);
@@ -126,9 +126,9 @@ __device__ __forceinline__ void ukf_fx(const ModelConsts& mc, double (&x)[N], do
     } else if constexpr (MODEL == MPCB_MODEL_PEN6 && FAST) {
         // same formulas, one sincos and one reciprocal (d still comes from x[2].cos(), as the reference writes it)
         const double mlc = mc.k[slot::NL_ML] * cos(x[2]);
-        const double id = 1.0 / fma(-mlc, mlc, mc.k[slot::NL_D]);
+        const double id = rcp_f64_fast(fma(-mlc, mlc, mc.k[slot::NL_D]));
         double s3, c3;
-        sincos(x[3], &s3, &c3);
+        sincos_f64_fast(x[3], &s3, &c3);
         const double q = fma(mc.k[slot::NL_ML] * (x[4] * x[4]), s3, mc.k[slot::NL_KTR] * u);
         const double r0 = fma(x[1], dt, x[0]);
         const double r1 = fma(x[2], dt, x[1]);
@@ -184,7 +184,7 @@ __device__ __forceinline__ void ukf_hx(const ModelConsts& mc, const double (&x)[
         z[2] = x[3] * mc.k[uslot::DEG];
     } else if constexpr (MODEL == MPCB_MODEL_PEN6 && FAST) {
         double s3, c3;
-        sincos(x[3], &s3, &c3);
+        sincos_f64_fast(x[3], &s3, &c3);
         const double m2a = mc.k[uslot::M2] * x[2];
         const double v = fma(mc.k[uslot::M2G], c3, fma(m2a, s3, -mc.k[uslot::M2L] * (x[4] * x[4])));
         const double h = fma(-mc.k[uslot::M2G], s3, fma(m2a, c3, mc.k[uslot::M2L] * x[5]));
@@ -205,7 +205,7 @@ __device__ __forceinline__ void ukf_hx(const ModelConsts& mc, const double (&x)[
         z[4] = h / mc.k[uslot::G];
     } else if constexpr (FAST) {
         double s3, c3;
-        sincos(x[3], &s3, &c3);
+        sincos_f64_fast(x[3], &s3, &c3);
         const double ax = fma(mc.k[uslot::G], s3, fma(x[2], c3, mc.k[uslot::L] * x[5]));
         const double az = fma(mc.k[uslot::G], c3, fma(-x[2], s3, mc.k[uslot::L] * (x[4] * x[4])));
         z[0] = mc.k[uslot::RPM] * x[1];
@@ -348,9 +348,9 @@ __device__ __forceinline__ void sym_eig_sqrt(double (&A)[N][N], double (&Lo)[N][
                         const double h2 = fma(th, th, apq * apq);
                         double c, s, t;
                         if (h2 > 1e-280 && h2 < 1e280) {
-                            const double rh = rsqrt(h2);
+                            const double rh = rsqrt_f64_fast(h2);
                             const double c2 = fma(0.5, fabs(th) * rh, 0.5);  // in [0.5, 1]
-                            const double rc = rsqrt(c2);
+                            const double rc = rsqrt_f64_fast(c2);
                             c = c2 * rc;
                             const double sa = (0.5 * rc) * (fabs(apq) * rh);
                             s = (th != 0.0 && ((th < 0.0) != (apq < 0.0))) ? -sa : sa;
