@@ -589,7 +589,8 @@ def run_gpu(args):
         "traffic": MPPI_DRAM_TRAFFIC_BYTES, "kernel_ms": kern_ms, "kernel_ms_with_l2_flush": total_ms / args.steps,
         "note": f"{FLOPS_PER_STEP:.0f} algorithmic FP32 flops per rollout-step (SURVEY.md 8d) x {K_PER_GPU * H} steps per launch; "
                 f"peak = {peaks['fp32_source']}; neither 'hbm' nor 'tensor' bounds this kernel: it is bound by the SM's instruction "
-                "dispatch (66 issued instructions per rollout-step, DESIGN.md 4.1) and moves 74 KB of DRAM per launch (traffic: bytes, "
+                "dispatch (66 issued instructions per rollout-step; this instruction mix caps at frac 0.36, and at 0.22 on this shape "
+                "with its fixed launch + merge tail, DESIGN.md 4.1b) and moves 74 KB of DRAM per launch (traffic: bytes, "
                 "this round's ncu capture); kernel_ms = back-to-back launches enqueued from compiled code, no L2 flush"
                 + ("; at N > 1 it includes the in-kernel cross-GPU exchange" if world > 1 else ""),
     }
@@ -597,9 +598,12 @@ def run_gpu(args):
         gbs = ukf_out["value"] / world * UKF_BYTES / 1e9
         ukf_out["roofline"] = {"bound": "hbm", "kernel": "ukf_kernel<4,2,PEN_LIN,cholesky,interleaved,fused>", "achieved": gbs,
                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": UKF_DRAM_TRAFFIC_BYTES,
+                               "traffic_gbs": UKF_DRAM_TRAFFIC_BYTES / (ukf_out["ms_per_step"] * 1e-3) / 1e9,
+                               "traffic_frac": UKF_DRAM_TRAFFIC_BYTES / (ukf_out["ms_per_step"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
                                "note": f"{UKF_BYTES:.0f} algorithmic bytes per filter-update (x, full P in and out, z: SURVEY.md 8d); the "
                                        "kernel neither reads nor writes the strictly-upper triangle of the exactly symmetric P, so the DRAM "
-                                       f"traffic is lower than the algorithmic figure; peak = {peaks['hbm_source']}; "
+                                       "traffic is lower than the algorithmic figure: traffic_frac is the fraction of the HBM peak in bytes "
+                                       f"actually moved (the kernel sits between the HBM and the FP64 roof, DESIGN.md 4.2); peak = {peaks['hbm_source']}; "
                                        f"FP64 pipe peak {peaks['fp64_tflops']:.1f} TFLOP/s ({peaks['fp32_source']})"}
     cpu_val, cpu_info = cpu_baseline(None, 2, budget_s=12.0) if world == 1 else (None, None)
     line = {

@@ -110,6 +110,17 @@ constexpr uint32_t kPeerMagic = 0x4d504258u;  // "MPBX"
 
 namespace {
 
+// spin-wait hint of the host CPU (the B200 boxes are x86-64; GB200 hosts are aarch64)
+inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#elif defined(__aarch64__)
+    asm volatile("yield" ::: "memory");
+#else
+    asm volatile("" ::: "memory");
+#endif
+}
+
 size_t elt_size(const mpcb_mppi* h) { return h->cfg.precision != MPCB_F32 ? sizeof(double) : sizeof(float); }
 
 // Chooses block size, blocks per controller and merge-tree shape (see the header of mppi_kernel.cuh).
@@ -453,7 +464,7 @@ mpcb_status finish_host(mpcb_mppi* h, double* u_out, mpcb_mppi_info* info, bool 
             bool all = true;
             for (int w = 0; w < words; ++w) all = all && (flag[w] == want);
             if (all) { done = true; break; }
-            __builtin_ia32_pause();
+            cpu_relax();
         }
         __atomic_thread_fence(__ATOMIC_ACQUIRE);
     }

@@ -3,7 +3,7 @@
 // Rounds: kPhiloxRounds = 7 — the fewest rounds for which the paper reports Philox4x32 passing BigCrush
 // ("Crush-resistant"; 10 is the paper's default with a safety margin).  Generate mode defines its own noise
 // stream (the reference seeds from OS entropy), so the round count is a quality/speed choice, not a parity one;
-// tests/test_mppi_gpu.py checks the moments, the tails and the serial correlation of the dumped stream.
+// tests/test_mppi_gpu.py::test_generated_noise_statistics checks the moments, the tails and the serial correlation of the dumped stream.
 // Replaces the rand_distr::Normal / Xoshiro256Plus::from_entropy draw of src/mppi.rs:38-45.
 //
 // Counter layout (so the sample set does not depend on how samples are sharded over GPUs or blocks):

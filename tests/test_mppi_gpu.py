@@ -152,6 +152,44 @@ def test_generate_mode_replays_its_own_dump(gpu_required):
             assert not np.array_equal(eps, eps2)
 
 
+def test_generated_noise_statistics(gpu_required):
+    """Generate mode draws its own stream (Philox4x32-7 + Box-Muller, csrc/philox.cuh) in place of the reference's
+    rand_distr::Normal (src/mppi.rs:38-45): 6.5 M dumped draws are held to the moments, tail mass, distribution (KS) and
+    independence (lag correlations along the horizon, across samples and across calls) of N(0, sigma^2)."""
+    from scipy import stats
+    model, oid, H, dt, lam, sig, lim = CASES["NL_h100"]
+    K = 65536
+    with Mppi(H, K, model=model, lam=lam, std_dev=sig, limit=lim, precision="f32", dt=dt, seed=12345) as m:
+        _, e1 = m.compute_dump(X0, np.zeros(H))
+        _, e2 = m.compute_dump(X0, np.zeros(H))
+    z = e1.astype(np.float64) / sig
+    n = z.size
+    se = 1.0 / np.sqrt(n)
+    assert abs(z.mean()) < 5 * se
+    assert abs(z.var() - 1.0) < 5 * np.sqrt(2.0) * se
+    assert abs(stats.skew(z.ravel())) < 5 * np.sqrt(6.0) * se
+    assert abs(stats.kurtosis(z.ravel())) < 5 * np.sqrt(24.0) * se
+    for thr in (1.0, 2.0, 3.0, 4.0):  # two-sided tail mass within 5 binomial standard errors
+        pt = 2.0 * stats.norm.sf(thr)
+        frac = np.mean(np.abs(z) > thr)
+        assert abs(frac - pt) < 5 * np.sqrt(pt * (1 - pt) / n), (thr, frac, pt)
+    assert np.abs(z).max() < 6.8  # the radius word has 32 bits: tails reach 6.7 sigma
+    ks = stats.kstest(z.ravel()[:: 7], "norm")
+    assert ks.pvalue > 1e-4, ks
+    # independence: along the horizon (neighbouring steps share a Philox block: lags 1..4), across samples, across calls
+    for lag in (1, 2, 3, 4, 8):
+        r = np.mean(z[:, :-lag] * z[:, lag:])
+        assert abs(r) < 5.0 / np.sqrt(z[:, lag:].size), (lag, r)
+    for lag in (1, 32, 448):
+        r = np.mean(z[:-lag] * z[lag:])
+        assert abs(r) < 5.0 / np.sqrt(z[lag:].size), (lag, r)
+    z2 = e2.astype(np.float64) / sig
+    assert abs(np.mean(z * z2)) < 5 * se
+    # Box-Muller pairs (cos, sin branches of one radius): squared magnitudes must not be correlated either
+    r2 = np.corrcoef((z[:, 0::2] ** 2).ravel(), (z[:, 1::2] ** 2).ravel())[0, 1]
+    assert abs(r2) < 5.0 / np.sqrt(n / 2)
+
+
 def test_batched_controllers(gpu_required):
     """C independent controllers in one call equal C single-controller calls (segmented reduction)."""
     model, oid, H, dt, lam, sig, lim = CASES["NL6_shipped"]
