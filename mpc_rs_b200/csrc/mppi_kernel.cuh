@@ -495,11 +495,13 @@ __device__ __forceinline__ bool ll_load(const uint4* cell, unsigned int tag, dou
 // ll != nullptr (FINAL_PEER_EXCHANGE): the warp's un-normalised sums go to every rank's mailbox as tagged cells, the warp
 // collects the G ranks' records of its pair (lane r = rank r) and combines them exactly like rows of one GPU — every
 // rank does the same arithmetic on the same records, so the ranks' results agree bitwise.
-template <bool kFastExp>
+// RPL = rows per lane (n_rows <= 32 RPL): the caller picks the smallest instantiation that covers its rows — 4 RPL
+// 16-byte loads are in flight per lane, and at the 128-register cap of the 512-thread kernels the 32 loads of RPL = 8 were
+// issued in dependent batches (configs[1] has 147 rows: RPL = 5).
+template <bool kFastExp, int RPL = kMergeFan / 32>
 static __device__ __forceinline__ int mppi_warp_merge(const double* rows, long long pair_stride, int n_rows, int H, int pair,
                                                       double inv_lambda, int final_mode, const MergeOut& o, bool write_info,
                                                       const PeerLL* ll = nullptr, int ctrl = 0) {
-    constexpr int RPL = kMergeFan / 32;  // rows per lane
     const unsigned int full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     double2 hd[RPL], p0[RPL], p1[RPL], pv[RPL];
@@ -975,9 +977,14 @@ __device__ __forceinline__ void mppi_block_tail(const MppiParams& p, int c, int 
             pll.ll_offset = p.peer_ll_offset;
             pll.G = p.G; pll.rank = p.rank; pll.C = p.C; pll.ncell = mppi_ll_cells(H);
             pll.epoch = p.xepoch;
-            for (int pair = p_lo + wid; pair < p_hi; pair += BLOCK / 32)
-                mppi_warp_merge<kFastExp>(ctrl_rows, pair_stride, p.chunks, H, pair, inv_lambda_m, peer_ll ? FINAL_NORMALISE : p.final_mode, fo,
-                                          mi == 0 && pair == 1, peer_ll ? &pll : nullptr, c);
+            for (int pair = p_lo + wid; pair < p_hi; pair += BLOCK / 32) {
+                if (p.chunks <= 160)
+                    mppi_warp_merge<kFastExp, 5>(ctrl_rows, pair_stride, p.chunks, H, pair, inv_lambda_m, peer_ll ? FINAL_NORMALISE : p.final_mode,
+                                                 fo, mi == 0 && pair == 1, peer_ll ? &pll : nullptr, c);
+                else
+                    mppi_warp_merge<kFastExp>(ctrl_rows, pair_stride, p.chunks, H, pair, inv_lambda_m, peer_ll ? FINAL_NORMALISE : p.final_mode,
+                                              fo, mi == 0 && pair == 1, peer_ll ? &pll : nullptr, c);
+            }
             if (p.final_mode == FINAL_RANK_ROW && mi == 0 && tid == 0 && PL > kPartialHdr + H) fo.out_row[kPartialHdr + H] = 0.0;
             if (dbg != nullptr && tid == 0) dbg[11] = globaltimer_ns();
         }
