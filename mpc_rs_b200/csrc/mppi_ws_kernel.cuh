@@ -358,6 +358,11 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) mppi_ws_kernel(const __gr
             }
             if (p.debug_ts != nullptr && lane == 0 && live[0] && (cw == 0 || cw + 1 == (nlw < NCW ? nlw : NCW)))
                 p.debug_ts[(size_t)blockIdx.x * 16 + (cw == 0 ? 14 : 15)] = globaltimer_ns();
+            // PASS 3, first stage: the consumer warp reduces its own samples (finite costs only, lowest index on ties) right
+            // here, so that after the barrier every warp only has to reduce the NCW warp results
+            double tm = -CUDART_INF;
+            long long ta = kNoArg;
+            int nf = 0;
 #pragma unroll
             for (int s = 0; s < SPT; ++s) {
                 const int k = ctid + s * U;
@@ -366,35 +371,28 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) mppi_ws_kernel(const __gr
                 if (!valid) ck[s] = -CUDART_INF;
                 c_s[k] = ck[s];
                 if (p.costs != nullptr && valid) p.costs[(long long)c * p.K_local + kl] = ck[s];
+                if (finite_f64(ck[s])) {
+                    ++nf;
+                    if (ta == kNoArg || ck[s] > tm) { tm = ck[s]; ta = p.k_offset + kl; }  // s ascending = index ascending
+                }
             }
+            double wm_;
+            long long wa_;
+            warp_max_minidx(tm, ta, ta != kNoArg, &wm_, &wa_);
+            const int wn_ = __reduce_add_sync(0xffffffffu, nf);
+            if (lane == 0) { red_m[cw] = wm_; red_a[cw] = wa_; red_n[cw] = wn_; }
         }
         __syncthreads();
         if (tid == 0) s_next = 0;  // the next batch's queue (its first use comes after further barriers)
         if constexpr (kReplay)
             for (int k = tid; k < SB; k += NT) nan_s[k] = 0;
 
-        // ---- PASS 3: block max over finite c_k, lowest index on ties (the first TB threads) ----
+        // ---- PASS 3, second stage: block max over the consumer warps' results (every warp computes it) ----
         double bm = -CUDART_INF;
         long long ba = kNoArg;
         int bn = 0;
-        if (tid < TB) {
-            double tm = -CUDART_INF;
-            long long ta = kNoArg;
-            int nf = 0;
-            for (int k = tid; k < SB; k += TB) {
-                const double cv = c_s[k];
-                if (finite_f64(cv)) {
-                    ++nf;
-                    if (ta == kNoArg || cv > tm) { tm = cv; ta = p.k_offset + wb * 32 + k; }
-                }
-            }
-            warp_max_minidx(tm, ta, ta != kNoArg, &bm, &ba);
-            bn = __reduce_add_sync(0xffffffffu, nf);
-            if (lane == 0) { red_m[wid] = bm; red_a[wid] = ba; red_n[wid] = bn; }
-        }
-        __syncthreads();
         {
-            const bool has = lane < NTW;
+            const bool has = lane < NCW;
             const double wm = has ? red_m[lane] : -CUDART_INF;
             const long long wa = has ? red_a[lane] : kNoArg;
             const int wn = has ? red_n[lane] : 0;
