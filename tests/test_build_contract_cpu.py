@@ -41,7 +41,7 @@ def test_mppi_configs1_kernel_resources():
     assert name in e, sorted(e)[:4]
     k = e[name]
     assert k["regs"] <= 128, k            # 256 threads x 128 registers = half the register file: one block per SM + headroom
-    assert k["spill_st"] <= 64 and k["spill_ld"] <= 64, k
+    assert k["spill_st"] <= 64 and k["spill_ld"] <= 96, k  # the merge tail's spills (two instantiations of the warp merge: 5 / 8 rows per lane)
     # every generate-mode (NOISE = 0) FP32 flavour of model NL that keeps the v tile stays within 128 registers: the multi-batch
     # plans then hold 16 warps per SM (the dump / replay flavours are verification modes and may use more).  The kernels are
     # capped at 128 registers by __launch_bounds__; the few bytes ptxas spills under the cap belong to the merge tail (the
@@ -96,3 +96,19 @@ def test_sass_has_the_instructions_the_design_relies_on():
     u = sass("ukf_n4_fast.o", "_ZN4mpcb10ukf_kernelILi4ELi2ELi16ELi0ELi1ELi2ELb1EEEvNS_9UkfParamsE")
     assert u.count("LDGSTS") >= 17, u.count("LDGSTS")  # x (4) + lower triangle of P (10) + z (2) + status per tile
     assert u.count("DFMA") > 200 and " LDL" not in u and " STL" not in u
+
+
+def test_graft_entry_build_runs_here_without_a_gpu():
+    """The driver's "does it build" check: __graft_entry__.build() end to end (make is incremental, so this is seconds when
+    the tree is built) — every command it runs (nvcc, the oracle's Makefile, the C++ examples, the compiled e2e loop) must
+    succeed here and leave its record."""
+    import json
+    import sys
+    root = os.path.dirname(CSRC.rstrip(os.sep).rsplit(os.sep, 1)[0])
+    sys.path.insert(0, root)
+    import __graft_entry__ as g
+    g.build()
+    rec = json.load(open(os.path.join(root, "build", "build_record.json")))
+    assert rec["arch"] == "compute_100a/sm_100a" and rec["objects"] >= 28
+    for artefact in ("mpc_rs_b200/libmpc_b200.so", "oracle/libmpc_oracle.so", "tools/libmpcb_e2e.so", "tools/peak_bench", "build/cpp/mppi4"):
+        assert os.path.exists(os.path.join(root, artefact)), artefact
