@@ -289,6 +289,7 @@ __device__ __forceinline__ void sym_eig_sqrt(double (&A)[N][N], double (&Lo)[N][
         }
     for (int sweep = 0; sweep < 10; ++sweep) {
         double off = 0.0;
+        double skip = 0.0;  // FAST: rotations whose a_pq^2 is below their share of the stopping mass are left out
 #pragma unroll
         for (int p = 0; p < N - 1; ++p)
 #pragma unroll
@@ -301,6 +302,10 @@ __device__ __forceinline__ void sym_eig_sqrt(double (&A)[N][N], double (&Lo)[N][
 #pragma unroll
             for (int k = 0; k < N; ++k) dsum = fma(A[k][k], A[k][k], dsum);
             if (off <= 3.0e-33 * dsum) break;
+            // an entry with a_pq^2 <= (3e-33 / #pairs) sum a_kk^2 cannot keep the sweep loop alive on its own: if every
+            // entry is that small the criterion above holds.  Leaving those rotations out changes nothing above rounding
+            // and, in the last sweep or two, most rotations of most filters of a warp are that small.
+            skip = (3.0e-33 / (N * (N - 1) / 2)) * dsum;
         } else {
             if (off == 0.0) break;
         }
@@ -309,7 +314,10 @@ __device__ __forceinline__ void sym_eig_sqrt(double (&A)[N][N], double (&Lo)[N][
 #pragma unroll
             for (int q = p + 1; q < N; ++q) {
                 const double apq = A[p][q];
-                if (apq != 0.0) {
+                bool rotate;
+                if constexpr (FAST) rotate = apq * apq > skip;
+                else rotate = apq != 0.0;
+                if (rotate) {
                     if constexpr (!FAST) {
                         // the oracle's operation order (two divisions, two square roots, full two-sided update)
                         const double tau = (A[q][q] - A[p][p]) / (2.0 * apq);
