@@ -978,7 +978,7 @@ __device__ __forceinline__ void mppi_block_tail(const MppiParams& p, int c, int 
             pll.G = p.G; pll.rank = p.rank; pll.C = p.C; pll.ncell = mppi_ll_cells(H);
             pll.epoch = p.xepoch;
             for (int pair = p_lo + wid; pair < p_hi; pair += BLOCK / 32) {
-                if (p.chunks <= 160)
+                if (p.chunks <= 160 && !peer_ll)  // (with the cross-GPU exchange inlined twice the RPL = 5 copy measured +6 us per step)
                     mppi_warp_merge<kFastExp, 5>(ctrl_rows, pair_stride, p.chunks, H, pair, inv_lambda_m, peer_ll ? FINAL_NORMALISE : p.final_mode,
                                                  fo, mi == 0 && pair == 1, peer_ll ? &pll : nullptr, c);
                 else
