@@ -56,10 +56,10 @@ UKF_B = 1 << 20
 UKF_T = 100  # T = 100 steps, as examples/ukf-pen.rs:154-178 runs
 UKF_BYTES = 336.0  # 8*(2n + 2n^2 + o), n=4, o=2
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from this round's ncu --set full captures of these kernels
-# (profiles/mppi_r2_ncu_full_summary.txt, profiles/ukf_r2_ncu_full_summary.txt; tools/prof_round.sh) — the one roofline
+# (profiles/mppi_r2d_ncu_full_summary.txt, profiles/ukf_r2d_ncu_full_summary.txt; tools/prof_round.sh) — the one roofline
 # field that cannot be measured inside this run
-MPPI_DRAM_TRAFFIC_BYTES = 73_728 + 0
-UKF_DRAM_TRAFFIC_BYTES = 138_444_032 + 63_853_568
+MPPI_DRAM_TRAFFIC_BYTES = 70_912 + 0
+UKF_DRAM_TRAFFIC_BYTES = 138_444_288 + 62_852_096
 FP32_FALLBACK_TFLOPS = 69.5  # tools/peak_bench on this pool's B200 (profiles/peaks_r1.json)
 FP64_FALLBACK_TFLOPS = 33.9
 METRIC = "mppi_rollout_steps_per_sec"
@@ -590,7 +590,7 @@ def run_gpu(args):
         "note": f"{FLOPS_PER_STEP:.0f} algorithmic FP32 flops per rollout-step (SURVEY.md 8d) x {K_PER_GPU * H} steps per launch; "
                 f"peak = {peaks['fp32_source']}; neither 'hbm' nor 'tensor' bounds this kernel: it is bound by the SM's instruction "
                 "dispatch (66 issued instructions per rollout-step; this instruction mix caps at frac 0.36, and at 0.22 on this shape "
-                "with its fixed launch + merge tail, DESIGN.md 4.1b) and moves 74 KB of DRAM per launch (traffic: bytes, "
+                "with its fixed launch + merge tail, DESIGN.md 4.1b) and moves 71 KB of DRAM per launch (traffic: bytes, "
                 "this round's ncu capture); kernel_ms = back-to-back launches enqueued from compiled code, no L2 flush"
                 + ("; at N > 1 it includes the in-kernel cross-GPU exchange" if world > 1 else ""),
     }
