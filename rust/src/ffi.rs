@@ -18,6 +18,10 @@ pub enum MpcbMppi {}
 pub enum MpcbUkf {}
 pub const MPCB_MODEL_USER_UKF: i32 = 20; // fx + hx supplied as CUDA source (mpcb_ukf_create_user)
 pub const MPCB_MODEL_USER: i32 = 3; // dynamics + cost supplied as CUDA source (mpcb_mppi_create_user)
+// mpcb_precision (include/mpc_b200.h): mpcb_mppi_default_cfg picks F32 for models L / NL and F64_FAST for model NL6
+pub const MPCB_F32: i32 = 0; // FP32 rollouts, FP64 accumulation: 1e-5 from the f64 reference on L / NL
+pub const MPCB_F64: i32 = 1; // the reference's own operation order, no FMA contraction
+pub const MPCB_F64_FAST: i32 = 2; // FP64 in the folded form: 1e-9 from the reference at about half the cost of MPCB_F64
 
 extern "C" {
     pub fn mpcb_last_error_string() -> *const std::os::raw::c_char;
