@@ -43,6 +43,7 @@ struct mpcb_ukf {
     cudaStream_t stream = nullptr;
     ModelConsts mc;
     UkfKernelFn k_predict = nullptr, k_update = nullptr, k_fused = nullptr;
+    size_t fused_smem = 0;  // dynamic shared memory of k_fused (the streaming six-state kernels keep the sigma points there)
     long long grid_cap = 0;  // resident blocks of the fused kernel on this device
     RtcModule rtc;  // user-supplied fx / hx (mpcb_ukf_create_user): the kernels above live in this module
     double Q[36], R[25];
@@ -132,7 +133,8 @@ mpcb_status launch(mpcb_ukf* h, UkfKernelFn fn, const UkfParams& p) {
     // explicit cudaLaunchKernel: `fn` is a compiled-in __global__ function or the cudaKernel_t of a user model
     UkfParams pp = p;
     void* args[1] = {&pp};
-    MPCB_CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(fn), dim3(grid), dim3(kThreads), args, 0, h->stream));
+    const size_t smem = (fn == h->k_fused) ? h->fused_smem : 0;
+    MPCB_CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(fn), dim3(grid), dim3(kThreads), args, smem, h->stream));
     h->launches += 1;
     return MPCB_OK;
 }
@@ -336,6 +338,19 @@ static mpcb_status ukf_create_impl(mpcb_ukf** out, const mpcb_ukf_cfg* cfg, cons
         h->k_predict = pick(cfg->model_id, cfg->sqrt_mode, cfg->sigma_order, UKF_PREDICT);
         h->k_update = pick(cfg->model_id, cfg->sqrt_mode, cfg->sigma_order, UKF_UPDATE);
         h->k_fused = pick(cfg->model_id, cfg->sqrt_mode, cfg->sigma_order, UKF_FUSED);
+        // six-state filters in fast arithmetic: the fused step runs the streaming kernel (ukf_stream_kernel.cuh: sigma
+        // points in shared memory, one-pass shifted transforms); MPCB_UKF_NO_STREAM=1 keeps the general kernel (A/B)
+        if (!cfg->exact && n == 6 && !getenv("MPCB_UKF_NO_STREAM")) {
+            size_t smem = 0;
+            UkfKernelFn ks = ukf_stream_kernel_n6(cfg->model_id, cfg->sqrt_mode, cfg->sigma_order, &smem);
+            if (ks != nullptr &&
+                cudaFuncSetAttribute(reinterpret_cast<const void*>(ks), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
+                h->k_fused = ks;
+                h->fused_smem = smem;
+            } else {
+                cudaGetLastError();
+            }
+        }
     }
     if (!h->k_predict || !h->k_update || !h->k_fused) {
         set_error("no UKF kernel for model %d / sqrt %d / order %d", cfg->model_id, cfg->sqrt_mode, cfg->sigma_order);
@@ -343,7 +358,7 @@ static mpcb_status ukf_create_impl(mpcb_ukf** out, const mpcb_ukf_cfg* cfg, cons
     }
     {
         int occ = 0, sms = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void*>(h->k_fused), kThreads, 0) != cudaSuccess ||
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void*>(h->k_fused), kThreads, h->fused_smem) != cudaSuccess ||
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device) != cudaSuccess || occ < 1 || sms < 1) {
             cudaGetLastError();
             occ = 0;

@@ -962,5 +962,7 @@ UkfKernelFn ukf_kernel_n4(int model_id, int sqrt_mode, int order, int mode);
 UkfKernelFn ukf_kernel_n6(int model_id, int sqrt_mode, int order, int mode);
 UkfKernelFn ukf_kernel_n4_fast(int model_id, int sqrt_mode, int order, int mode);
 UkfKernelFn ukf_kernel_n6_fast(int model_id, int sqrt_mode, int order, int mode);
+// fused fast kernels of the six-state models in the streaming form (ukf_stream_kernel.cuh, ukf_n6_stream.cu)
+UkfKernelFn ukf_stream_kernel_n6(int model_id, int sqrt_mode, int order, size_t* smem_bytes);
 
 }  // namespace mpcb

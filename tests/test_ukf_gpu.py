@@ -95,7 +95,11 @@ def test_trajectory_config3(gpu_required):
 
 
 def test_split_predict_update_equals_fused(gpu_required):
-    """predict() then update() (sigma points through HBM) == step() (sigma points in registers), bit for bit."""
+    """predict() then update() (sigma points through HBM) == step() (sigma points in registers), bit for bit — for the
+    four-state filters, whose fused step is the same kernel code.  The six-state fused step in fast arithmetic runs the
+    streaming kernel (ukf_stream_kernel.cuh: one-pass shifted transforms, algebraically the same sums): equal to the
+    split calls to rounding times the growth of four free-running steps of this filter (measured 6e-9 / 2e-8, bar 1e-6;
+    per step both are within 1e-7 of the oracle), and bit for bit again with exact=True."""
     B, T = 300, 4
     for name in ("PEN_NL", "PEN6"):
         model, oid, p, n, o, Q, R, P0, u, zs = make_problem(name, B, T, 3)
@@ -108,8 +112,23 @@ def test_split_predict_update_equals_fused(gpu_required):
                 b.step(u, zs[t])
             xa, Pa = a.get_state()
             xb, Pb = b.get_state()
-            np.testing.assert_array_equal(xa, xb)
-            np.testing.assert_array_equal(Pa, Pb)
+            if name == "PEN6":
+                assert relerr(xb, xa) < 1e-6 and relerr(Pb, Pa) < 1e-6, (relerr(xb, xa), relerr(Pb, Pa))
+            else:
+                np.testing.assert_array_equal(xa, xb)
+                np.testing.assert_array_equal(Pa, Pb)
+        if name == "PEN6":
+            with BatchedUkf(model, B, exact=True) as a, BatchedUkf(model, B, exact=True) as b:
+                a.init(np.zeros(n), P0, Q, R)
+                b.init(np.zeros(n), P0, Q, R)
+                for t in range(T):
+                    a.predict(u)
+                    a.update(zs[t])
+                    b.step(u, zs[t])
+                xa, Pa = a.get_state()
+                xb, Pb = b.get_state()
+                np.testing.assert_array_equal(xa, xb)
+                np.testing.assert_array_equal(Pa, Pb)
 
 
 def test_reference_style_single_filter(gpu_required):
