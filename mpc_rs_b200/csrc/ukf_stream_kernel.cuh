@@ -5,9 +5,10 @@
 // general fused kernel keeps the 78 propagated sigma-point doubles AND the 65 measurement doubles in registers across
 // the update — 255 registers, ~2 KB of spills per thread (ncu: long_scoreboard 1.7 cycles per issue from local memory),
 // and 150 KB of straight-line code because every sigma point's fx / hx / accumulation is unrolled.  Here
-//   * the sigma points live in shared memory, one column of 78 doubles per thread ([row][128 threads]: a warp's access
-//     is two conflict-free wavefronts), so fx, hx and the moment sums are REAL loops over the 13 points — the loop
-//     body exists once in the code — and
+//   * the 2n off-centre sigma points live in shared memory, 72 doubles per thread ([row][128 threads]: a warp's access
+//     is two conflict-free wavefronts; the centre point stays in registers), so fx, hx and the moment sums are REAL
+//     loops over the n pairs x +- L_j — the loop body exists once in the code, and the two points of a pair are two
+//     independent dependency chains for the scheduler — and
 //   * both unscented transforms are one-pass and SHIFTED: with y_0 the image of the centre point, d_i = y_i - y_0,
 //     s = sum_{i>=1} d_i and S = sum_{i>=1} d_i d_i^T,
 //         mean = y_0 + w_i s                                  (sum of the mean weights is 1)
