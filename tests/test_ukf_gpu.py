@@ -198,11 +198,13 @@ def test_failure_statuses(gpu_required):
             f.step(u, np.zeros((2, o)))
 
 
-def test_multi_step_device_run(gpu_required):
-    """run_device: T fused steps on device-resident z[T][o][B] equal T host-driven steps."""
+@pytest.mark.parametrize("name,T", [("PEN_LIN", 10), ("PEN6", 4), ("NL6_UKF", 3)])
+def test_multi_step_device_run(gpu_required, name, T):
+    """run_device: T fused steps on device-resident z[T][o][B] equal T host-driven steps, bit for bit — the pipelined
+    four-state kernel and the streaming six-state kernel (state in registers between steps vs through memory)."""
     import ctypes as C
-    B, T = 1000, 10
-    model, oid, p, n, o, Q, R, P0, u, zs = make_problem("PEN_LIN", B, T, 12)
+    B = 1000
+    model, oid, p, n, o, Q, R, P0, u, zs = make_problem(name, B, T, 12, 0.01 if name == "NL6_UKF" else 0.0)
     z_soa = np.ascontiguousarray(np.transpose(zs, (0, 2, 1)))  # [T][o][B]
     d_z = C.c_void_p()
     A.check(A.lib().mpcb_device_alloc(0, z_soa.nbytes, C.byref(d_z)))
@@ -210,10 +212,11 @@ def test_multi_step_device_run(gpu_required):
     with BatchedUkf(model, B) as a, BatchedUkf(model, B) as b:
         a.init(np.zeros(n), P0, Q, R)
         b.init(np.zeros(n), P0, Q, R)
-        a.run_device(T, d_z.value, u=u)
+        dt = 0.01 if name == "NL6_UKF" else 0.0
+        a.run_device(T, d_z.value, u=u, dt=dt)
         a.sync()
         for t in range(T):
-            b.step(u, zs[t])
+            b.step(u, zs[t], dt)
         xa, Pa = a.get_state()
         xb, Pb = b.get_state()
         np.testing.assert_array_equal(xa, xb)
