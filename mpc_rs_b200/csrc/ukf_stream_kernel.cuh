@@ -294,44 +294,94 @@ __global__ void __launch_bounds__(kUkfThreads, 2) ukf_stream_kernel(const __grid
 #pragma unroll
                 for (int c = 0; c < O; ++c) pxz[r][c] = fma(wi, Sxz[r][c], -we * dzm[c]);
             }
-            double pzi[O][O];
-            if (!inverse_small<O, true>(pz, pzi)) { st = MPCB_INVERSE_FAIL; break; }
-            double k[N][O];
+            // ---- gain K = Pxz Pz^-1 (src/ukf2.rs:67-68 forms the inverse): Gaussian elimination with partial pivoting on
+            // [Pz | Pxz^T] — Pz is symmetric, so K^T = Pz^-1 Pxz^T — with the row swaps as predicated selects; a zero pivot
+            // column is the reference's "Inverse fail".  No O x O inverse and no identity right-hand side exist. ----
+            double kt[O][N];
+#pragma unroll
+            for (int c = 0; c < O; ++c)
+#pragma unroll
+                for (int r = 0; r < N; ++r) kt[c][r] = pxz[r][c];
+            bool inv_ok = true;
+#pragma unroll
+            for (int kk = 0; kk < O; ++kk) {
+                // (full-range loops with compile-time guards: the triangular forms were left partly rolled, with pz and
+                // kt in local memory)
+                int piv = kk;
+                double best = fabs(pz[kk][kk]);
+#pragma unroll
+                for (int i = 0; i < O; ++i) {
+                    if (i > kk) {
+                        const double v = fabs(pz[i][kk]);
+                        if (v > best) { best = v; piv = i; }
+                    }
+                }
+                if (best == 0.0) inv_ok = false;
+#pragma unroll
+                for (int i = 0; i < O; ++i) {
+                    if (i > kk) {
+                        const bool sw = (piv == i);
+#pragma unroll
+                        for (int j = 0; j < O; ++j) {
+                            if (j >= kk) {
+                                const double a = pz[kk][j], bb = pz[i][j];
+                                pz[kk][j] = sw ? bb : a;
+                                pz[i][j] = sw ? a : bb;
+                            }
+                        }
+#pragma unroll
+                        for (int r = 0; r < N; ++r) {
+                            const double a = kt[kk][r], bb = kt[i][r];
+                            kt[kk][r] = sw ? bb : a;
+                            kt[i][r] = sw ? a : bb;
+                        }
+                    }
+                }
+                const double ip = 1.0 / pz[kk][kk];
+                pz[kk][kk] = ip;  // the diagonal keeps the reciprocal pivots for the back substitution
+#pragma unroll
+                for (int i = 0; i < O; ++i) {
+                    if (i > kk) {
+                        const double l = pz[i][kk] * ip;
+#pragma unroll
+                        for (int j = 0; j < O; ++j)
+                            if (j > kk) pz[i][j] = fma(-l, pz[kk][j], pz[i][j]);
+#pragma unroll
+                        for (int r = 0; r < N; ++r) kt[i][r] = fma(-l, kt[kk][r], kt[i][r]);
+                    }
+                }
+            }
+            if (!inv_ok) { st = MPCB_INVERSE_FAIL; break; }
+#pragma unroll
+            for (int ii = 0; ii < O; ++ii) {
+                constexpr int kLast = O - 1;
+                const int i = kLast - ii;
+#pragma unroll
+                for (int r = 0; r < N; ++r) {
+                    double acc = kt[i][r];
+#pragma unroll
+                    for (int j = 0; j < O; ++j)
+                        if (j > i) acc = fma(-pz[i][j], kt[j][r], acc);
+                    kt[i][r] = acc * pz[i][i];
+                }
+            }
+            // x += K (z - zp);  P -= K Pz K^T = Pxz K^T (K Pz is Pxz itself), symmetric (src/ukf2.rs:69-73)
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+                double acc = kt[0][r] * (zc[0] - zp[0]);
+#pragma unroll
+                for (int j = 1; j < O; ++j) acc = fma(kt[j][r], zc[j] - zp[j], acc);
+                x[r] += acc;
+            }
 #pragma unroll
             for (int r = 0; r < N; ++r)
 #pragma unroll
-                for (int c = 0; c < O; ++c) {
-                    double acc = pxz[r][0] * pzi[0][c];
-#pragma unroll
-                    for (int j = 1; j < O; ++j) acc = fma(pxz[r][j], pzi[j][c], acc);
-                    k[r][c] = acc;
-                }
-#pragma unroll
-            for (int r = 0; r < N; ++r) {
-                double acc = k[r][0] * (zc[0] - zp[0]);
-#pragma unroll
-                for (int j = 1; j < O; ++j) acc = fma(k[r][j], zc[j] - zp[j], acc);
-                x[r] += acc;
-            }
-            // P -= K Pz K^T = (K Pz) K^T, symmetric: upper triangle and mirror (src/ukf2.rs:71-73)
-#pragma unroll
-            for (int r = 0; r < N; ++r) {
-                double kp[O];
-#pragma unroll
-                for (int c = 0; c < O; ++c) {
-                    double acc = k[r][0] * pz[0][c];
-#pragma unroll
-                    for (int j = 1; j < O; ++j) acc = fma(k[r][j], pz[j][c], acc);
-                    kp[c] = acc;
-                }
-#pragma unroll
                 for (int c = r; c < N; ++c) {
-                    double acc = kp[0] * k[c][0];
+                    double acc = pxz[r][0] * kt[0][c];
 #pragma unroll
-                    for (int j = 1; j < O; ++j) acc = fma(kp[j], k[c][j], acc);
+                    for (int j = 1; j < O; ++j) acc = fma(pxz[r][j], kt[j][c], acc);
                     PS(r, c) -= acc;
                 }
-            }
 #pragma unroll
             for (int c = 0; c < O; ++c) zc[c] = zn[c];
         }
