@@ -449,36 +449,44 @@ __device__ __forceinline__ bool inverse_small(const double (&A)[O][O], double (&
                 lu[i][j] = A[i][j];
                 rhs[i][j] = (i == j) ? 1.0 : 0.0;
             }
+        // (full-range loops with compile-time guards: nvcc left the triangular forms partly rolled, with lu / rhs in local memory)
 #pragma unroll
         for (int k = 0; k < O; ++k) {
             int piv = k;
             double best = fabs(lu[k][k]);
 #pragma unroll
-            for (int i = k + 1; i < O; ++i) {
-                const double v = fabs(lu[i][k]);
-                if (v > best) { best = v; piv = i; }
+            for (int i = 0; i < O; ++i) {
+                if (i > k) {
+                    const double v = fabs(lu[i][k]);
+                    if (v > best) { best = v; piv = i; }
+                }
             }
             if (best == 0.0) ok = false;
 #pragma unroll
-            for (int i = k + 1; i < O; ++i) {
-                const bool sw = (piv == i);
+            for (int i = 0; i < O; ++i) {
+                if (i > k) {
+                    const bool sw = (piv == i);
 #pragma unroll
-                for (int j = 0; j < O; ++j) {
-                    const double a = lu[k][j], b = lu[i][j];
-                    lu[k][j] = sw ? b : a;
-                    lu[i][j] = sw ? a : b;
-                    const double ra = rhs[k][j], rb = rhs[i][j];
-                    rhs[k][j] = sw ? rb : ra;
-                    rhs[i][j] = sw ? ra : rb;
+                    for (int j = 0; j < O; ++j) {
+                        const double a = lu[k][j], b = lu[i][j];
+                        lu[k][j] = sw ? b : a;
+                        lu[i][j] = sw ? a : b;
+                        const double ra = rhs[k][j], rb = rhs[i][j];
+                        rhs[k][j] = sw ? rb : ra;
+                        rhs[i][j] = sw ? ra : rb;
+                    }
                 }
             }
             const double d = lu[k][k];
 #pragma unroll
-            for (int i = k + 1; i < O; ++i) {
-                lu[i][k] /= d;
-                const double l = lu[i][k];
+            for (int i = 0; i < O; ++i) {
+                if (i > k) {
+                    lu[i][k] /= d;
+                    const double l = lu[i][k];
 #pragma unroll
-                for (int j = k + 1; j < O; ++j) lu[i][j] -= l * lu[k][j];
+                    for (int j = 0; j < O; ++j)
+                        if (j > k) lu[i][j] -= l * lu[k][j];
+                }
             }
         }
 #pragma unroll
@@ -488,14 +496,18 @@ __device__ __forceinline__ bool inverse_small(const double (&A)[O][O], double (&
             for (int i = 0; i < O; ++i) {
                 double s = rhs[i][c];
 #pragma unroll
-                for (int j = 0; j < i; ++j) s -= lu[i][j] * y[j];
+                for (int j = 0; j < O; ++j)
+                    if (j < i) s -= lu[i][j] * y[j];
                 y[i] = s;
             }
 #pragma unroll
-            for (int i = O - 1; i >= 0; --i) {
+            for (int ii = 0; ii < O; ++ii) {
+                constexpr int kLast = O - 1;
+                const int i = kLast - ii;
                 double s = y[i];
 #pragma unroll
-                for (int j = i + 1; j < O; ++j) s -= lu[i][j] * Ai[j][c];
+                for (int j = 0; j < O; ++j)
+                    if (j > i) s -= lu[i][j] * Ai[j][c];
                 Ai[i][c] = s / lu[i][i];
             }
         }
