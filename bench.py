@@ -56,7 +56,7 @@ UKF_B = 1 << 20
 UKF_T = 100  # T = 100 steps, as examples/ukf-pen.rs:154-178 runs
 UKF_BYTES = 336.0  # 8*(2n + 2n^2 + o), n=4, o=2
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from this round's ncu --set full captures of these kernels
-# (profiles/mppi_r2d_ncu_full_summary.txt, profiles/ukf_r2d_ncu_full_summary.txt; tools/prof_round.sh) — the one roofline
+# (profiles/mppi_r2e_ncu_full_summary.txt, profiles/ukf_r2e_ncu_full_summary.txt; tools/prof_round.sh) — the one roofline
 # field that cannot be measured inside this run
 MPPI_DRAM_TRAFFIC_BYTES = 70_912 + 0
 UKF_DRAM_TRAFFIC_BYTES = 138_444_288 + 62_852_096

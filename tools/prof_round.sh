@@ -17,10 +17,10 @@ python tools/prof_ukf.py 1048576 4 PEN_LIN > gpurun_out/prof_${tag}_ukf_plain.lo
 ncu --set full --clock-control none --import-source on -k regex:ukf_kernel -s 2 -c 2 -o gpurun_out/prof_${tag}_ukf -f \
     python tools/prof_ukf.py 1048576 4 PEN_LIN > gpurun_out/prof_${tag}_ukf_ncu.log 2>&1
 echo "ukf rc=$?"
-#   4. --set full of the six-state library UKF (NL6_UKF, eigen square root) at B = 2^18
+#   4. --set full of the six-state library UKF (NL6_UKF, eigen square root; the streaming kernel) at B = 2^18
 #   5. --set full of the MPCB_F64_FAST rollout kernel on the config #4 shape (1024 of its 4096 controllers)
 python tools/prof_ukf.py 262144 2 NL6_UKF > gpurun_out/prof_${tag}_ukf6_plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:ukf_kernel -s 1 -c 1 -o gpurun_out/prof_${tag}_ukf6 -f \
+ncu --set full --clock-control none --import-source on -k regex:ukf_stream -s 1 -c 1 -o gpurun_out/prof_${tag}_ukf6 -f \
     python tools/prof_ukf.py 262144 2 NL6_UKF > gpurun_out/prof_${tag}_ukf6_ncu.log 2>&1
 echo "ukf6 rc=$?"
 python tools/prof_mppi_cl.py f64fast 1024 > gpurun_out/prof_${tag}_f64fast_plain.log 2>&1 &&
