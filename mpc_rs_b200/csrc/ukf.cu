@@ -338,9 +338,14 @@ static mpcb_status ukf_create_impl(mpcb_ukf** out, const mpcb_ukf_cfg* cfg, cons
         h->k_predict = pick(cfg->model_id, cfg->sqrt_mode, cfg->sigma_order, UKF_PREDICT);
         h->k_update = pick(cfg->model_id, cfg->sqrt_mode, cfg->sigma_order, UKF_UPDATE);
         h->k_fused = pick(cfg->model_id, cfg->sqrt_mode, cfg->sigma_order, UKF_FUSED);
-        // six-state filters in fast arithmetic: the fused step runs the streaming kernel (ukf_stream_kernel.cuh: sigma
+        // six-state filters in fast arithmetic: the split predict / update calls run the reference-order kernels — the general
+        // fast kernel's unshifted sums lose the state on NL6_UKF with covariances >> 1 (tools/dev_ukf6_random.py: Cholesky,
+        // 8 x a Wishart matrix, x off by 7 where the reference-order and the streaming kernel agree with the oracle to 3e-5) —
+        // and the fused step runs the streaming kernel (ukf_stream_kernel.cuh: sigma
         // points in shared memory, one-pass shifted transforms); MPCB_UKF_NO_STREAM=1 keeps the general kernel (A/B)
         if (!cfg->exact && n == 6 && !getenv("MPCB_UKF_NO_STREAM")) {
+            h->k_predict = ukf_kernel_n6(cfg->model_id, cfg->sqrt_mode, cfg->sigma_order, UKF_PREDICT);
+            h->k_update = ukf_kernel_n6(cfg->model_id, cfg->sqrt_mode, cfg->sigma_order, UKF_UPDATE);
             size_t smem = 0;
             UkfKernelFn ks = ukf_stream_kernel_n6(cfg->model_id, cfg->sqrt_mode, cfg->sigma_order, &smem);
             if (ks != nullptr &&

@@ -308,6 +308,61 @@ def test_many_tiles_per_block_ragged_batch(gpu_required, name, steps_per_launch)
     assert np.all(np.isfinite(xg)) and np.all(np.isfinite(Pg))
 
 
+def test_six_state_streaming_kernel_random_covariances_and_failures(gpu_required):
+    """The fused six-state step in fast arithmetic runs ukf_stream_kernel (sigma points in shared memory, one-pass shifted
+    transforms, gain by elimination): random states, random covariances (sometimes NOT positive definite for the Cholesky
+    square root), random Q / R / z, both models and both square roots against the oracle: the oracle's failure status for
+    exactly the same filters, failed filters keep their state, a singular Pz is "Inverse fail" as in the reference, and the
+    state and covariance are as close to the oracle as the REFERENCE-ORDER kernel is on the same draw (within 20x, floor
+    1e-6).  The yardstick is relative on purpose: on random covariances the reference algorithm itself is ill-conditioned
+    on these models — two faithful f64 evaluations of src/ukf2.rs (oracle, exact kernel) disagree by 1e-9 at small
+    covariances and 1e-5..3e-3 at 10..50 x a Wishart matrix (tools/dev_ukf6_random.py); the streaming kernel stays with
+    them everywhere, the general fast kernel's unshifted sums do not (NL6_UKF, Cholesky, scale 8: x off by 7)."""
+    rng = np.random.default_rng(20240611)
+    for name in ("PEN6", "NL6_UKF"):
+        model, oid, u = MODELS[name]
+        p = O.model_defaults(oid)
+        n, o = O.dims(oid)
+        dt = 0.01 if name == "NL6_UKF" else 0.0
+        for sqrt_mode in ("eig", "cholesky"):
+            for trial in range(4):
+                B = int(rng.integers(1, 300))
+                a = rng.normal(0, 1, (B, n, n))
+                scale = float(np.exp(rng.uniform(np.log(1e-3), np.log(50.0))))
+                P = scale * (a @ np.transpose(a, (0, 2, 1)) + 0.05 * np.eye(n))
+                bad = -1
+                if sqrt_mode == "cholesky" and trial % 2 == 1:
+                    bad = int(rng.integers(0, B))
+                    P[bad] = -P[bad]
+                x = rng.normal(0, 0.2, (B, n))
+                Q = np.diag(rng.uniform(0, 1, n))
+                R = np.diag(rng.uniform(0.05, 5.0, o))
+                z = rng.normal(0, 1, (B, o))
+                xr, Pr, st_o = O.ukf_step_batch(oid, p, x, P, Q, R, u, z, dt, SQRT[sqrt_mode], O.ORDER_LIBRARY)
+                res = {}
+                for exact in (False, True):
+                    with BatchedUkf(model, B, sqrt_mode=sqrt_mode, sigma_order="library", exact=exact) as f:
+                        f.init(np.zeros(n), np.eye(n), Q, R)
+                        f.set_state(x, P)
+                        f.step(u, z, dt, check=False)
+                        res[exact] = (f.status(), *f.get_state())
+                st_g, xg, Pg = res[False]
+                assert np.array_equal(st_g != 0, np.asarray(st_o) != 0), (name, sqrt_mode, st_g, st_o)
+                ok = np.asarray(st_o) == 0
+                ex_x, ex_P = relerr(res[True][1][ok], xr[ok]), relerr(res[True][2][ok], Pr[ok])
+                assert relerr(xg[ok], xr[ok]) < max(20 * ex_x, 1e-6), (name, sqrt_mode, scale, relerr(xg[ok], xr[ok]), ex_x)
+                assert relerr(Pg[ok], Pr[ok]) < max(20 * ex_P, 1e-6), (name, sqrt_mode, scale, relerr(Pg[ok], Pr[ok]), ex_P)
+                np.testing.assert_allclose(Pg[ok], np.transpose(Pg[ok], (0, 2, 1)), rtol=0, atol=0)  # exactly symmetric
+                if bad >= 0:
+                    assert st_g[bad] == A.CHOLESKY_FAIL
+                    np.testing.assert_array_equal(Pg[bad], P[bad])
+                    np.testing.assert_array_equal(xg[bad], x[bad])
+        with BatchedUkf(model, 3, exact=False) as f:
+            f.init(np.zeros(n), np.zeros((n, n)), np.zeros((n, n)), np.zeros((o, o)))  # P = Q = R = 0 -> Pz = 0
+            with pytest.raises(UkfError, match="Inverse fail"):
+                f.step(u, np.zeros((3, o)), dt)
+
+
 def test_property_random_covariances_and_failures(gpu_required):
     """SURVEY.md §4 property layer for the filter: hypothesis draws (model, square root, state, a random covariance that is
     sometimes NOT positive definite, Q, R, z); one fused step of the reference-order kernel must give the oracle's state
