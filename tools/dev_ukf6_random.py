@@ -9,7 +9,8 @@ sys.path.insert(0, "tests")
 import oracle_lib as O
 from mpc_rs_b200 import BatchedUkf, models
 
-MODELS = {"PEN6": (models.PEN6, O.MODEL_PEN6, 0.1), "NL6_UKF": (models.NL6_UKF, O.MODEL_NL6_UKF, 0.3)}
+MODELS = {"PEN6": (models.PEN6, O.MODEL_PEN6, 0.1), "NL6_UKF": (models.NL6_UKF, O.MODEL_NL6_UKF, 0.3),
+          "PEN_LIN": (models.PEN_LIN, O.MODEL_PEN_LIN, 0.0015), "PEN_NL": (models.PEN_NL, O.MODEL_PEN_NL, 0.1)}
 SQRT = {"cholesky": O.SQRT_CHOLESKY, "eig": O.SQRT_EIG}
 
 
@@ -18,7 +19,7 @@ def relerr(a, b):
 
 
 rng = np.random.default_rng(20240611)
-for name in ("PEN6", "NL6_UKF"):
+for name in (sys.argv[1:] or ["PEN6", "NL6_UKF"]):
     model, oid, u = MODELS[name]
     p = O.model_defaults(oid)
     n, o = O.dims(oid)
