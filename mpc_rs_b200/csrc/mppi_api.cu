@@ -8,6 +8,7 @@
 #include <new>
 
 #include "mppi_ws_kernel.cuh"
+#include "mppi_short_kernel.cuh"
 #include "mppi_rtc.h"
 #include "nccl_shim.h"
 
@@ -318,6 +319,33 @@ mpcb_status pick_kernels(mpcb_mppi* h) {
                 if (plan.chunks < 1) plan.chunks = 1;
             }
             h->ws_variant = pick;
+        }
+    }
+    // FP64, H <= 8, several batches per block (BASELINE config #4: 4096 controllers x 8192 samples x 8 steps): the
+    // register-accumulating kernel (mppi_short_kernel.cuh) — no tile, no per-batch softmax passes.  A block that walks
+    // fewer than four batches keeps the fused kernel (its one merge of 9 sums per thread would not be amortised).
+    // MPCB_MPPI_SHORT=0 disables, =1 forces it for every FP64 plan with H <= 8.
+    if (f64 && !h->user && h->H <= kShortHorizon) {
+        const char* sh_env = getenv("MPCB_MPPI_SHORT");
+        const int want = sh_env ? atoi(sh_env) : -1;  // -1: auto
+        auto short_of = [&](int noise) { return f64_fast ? mppi_kernel_f64fast_short(h->cfg.model_id, noise) : mppi_kernel_f64_short(h->cfg.model_id, noise); };
+        if (want != 0 && short_of(NOISE_GENERATE) != nullptr) {
+            Plan ps;
+            ps.spt = 1;
+            ps.sb = ps.block = kShortBlock;
+            ps.vt = 0;
+            ps.smem = mppi_smem_bytes<double>(h->H, kShortBlock, false);
+            for (int noise = 0; noise < 3; ++noise) {
+                ps.k[noise] = short_of(noise);
+                MPCB_CUDA_TRY(cudaFuncSetAttribute((const void*)ps.k[noise], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps.smem));
+            }
+            MPCB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps.occ, (const void*)ps.k[NOISE_GENERATE], ps.block, ps.smem));
+            if (ps.occ < 1) ps.occ = 1;
+            const long long nbatches = (h->W * 32 + ps.sb - 1) / ps.sb;
+            ps.chunks = (long long)ps.occ * h->num_sms / h->C;
+            if (ps.chunks > nbatches) ps.chunks = nbatches;
+            if (ps.chunks < 1) ps.chunks = 1;
+            if (want == 1 || (!plan.single_batch && nbatches / ps.chunks >= 4)) plan = ps;
         }
     }
     h->spt = plan.spt;

@@ -531,3 +531,86 @@ def test_merge_wait_timeout_is_reported(gpu_required, monkeypatch):
         monkeypatch.delenv("MPCB_MPPI_WS_DEBUG")
         with Mppi(20, 60000, model=model, lam=lam, std_dev=sig, limit=lim, precision="f32", dt=0.04) as m:
             assert np.all(np.isfinite(m.compute(X0, np.zeros(20))))
+
+
+@pytest.mark.parametrize("precision", ["f64", "f64fast"])
+def test_short_horizon_kernel(gpu_required, monkeypatch, precision):
+    """mppi_short_kernel.cuh (FP64, H <= 8: the softmax of a thread's samples stays in registers, one block merge):
+    forced for every shape with MPCB_MPPI_SHORT=1 and held to the bounds of the fused FP64 kernels — closed-loop replay
+    parity on the three shipped H = 8 cases, ragged sizes and horizons, several controllers, generate -> dump -> oracle."""
+    monkeypatch.setenv("MPCB_MPPI_SHORT", "1")
+    for case in ("L_shipped", "NL_shipped", "NL6_shipped"):
+        for u_g, u_o, ig, io, c_g, c_o in closed_loop(case, 16384, precision):
+            assert ig["argmax"] == io["argmax"] and ig["n_finite"] == io["n_finite"]
+            near = c_o > io["max"] - 1e4
+            np.testing.assert_allclose(c_g[near], c_o[near], rtol=1e-6, atol=1e-8)
+            assert abs(ig["max"] - io["max"]) <= 1e-8 * abs(io["max"]) + 1e-11
+            assert abs(ig["sum"] - io["sum"]) <= 1e-8 * io["sum"]
+            assert rel_err(u_g, u_o) < 1e-9
+    model, oid, _, dt, lam, sig, lim = CASES["NL6_shipped"]
+    p = O.model_defaults(oid, dt=dt)
+    rng = np.random.default_rng(77)
+    for K, H in ((1, 8), (33, 1), (4097, 5), (100003, 7), (300001, 8)):
+        eps = sig * rng.standard_normal((K, H))
+        u_n = rng.uniform(-1, 1, H)
+        st, u_o, io, _ = O.mppi_compute(oid, p, K, H, lam, sig, lim[0], lim[1], X0, u_n, eps)
+        assert st == 0
+        with Mppi(H, K, model=model, lam=lam, std_dev=sig, limit=lim, precision=precision, dt=dt, seed=9) as m:
+            u_g = m.compute_replay(X0, u_n, eps)
+            assert m.info[0]["argmax"] == io["argmax"] and m.info[0]["n_finite"] == io["n_finite"], (K, H)
+            assert rel_err(u_g, u_o) < 1e-9, (K, H, rel_err(u_g, u_o))
+            u_gen, eps_gen = m.compute_dump(X0, u_n)
+            st2, u_o2, io2, _ = O.mppi_compute(oid, p, K, H, lam, sig, lim[0], lim[1], X0, u_n, eps_gen.astype(np.float64))
+            assert st2 == 0 and m.info[0]["argmax"] == io2["argmax"]
+            assert rel_err(u_gen, u_o2) < 1e-9, (K, H)
+    # 37 controllers x 8192 samples: the shape class the selection takes by itself (>= 4 batches per block)
+    monkeypatch.delenv("MPCB_MPPI_SHORT")
+    C, K, H = 37, 8192, 8
+    xs = rng.normal(0, 0.1, (C, 4))
+    us = rng.uniform(-1, 1, (C, H))
+    eps = sig * rng.standard_normal((C, K, H))
+    with Mppi(H, K, model=model, lam=lam, std_dev=sig, limit=lim, precision=precision, dt=dt, controllers=C) as m:
+        u_g = m.compute_replay(xs, us, eps)
+        for c in range(0, C, 4):
+            st, u_o, io, _ = O.mppi_compute(oid, p, K, H, lam, sig, lim[0], lim[1], xs[c], us[c], eps[c])
+            assert m.info[c]["argmax"] == io["argmax"]
+            assert rel_err(u_g[c], u_o) < 1e-9
+
+
+def test_short_horizon_kernel_error_semantics(gpu_required, monkeypatch):
+    """The poisoned-sample property of test_property_random_problems_with_poisoned_samples on the short-horizon kernel: the
+    same Err of src/mppi.rs:69,77,88 as the oracle, or the same controls and argmin."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    monkeypatch.setenv("MPCB_MPPI_SHORT", "1")
+    finite = dict(allow_nan=False, allow_infinity=False)
+
+    @settings(max_examples=40, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(case=st.sampled_from(["L_shipped", "NL_shipped", "NL6_shipped"]), K=st.integers(1, 1500), H=st.integers(1, 8),
+           lam=st.floats(0.05, 5.0, **finite), sig=st.floats(0.1, 6.0, **finite), seed=st.integers(0, 2 ** 31 - 1),
+           poison=st.sampled_from([None, "nan", "inf", "-inf", "nan_state"]), prec=st.sampled_from(["f64", "f64fast"]))
+    def check(case, K, H, lam, sig, seed, poison, prec):
+        model, oid, _, dt, _, _, _ = CASES[case]
+        lo, hi = -12.0, 9.0
+        p = O.model_defaults(oid, dt=dt)
+        rng = np.random.default_rng(seed)
+        x = rng.normal(0, 0.3, 4)
+        u_n = rng.uniform(lo, hi, H)
+        eps = sig * rng.standard_normal((K, H))
+        if poison == "nan_state":
+            x[rng.integers(0, 4)] = np.nan
+        elif poison is not None:
+            eps[rng.integers(0, K), rng.integers(0, H)] = {"nan": np.nan, "inf": np.inf, "-inf": -np.inf}[poison]
+        st_o, u_o, io, _ = O.mppi_compute(oid, p, K, H, lam, sig, lo, hi, x, u_n, eps)
+        with Mppi(H, K, model=model, lam=lam, std_dev=sig, limit=(lo, hi), precision=prec, dt=dt) as m:
+            try:
+                u_g = m.compute_replay(x, u_n, eps)
+                st_g = 0
+            except MppiError as e:
+                st_g, u_g = e.status, None
+            assert st_g == st_o, (prec, st_g, st_o, poison)
+            if st_o == 0:
+                assert m.info[0]["argmax"] == io["argmax"]
+                assert case == "NL6_shipped" or m.info[0]["n_finite"] == io["n_finite"]
+                assert rel_err(u_g, u_o) < 1e-8, rel_err(u_g, u_o)
+
+    check()
