@@ -20,9 +20,12 @@
 namespace mpcb {
 
 constexpr int kShortHorizon = 8;
+#ifndef MPCB_SHORT_MINB
+#define MPCB_SHORT_MINB 4  // resident blocks of 128 threads per SM the register budget is set for
+#endif
 
 template <template <typename> class ModelT, int BLOCK, int NOISE, int HMAX>
-__global__ void __launch_bounds__(BLOCK, (512 / BLOCK > 0 ? 512 / BLOCK : 1)) mppi_short_kernel(const __grid_constant__ MppiParams p) {
+__global__ void __launch_bounds__(BLOCK, MPCB_SHORT_MINB) mppi_short_kernel(const __grid_constant__ MppiParams p) {
     using real = double;
     static_assert(HMAX % 4 == 0 && HMAX <= 16, "whole Philox blocks, registers");
     constexpr int NW = BLOCK / 32;
