@@ -99,6 +99,10 @@ if __name__ == "__main__":
     mppi_case("f32 L odd horizon", 7, 5000, models.L, "f32", env=nospin)
     mppi_case("f64 NL6", 8, 5000, models.NL6, "f64", env=nospin)
     mppi_case("f32 replay", 16, 4096, models.NL, "f32", replay=True, env=nospin)
+    short = {"MPCB_MPPI_SHORT": "1", **nospin}
+    mppi_case("f64fast short-horizon kernel", 8, 20000, models.NL6, "f64fast", env=short)
+    mppi_case("f64 short-horizon kernel, odd horizon, batched", 5, 3001, models.NL, "f64", controllers=7, env=short)
+    mppi_case("f64fast short-horizon kernel, replay", 8, 4096, models.L, "f64fast", replay=True, env=short)
     mppi_case("f32 batched controllers", 8, 2048, models.NL6, "f32", controllers=24, env=nospin)
     mppi_case("f32 batched packed", 8, 8192, models.NL6, "f32", controllers=8, env={"MPCB_MPPI_SPT": "2", **nospin})
     mppi_case("f32 no v tile", 40, 4096, models.NL, "f32", controllers=8, env={"MPCB_MPPI_VT": "0", **nospin})
