@@ -57,6 +57,19 @@ def test_mppi_configs1_kernel_resources():
     assert e[name]["regs"] <= 128 and e[name]["spill_st"] <= 128, e[name]
 
 
+def test_mppi_short_horizon_kernel_resources():
+    # mppi_short_kernel<ModelNL6F, BLOCK=128, NOISE_GENERATE=0, HMAX=8>: the MPPI of BASELINE config #4.
+    # 128 registers = four resident blocks of 128 threads per SM; the softmax state (9 FP64 sums, 8 controls) lives in
+    # registers, so the only local memory is the merge tail's (the same 280 / 276 bytes the fused FP64 kernels have).
+    e = entries("mppi_f64fast_short.o.ptxas.log")
+    name = "_ZN4mpcb17mppi_short_kernelINS_9ModelNL6FELi128ELi0ELi8EEEvNS_10MppiParamsE"
+    assert name in e, sorted(e)[:4]
+    k = e[name]
+    assert k["regs"] <= 128 and k["spill_st"] <= 288 and k["spill_ld"] <= 288, k
+    assert 0 < k["smem"] <= 1024, k   # static: the warps' nine sums; everything else is the small dynamic row area
+    assert len([n for n in e if "mppi_short_kernel" in n]) == 9  # three models x three noise modes
+
+
 def test_ukf_config3_kernel_resources():
     # ukf_kernel<4, 2, PEN_LIN=16, CHOLESKY=0, INTERLEAVED=1, FUSED=2, FAST=true>
     e = entries("ukf_n4_fast.o.ptxas.log")

@@ -577,6 +577,38 @@ def test_short_horizon_kernel(gpu_required, monkeypatch, precision):
             assert rel_err(u_g[c], u_o) < 1e-9
 
 
+def test_short_horizon_kernel_sharded(gpu_required, monkeypatch):
+    """The short-horizon kernel as a sample shard: three handles on one device reduce their shards to partial
+    rows (k_offset, global replay rows, FINAL_RANK_ROW tail), the combined rows equal the oracle's control over all K."""
+    import ctypes as C
+    monkeypatch.setenv("MPCB_MPPI_SHORT", "1")
+    model, oid, H, dt, lam, sig, lim = CASES["NL6_shipped"]
+    K, G = 50001, 3
+    p = O.model_defaults(oid, dt=dt)
+    rng = np.random.default_rng(23)
+    u_n = rng.uniform(-2, 2, H)
+    eps = sig * rng.standard_normal((K, H))
+    st, u_o, io, _ = O.mppi_compute(oid, p, K, H, lam, sig, lim[0], lim[1], X0, u_n, eps)
+    assert st == 0
+    d_eps, d_rows = C.c_void_p(), C.c_void_p()
+    A.check(A.lib().mpcb_device_alloc(0, eps.nbytes, C.byref(d_eps)))
+    A.check(A.lib().mpcb_device_upload(0, d_eps, eps.ctypes.data_as(C.c_void_p), eps.nbytes))
+    for prec in ("f64", "f64fast"):
+        hs = [Mppi(H, K, model=model, lam=lam, std_dev=sig, limit=lim, precision=prec, dt=dt, rank=r, world_size=G)
+              for r in range(G)]
+        PL = hs[0].partial_len
+        A.check(A.lib().mpcb_device_alloc(0, 8 * PL * G, C.byref(d_rows)))
+        for r, h in enumerate(hs):
+            h.compute_partial(X0, u_n, d_rows.value + 8 * PL * r, d_eps=d_eps.value, eps_dtype=A.DT_F64)
+        u_g = hs[0].combine(d_rows.value, G)
+        assert hs[0].info[0]["argmax"] == io["argmax"] and hs[0].info[0]["n_finite"] == io["n_finite"]
+        assert rel_err(u_g, u_o) < 1e-9, (prec, rel_err(u_g, u_o))
+        for h in hs:
+            h.close()
+        A.lib().mpcb_device_free(0, d_rows)
+    A.lib().mpcb_device_free(0, d_eps)
+
+
 def test_short_horizon_kernel_error_semantics(gpu_required, monkeypatch):
     """The poisoned-sample property of test_property_random_problems_with_poisoned_samples on the short-horizon kernel: the
     same Err of src/mppi.rs:69,77,88 as the oracle, or the same controls and argmin."""
