@@ -63,6 +63,10 @@ struct mpcb_mppi {
     mpcb_mppi_info* h_info_dev = nullptr;
     unsigned int* h_done = nullptr;      // mapped completion word the host spins on (C == 1)
     unsigned int* h_done_dev = nullptr;
+    // C == 1 with the single-level warp merge: results as self-validating cells (MppiParams::host_cells), no fence, no word
+    unsigned long long* h_cells = nullptr;      // mapped: [2 * (H + 5)]
+    unsigned long long* h_cells_dev = nullptr;
+    bool use_cells = false;
     unsigned int epoch = 0;
     bool costs_valid = false;
     uint32_t call_idx = 0;
@@ -482,8 +486,45 @@ mpcb_status stage_inputs(mpcb_mppi* h, MppiParams& p, const double* x, const dou
 // Single controller: the final block stores an epoch word after the results; spinning on it avoids the wake-up
 // latency of cudaStreamSynchronize.  After ~2 ms without completion (or for C > 1) fall back to the stream sync,
 // which also surfaces any launch/runtime error.
-mpcb_status finish_host(mpcb_mppi* h, double* u_out, mpcb_mppi_info* info, bool spin, int words) {
+mpcb_status finish_host(mpcb_mppi* h, double* u_out, mpcb_mppi_info* info, bool spin, int words, bool cells = false) {
     bool done = false;
+    if (cells) {
+        // every result word arrives as two cells (half | epoch << 32): wait for each cell to show this call's epoch
+        const volatile unsigned long long* cell = h->h_cells;
+        const unsigned long long want = h->epoch;
+        const int nwords = h->H + 5;
+        unsigned long long out[kMaxHorizon + 5];
+        long budget = 4000000;
+        for (int pass = 0; pass < 2 && !done; ++pass) {
+            int i = 0;
+            while (i < nwords) {
+                const unsigned long long lo = cell[2 * i], hi = cell[2 * i + 1];
+                if ((lo >> 32) == want && (hi >> 32) == want) {
+                    out[i] = (lo & 0xffffffffull) | (hi << 32);
+                    ++i;
+                    continue;
+                }
+                if (--budget <= 0) break;
+                cpu_relax();
+            }
+            done = (i == nwords);
+            if (!done) {  // ~2 ms without the results: the stream sync surfaces a launch / runtime error, then one more look
+                MPCB_CUDA_TRY(cudaStreamSynchronize(h->stream));
+                budget = 1000;
+            }
+        }
+        if (!done) {
+            set_error("MPPI results did not reach the host cells (epoch %u)", h->epoch);
+            return MPCB_CUDA_ERROR;
+        }
+        memcpy(u_out, out, (size_t)h->H * sizeof(double));
+        mpcb_mppi_info hi_;
+        memcpy(&hi_, out + h->H, sizeof(hi_));
+        h->h_info[0] = hi_;  // mpcb_mppi_last_info reads the mirror
+        memcpy(h->h_out, out, (size_t)h->H * sizeof(double));
+        if (info) *info = hi_;
+        return (mpcb_status)hi_.status;
+    }
     if (spin) {
         // one completion word per merger block of the final merge
         volatile unsigned int* flag = h->h_done;
@@ -546,6 +587,9 @@ mpcb_status compute_host(mpcb_mppi* h, const double* x, const double* u_in, cons
         }
         if (peer) set_peer_params(h, p);
     }
+    // the single-level warp merge (the condition of `pair_major` in mppi_block_tail) hands the results over as cells
+    const bool cells = spin && h->use_cells && h->groups == 1 && h->mergers >= 1 && (!sharded || (peer && h->peer_ll));
+    if (cells) p.host_cells = h->h_cells_dev;
     st = launch(h, p);
     if (st != MPCB_OK) return st;
     if (sharded && !peer) {
@@ -554,7 +598,7 @@ mpcb_status compute_host(mpcb_mppi* h, const double* x, const double* u_in, cons
     }
     const int words = (sharded && !peer) ? 1 : (h->mergers > 0 ? h->mergers : 1);
     const double tr1 = h->trace ? host_now_us() : 0.0;
-    st = finish_host(h, u_out, info, spin, words);
+    st = finish_host(h, u_out, info, spin, words, cells);
     if (h->trace) {
         const double tr2 = host_now_us();
         h->tr_launch += tr1 - tr0;
@@ -748,6 +792,13 @@ static mpcb_status create_impl(mpcb_mppi** out, const mpcb_mppi_cfg* cfg, const 
     TRY_OR_FAIL(cudaHostAlloc(&h->h_done, 64, cudaHostAllocMapped));
     memset(h->h_done, 0, 64);
     TRY_OR_FAIL(cudaHostGetDevicePointer((void**)&h->h_done_dev, h->h_done, 0));
+    if (C == 1) {
+        const size_t cell_bytes = 2 * (H + 5) * sizeof(unsigned long long);
+        TRY_OR_FAIL(cudaHostAlloc(&h->h_cells, cell_bytes, cudaHostAllocMapped));
+        memset(h->h_cells, 0, cell_bytes);  // epoch 0 is never a call's epoch
+        TRY_OR_FAIL(cudaHostGetDevicePointer((void**)&h->h_cells_dev, h->h_cells, 0));
+        h->use_cells = getenv("MPCB_MPPI_HOST_CELLS") == nullptr || atoi(getenv("MPCB_MPPI_HOST_CELLS")) != 0;
+    }
 #undef TRY_OR_FAIL
     *out = h;
     return MPCB_OK;
@@ -799,6 +850,7 @@ void mpcb_mppi_destroy(mpcb_mppi* h) {
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_info) cudaFreeHost(h->h_info);
     if (h->h_done) cudaFreeHost(h->h_done);
+    if (h->h_cells) cudaFreeHost(h->h_cells);
     if (h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
     delete h;

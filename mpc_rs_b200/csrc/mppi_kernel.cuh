@@ -79,6 +79,10 @@ struct MppiParams {
     double* rank_partial;    // [C][kPartialHdr + H]
     unsigned int* done_host;       // mapped host word; the final block stores `epoch` after u_out/info (C == 1 only)
     unsigned int epoch, pad1;
+    // Host hand-over without a fence (C == 1, single-level warp merge): every 8-byte result word goes to mapped host
+    // memory as two self-validating cells (data half | epoch << 32), one 64-bit store each; the host polls the cells
+    // (mppi_api.cu finish_host).  nullptr: u_out_host / info_host + fence.sys + done_host words as before.
+    unsigned long long* host_cells;  // [2 * (H + 5)]: u_out[0..H), then the five words of mpcb_mppi_info
     // FINAL_PEER_EXCHANGE: device tables [G] of every rank's mailbox / flag base (own entry included)
     //   mailbox: [2 parity][G source ranks][C][kPartialHdr + H] doubles;  flags: [2][G][C] u32
     double* const* peer_mbox;
@@ -220,6 +224,15 @@ constexpr int kMergeBatch = 8;    // 16-byte loads in flight per thread (registe
 constexpr int kMergeMaxPart = 32;  // row partitions per column pair
 constexpr int kMaxMergers = 16;
 
+// One 8-byte result word as two cells in mapped host memory: (low half | epoch << 32), (high half | epoch << 32).  A
+// 64-bit store is single-copy atomic, so a cell whose upper half shows this call's epoch carries this call's data: no
+// fence.sys (which waits for the posted PCIe writes to be acknowledged: ~2 us each, two per step) and no completion word.
+__device__ __forceinline__ void st_host_cells(unsigned long long* cells, int idx, unsigned long long bits, unsigned int epoch) {
+    const unsigned long long e = (unsigned long long)epoch << 32;
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(cells + 2 * idx), "l"((bits & 0xffffffffull) | e) : "memory");
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(cells + 2 * idx + 1), "l"((bits >> 32) | e) : "memory");
+}
+
 struct MergeOut {
     double* u_out;
     double* u_out_host;
@@ -231,6 +244,7 @@ struct MergeOut {
     int n_copies, copy_skip;
     unsigned int* done_host;  // [nm] completion words (mapped host memory) or nullptr
     unsigned int epoch;
+    unsigned long long* host_cells;  // MppiParams::host_cells (mppi_warp_merge only)
     int forced_status;
     unsigned long long* ts;
 };
@@ -649,10 +663,12 @@ static __device__ __forceinline__ int mppi_warp_merge(const double* rows, long l
         const double u0 = (status == MPCB_OK) ? ax / s : 0.0;
         const double u1 = (status == MPCB_OK) ? ay / s : 0.0;
         o.u_out[t0] = u0;
-        if (o.u_out_host) o.u_out_host[t0] = u0;
+        if (o.host_cells) st_host_cells(o.host_cells, t0, (unsigned long long)__double_as_longlong(u0), o.epoch);
+        else if (o.u_out_host) o.u_out_host[t0] = u0;
         if (t0 + 1 < H) {
             o.u_out[t0 + 1] = u1;
-            if (o.u_out_host) o.u_out_host[t0 + 1] = u1;
+            if (o.host_cells) st_host_cells(o.host_cells, t0 + 1, (unsigned long long)__double_as_longlong(u1), o.epoch);
+            else if (o.u_out_host) o.u_out_host[t0 + 1] = u1;
         }
         if (write_info) {
             mpcb_mppi_info out;
@@ -663,7 +679,16 @@ static __device__ __forceinline__ int mppi_warp_merge(const double* rows, long l
             out.sum = s;
             out.n_finite = (long long)nf;
             *o.info = out;
-            if (o.info_host) *o.info_host = out;
+            if (o.host_cells) {
+                static_assert(sizeof(mpcb_mppi_info) == 40, "five 8-byte words");
+                st_host_cells(o.host_cells, H + 0, (unsigned long long)(unsigned int)out.status, o.epoch);
+                st_host_cells(o.host_cells, H + 1, (unsigned long long)out.argmax, o.epoch);
+                st_host_cells(o.host_cells, H + 2, (unsigned long long)__double_as_longlong(out.max), o.epoch);
+                st_host_cells(o.host_cells, H + 3, (unsigned long long)__double_as_longlong(out.sum), o.epoch);
+                st_host_cells(o.host_cells, H + 4, (unsigned long long)out.n_finite, o.epoch);
+            } else if (o.info_host) {
+                *o.info_host = out;
+            }
         }
     }
     return status;
@@ -931,7 +956,7 @@ __device__ __forceinline__ void mppi_block_tail(const MppiParams& p, int c, int 
     MergeOut none;
     none.u_out = nullptr; none.u_out_host = nullptr; none.info = nullptr; none.info_host = nullptr; none.out_row = nullptr;
     none.copy_rows = nullptr; none.copy_offset = 0; none.n_copies = 0; none.copy_skip = -2;
-    none.done_host = nullptr; none.epoch = 0u; none.forced_status = MPCB_OK; none.ts = nullptr;
+    none.done_host = nullptr; none.epoch = 0u; none.forced_status = MPCB_OK; none.ts = nullptr; none.host_cells = nullptr;
     if (pair_major) {
         // ---- single-level merge by warps, no block barrier after the arrival (mppi_warp_merge): merger block mi owns
         // the column pairs [1 + mi*cp, 1 + (mi+1)*cp), one warp per pair; every warp waits for the arrivals itself ----
@@ -952,6 +977,8 @@ __device__ __forceinline__ void mppi_block_tail(const MppiParams& p, int c, int 
         fo.info = p.info + c;
         fo.info_host = p.info_host ? p.info_host + c : nullptr;
         fo.out_row = p.rank_partial ? p.rank_partial + (long long)c * PL : nullptr;
+        fo.host_cells = p.host_cells;  // (C == 1)
+        fo.epoch = p.epoch;
         if (wid < p_hi - p_lo || (wid == 0 && p.done_host)) {  // warps with a pair (warp 0 also signs off for the block)
             const unsigned int want = p.seq * (unsigned int)p.chunks;
             bool timed_out = false;
@@ -988,7 +1015,7 @@ __device__ __forceinline__ void mppi_block_tail(const MppiParams& p, int c, int 
             if (p.final_mode == FINAL_RANK_ROW && mi == 0 && tid == 0 && PL > kPartialHdr + H) fo.out_row[kPartialHdr + H] = 0.0;
             if (dbg != nullptr && tid == 0) dbg[11] = globaltimer_ns();
         }
-        if (p.done_host && p.final_mode != FINAL_RANK_ROW) {
+        if (p.done_host && p.host_cells == nullptr && p.final_mode != FINAL_RANK_ROW) {
             // results of every warp of this merger first, then its completion word the host spins on
             __threadfence_system();
             __syncthreads();

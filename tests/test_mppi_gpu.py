@@ -646,3 +646,30 @@ def test_short_horizon_kernel_error_semantics(gpu_required, monkeypatch):
                 assert rel_err(u_g, u_o) < 1e-8, rel_err(u_g, u_o)
 
     check()
+
+
+def test_host_cells_equal_completion_words(gpu_required, monkeypatch):
+    """The host hand-over of a single-controller compute: results as self-validating cells in mapped host memory (the
+    default with the single-level warp merge) against the round-1 protocol (plain stores, fence.sys, completion words:
+    MPCB_MPPI_HOST_CELLS=0) — bitwise the same controls and info over several calls, for a step that fails too."""
+    model, oid, H, dt, lam, sig, lim = CASES["NL_h100"]
+    runs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MPCB_MPPI_HOST_CELLS", mode)
+        got = []
+        for prec, K in (("f32", 65536), ("f64", 20000), ("f32", 333)):
+            with Mppi(H, K, model=model, lam=lam, std_dev=sig, limit=lim, precision=prec, dt=dt, seed=11) as m:
+                u = np.zeros(H)
+                for _ in range(5):
+                    u = m.compute(X0, u)
+                    got.append((u.copy(), dict(m.last_call_info()[0])))
+                bad = X0.copy()
+                bad[2] = np.nan
+                with pytest.raises(MppiError) as ei:
+                    m.compute(bad, u)
+                got.append((np.zeros(1), {"status": ei.value.status}))
+                got.append((m.compute(X0, u).copy(), dict(m.last_call_info()[0])))  # and the handle keeps working
+        runs[mode] = got
+    assert len(runs["1"]) == len(runs["0"])
+    for (ua, ia), (ub, ib) in zip(runs["1"], runs["0"]):
+        assert np.array_equal(ua, ub) and ia == ib
