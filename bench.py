@@ -13,7 +13,7 @@ per control step instead).
     value     device-resident closed loop (u_out of step i is u_in of step i+1), CUDA events per step on the
               handle's stream, L2 flushed between timed steps, max over ranks
     e2e       the same step through the C-ABI call mpcb_mppi_compute with HOST buffers (inputs travel in the kernel
-              parameters, u_out/info come back through mapped pinned memory and a completion word), host wall clock
+              parameters, u_out/info come back through mapped pinned memory as self-validating cells the host polls), host wall clock
               around a compiled closed loop (tools/e2e_loop.c, like the reference's compiled callers); the same loop
               written in Python is reported next to it (python_loop_value)
     roofline  algorithmic FP32 flops (60 per rollout-step) / kernel time vs the FFMA peak measured

@@ -101,8 +101,9 @@ def test_sass_has_the_instructions_the_design_relies_on():
     m = sass("mppi_f32x2_NL.o", "_ZN4mpcb19mppi_rollout_kernelINS_7ModelNLEfLi256ELi0ELi2ELb1EEEvNS_10MppiParamsE")
     assert m.count("FFMA2") > 100 and m.count("FMUL2") > 50, (m.count("FFMA2"), m.count("FMUL2"))
     assert "MUFU.SIN" in m and "MUFU.LG2" in m          # Box-Muller on the special-function unit
-    # the only local memory is the MergeOut argument block of the out-of-line merge functions (the 176-byte frame)
-    assert m.count(" LDL") + m.count(" STL") < 120, (m.count(" LDL"), m.count(" STL"))
+    # the only local memory is the MergeOut argument block of the out-of-line merge functions (the 184-byte frame: one
+    # more pointer since the host-cell hand-over) and the merge tail's spill slots
+    assert m.count(" LDL") + m.count(" STL") < 132, (m.count(" LDL"), m.count(" STL"))
     w = sass("mppi_ws_NL.o", "_ZN4mpcb14mppi_ws_kernelINS_7ModelNLELi7ELi9ELi0ELi2EEEvNS_10MppiParamsE")
     assert w.count("FFMA2") > 100 and "SYNCS" in w      # packed consumers; mbarrier hand-over between producer and consumer warps
     assert w.count("IMAD.WIDE.U32") >= 14               # Philox4x32-7: one wide multiply per 32x32->64 product
