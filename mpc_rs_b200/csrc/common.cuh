@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/mpc_b200.h"
@@ -41,10 +42,41 @@ struct ModelConsts {
 // Fills the constants for `model_id` from the physical parameter block, in the reference's association order.
 mpcb_status build_model_consts(int model_id, const mpcb_model_params& p, double dt, ModelConsts* out);
 
+#ifndef __CUDACC_RTC__
+// Launches a step kernel with programmatic stream serialization allowed (see pdl_entry below); MPCB_PDL=0 launches plainly.
+inline cudaError_t launch_pdl(const void* fn, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t stream) {
+    static const bool on = [] {
+        const char* e = getenv("MPCB_PDL");
+        return !(e && atoi(e) == 0);
+    }();
+    if (!on) return cudaLaunchKernel(fn, grid, block, args, smem, stream);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelExC(&cfg, fn, args);
+}
+#endif
+
 constexpr int kMaxHorizon = 512;
 constexpr int kInlineHorizon = 256;  // u_in up to this length travels inside the kernel parameters
 
 #ifdef __CUDACC__
+// Programmatic dependent launch (the step kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization,
+// api_common: launch_pdl): the NEXT launch of the stream may be scheduled onto SMs this grid has left as soon as every
+// block of this grid has passed this point, and this grid touches global memory only after the PREVIOUS grid has
+// completed and flushed.  What overlaps is the launch itself (block scheduling, parameter upload: 2-3 us per launch of a
+// back-to-back device loop), never the work.  Both instructions are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_entry() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 // ---- warp / block primitives ----
 __device__ __forceinline__ double shfl_down_f64(double v, int off) {
     int lo = __double2loint(v), hi = __double2hiint(v);

@@ -447,7 +447,7 @@ mpcb_status launch(mpcb_mppi* h, MppiParams& p) {
     p.seq = h->seq;
     // explicit cudaLaunchKernel: `fn` is either a compiled-in __global__ function or the cudaKernel_t of a user model
     void* args[1] = {&p};
-    MPCB_CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(fn), grid, block, args, h->smem, h->stream));
+    MPCB_CUDA_TRY(launch_pdl(reinterpret_cast<const void*>(fn), grid, block, args, h->smem, h->stream));
     h->launches += 1;
     h->call_idx += 1;
     h->costs_valid = h->cfg.keep_costs != 0;

@@ -1140,6 +1140,7 @@ __device__ __forceinline__ void mppi_block_tail(const MppiParams& p, int c, int 
 // 128 per SM) — the multi-batch shapes use it, so that the packed kernels keep >= 8 warps per SM at any horizon.
 template <template <typename> class ModelT, typename real, int BLOCK, int NOISE, int SPT, bool VT>
 __global__ void __launch_bounds__(BLOCK, (512 / BLOCK > 0 ? 512 / BLOCK : 1)) mppi_rollout_kernel(const __grid_constant__ MppiParams p) {
+    pdl_entry();
     static_assert(SPT == 1 || (SPT == 2 && sizeof(real) == 4), "two samples per thread is an FP32 layout");
     constexpr int NW = BLOCK / 32;
     constexpr int SB = BLOCK * SPT;  // samples per batch

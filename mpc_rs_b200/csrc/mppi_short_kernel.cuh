@@ -26,6 +26,7 @@ constexpr int kShortHorizon = 8;
 
 template <template <typename> class ModelT, int BLOCK, int NOISE, int HMAX>
 __global__ void __launch_bounds__(BLOCK, MPCB_SHORT_MINB) mppi_short_kernel(const __grid_constant__ MppiParams p) {
+    pdl_entry();
     using real = double;
     static_assert(HMAX % 4 == 0 && HMAX <= 16, "whole Philox blocks, registers");
     constexpr int NW = BLOCK / 32;

@@ -76,6 +76,7 @@ __host__ __device__ inline size_t mppi_ws_smem_bytes(int H, int ncw, int npw, in
 // NCW consumer warps, NPW producer warps, SPT samples per consumer thread; SB = 32 * NCW * SPT samples per batch.
 template <template <typename> class ModelT, int NCW, int NPW, int NOISE, int SPT>
 __global__ void __launch_bounds__((NCW + NPW) * 32, 1) mppi_ws_kernel(const __grid_constant__ MppiParams p) {
+    pdl_entry();
     constexpr int NT = (NCW + NPW) * 32;
     constexpr int NWT = NCW + NPW;
     constexpr int NPT = NPW * 32;

@@ -134,7 +134,7 @@ mpcb_status launch(mpcb_ukf* h, UkfKernelFn fn, const UkfParams& p) {
     UkfParams pp = p;
     void* args[1] = {&pp};
     const size_t smem = (fn == h->k_fused) ? h->fused_smem : 0;
-    MPCB_CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(fn), dim3(grid), dim3(kThreads), args, smem, h->stream));
+    MPCB_CUDA_TRY(launch_pdl(reinterpret_cast<const void*>(fn), dim3(grid), dim3(kThreads), args, smem, h->stream));
     h->launches += 1;
     return MPCB_OK;
 }

@@ -644,6 +644,7 @@ constexpr int kUkfThreads = 128;
 // while tile t is computed (PIPE).  The other modes and n = 6 (FP64-bound, 2x the rows) load directly.
 template <int N, int O, int MODEL, int SQRT, int ORDER, int MODE, bool FAST>
 __global__ void __launch_bounds__(kUkfThreads) ukf_kernel(const __grid_constant__ UkfParams p) {
+    pdl_entry();
     constexpr int M = 2 * N + 1;
     // predict never reads the strictly-upper triangle of P (the Cholesky / eigen square root take the lower one, the
     // unscented transform then rewrites P entirely), so the fused and predict kernels do not load it: 288 instead of

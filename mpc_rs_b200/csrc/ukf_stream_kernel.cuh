@@ -114,6 +114,7 @@ __host__ __device__ constexpr size_t ukf_stream_smem_bytes() { return (size_t)N 
 
 template <int N, int O, int MODEL, int SQRT>
 __global__ void __launch_bounds__(kUkfThreads, 2) ukf_stream_kernel(const __grid_constant__ UkfParams p) {
+    pdl_entry();
     constexpr int M2 = 2 * N;  // columns j = x + L_j, N + j = x - L_j (library order, src/ukf2.rs:129-135, without the centre)
     extern __shared__ __align__(16) double s_sig[];  // [N * M2][kUkfThreads]: this thread's sigma points, row-major (r * M2 + c)
     const long long B = p.B;

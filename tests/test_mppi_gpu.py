@@ -673,3 +673,42 @@ def test_host_cells_equal_completion_words(gpu_required, monkeypatch):
     assert len(runs["1"]) == len(runs["0"])
     for (ua, ia), (ub, ib) in zip(runs["1"], runs["0"]):
         assert np.array_equal(ua, ub) and ia == ib
+
+
+def test_back_to_back_device_steps_equal_synchronised_steps(gpu_required):
+    """The step kernels are launched with programmatic stream serialization (common.cuh: launch_pdl / pdl_entry): the next
+    launch may be scheduled while the previous grid drains, and touches memory only after it has completed.  Twelve
+    device-resident steps enqueued back to back (u_out of step i is u_in of step i + 1) must give bitwise what the same
+    steps give with a stream sync after each — for the warp-specialised kernel of configs[1], the fused multi-batch
+    kernel, the FP64 short-horizon kernel and several controllers."""
+    import ctypes as C
+    L = A.lib()
+
+    def dev(arr):
+        p = C.c_void_p()
+        A.check(L.mpcb_device_alloc(0, arr.nbytes, C.byref(p)))
+        A.check(L.mpcb_device_upload(0, p, arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+        return p
+
+    cases = [("NL_h100", 65536, "f32", 1), ("NL_h100", 300001, "f32", 1), ("NL6_shipped", 8192, "f64fast", 40),
+             ("NL_shipped", 20000, "f64", 1)]
+    for case, K, prec, Cn in cases:
+        model, oid, H, dt, lam, sig, lim = CASES[case]
+        x = np.tile(X0, (Cn, 1))
+        outs = []
+        for synced in (False, True):
+            with Mppi(H, K, model=model, lam=lam, std_dev=sig, limit=lim, precision=prec, dt=dt, seed=5, controllers=Cn) as m:
+                d_x, d_a, d_b = dev(x), dev(np.zeros((Cn, H))), dev(np.zeros((Cn, H)))
+                for i in range(12):
+                    m.compute_device(d_x.value, (d_a if i % 2 == 0 else d_b).value, (d_b if i % 2 == 0 else d_a).value)
+                    if synced:
+                        m.sync()
+                m.sync()
+                u = np.zeros((Cn, H))
+                A.check(L.mpcb_device_download(0, u.ctypes.data_as(C.c_void_p), d_a, u.nbytes))
+                outs.append((u, m.last_info()))
+                for p in (d_x, d_a, d_b):
+                    L.mpcb_device_free(0, p)
+        assert np.array_equal(outs[0][0], outs[1][0]), (case, K, prec)
+        assert outs[0][1] == outs[1][1]
+        assert all(i["status"] == 0 for i in outs[0][1]) and np.all(np.isfinite(outs[0][0]))
