@@ -23,6 +23,15 @@ L.mpcb_device_upload(0, p, xu.ctypes.data_as(C.c_void_p), xu.nbytes)
 for _ in range(5):
     m.compute_device(p.value, p.value + 32, p.value + 32 + 8 * H)
 m.sync()
+if len(sys.argv) > 3 and sys.argv[3] == "cold":
+    # the stamped launch after an L2 flush (what bench.py's `value` times): a 512 MB fill on the same device, then one step
+    import torch
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda:0")
+    flush.fill_(1)
+    torch.cuda.synchronize()
+    m.compute_device(p.value, p.value + 32, p.value + 32 + 8 * H)
+    m.sync()
+    print("(cold: after an L2 flush)")
 buf = np.zeros((4096, 16), dtype=np.uint64)
 n = L.mpcb_mppi_debug_timeline(m._h, buf.ctypes.data_as(C.c_void_p), 4096)
 ts = buf[:n].astype(np.int64)
