@@ -63,8 +63,9 @@ struct mpcb_mppi {
     mpcb_mppi_info* h_info_dev = nullptr;
     unsigned int* h_done = nullptr;      // mapped completion word the host spins on (C == 1)
     unsigned int* h_done_dev = nullptr;
-    // C == 1 with the single-level warp merge: results as self-validating cells (MppiParams::host_cells), no fence, no word
-    unsigned long long* h_cells = nullptr;      // mapped: [2 * (H + 5)]
+    // host-facing calls whose final merge is the single-level warp merge: results as self-validating cells
+    // (MppiParams::host_cells) instead of fence + completion words (C == 1) or a stream sync (C > 1)
+    unsigned long long* h_cells = nullptr;      // mapped: [C][2 * (H + 5)]
     unsigned long long* h_cells_dev = nullptr;
     bool use_cells = false;
     unsigned int epoch = 0;
@@ -489,13 +490,15 @@ mpcb_status stage_inputs(mpcb_mppi* h, MppiParams& p, const double* x, const dou
 mpcb_status finish_host(mpcb_mppi* h, double* u_out, mpcb_mppi_info* info, bool spin, int words, bool cells = false) {
     bool done = false;
     if (cells) {
-        // every result word arrives as two cells (half | epoch << 32): wait for each cell to show this call's epoch
-        const volatile unsigned long long* cell = h->h_cells;
+        // every result word arrives as two cells (half | epoch << 32): wait for each cell to show this call's epoch;
+        // controller c owns the cells [c * 2 (H + 5), (c + 1) * 2 (H + 5))
         const unsigned long long want = h->epoch;
         const int nwords = h->H + 5;
         unsigned long long out[kMaxHorizon + 5];
         long budget = 4000000;
-        for (int pass = 0; pass < 2 && !done; ++pass) {
+        bool synced = false;
+        for (long long c = 0; c < h->C; ++c) {
+            const volatile unsigned long long* cell = h->h_cells + (size_t)c * 2 * nwords;
             int i = 0;
             while (i < nwords) {
                 const unsigned long long lo = cell[2 * i], hi = cell[2 * i + 1];
@@ -504,26 +507,26 @@ mpcb_status finish_host(mpcb_mppi* h, double* u_out, mpcb_mppi_info* info, bool 
                     ++i;
                     continue;
                 }
-                if (--budget <= 0) break;
-                cpu_relax();
-            }
-            done = (i == nwords);
-            if (!done) {  // ~2 ms without the results: the stream sync surfaces a launch / runtime error, then one more look
+                if (--budget > 0) {
+                    cpu_relax();
+                    continue;
+                }
+                if (synced) {
+                    set_error("MPPI results did not reach the host cells (epoch %u, controller %lld)", h->epoch, c);
+                    return MPCB_CUDA_ERROR;
+                }
+                // ~2 ms without the results: the stream sync surfaces a launch / runtime error, then one more look
                 MPCB_CUDA_TRY(cudaStreamSynchronize(h->stream));
+                synced = true;
                 budget = 1000;
             }
+            memcpy(u_out + (size_t)c * h->H, out, (size_t)h->H * sizeof(double));
+            memcpy(h->h_out + (size_t)c * h->H, out, (size_t)h->H * sizeof(double));
+            memcpy(&h->h_info[c], out + h->H, sizeof(mpcb_mppi_info));  // mpcb_mppi_last_info reads the mirror
         }
-        if (!done) {
-            set_error("MPPI results did not reach the host cells (epoch %u)", h->epoch);
-            return MPCB_CUDA_ERROR;
-        }
-        memcpy(u_out, out, (size_t)h->H * sizeof(double));
-        mpcb_mppi_info hi_;
-        memcpy(&hi_, out + h->H, sizeof(hi_));
-        h->h_info[0] = hi_;  // mpcb_mppi_last_info reads the mirror
-        memcpy(h->h_out, out, (size_t)h->H * sizeof(double));
-        if (info) *info = hi_;
-        return (mpcb_status)hi_.status;
+        if (info) memcpy(info, h->h_info, (size_t)h->C * sizeof(mpcb_mppi_info));
+        if (h->C == 1) return (mpcb_status)h->h_info[0].status;
+        return MPCB_OK;
     }
     if (spin) {
         // one completion word per merger block of the final merge
@@ -588,8 +591,11 @@ mpcb_status compute_host(mpcb_mppi* h, const double* x, const double* u_in, cons
         if (peer) set_peer_params(h, p);
     }
     // the single-level warp merge (the condition of `pair_major` in mppi_block_tail) hands the results over as cells
-    const bool cells = spin && h->use_cells && h->groups == 1 && h->mergers >= 1 && (!sharded || (peer && h->peer_ll));
-    if (cells) p.host_cells = h->h_cells_dev;
+    const bool cells = h->use_cells && h->groups == 1 && h->mergers >= 1 && (!sharded || (peer && h->peer_ll));
+    if (cells) {
+        p.host_cells = h->h_cells_dev;
+        p.epoch = h->epoch;
+    }
     st = launch(h, p);
     if (st != MPCB_OK) return st;
     if (sharded && !peer) {
@@ -792,8 +798,8 @@ static mpcb_status create_impl(mpcb_mppi** out, const mpcb_mppi_cfg* cfg, const 
     TRY_OR_FAIL(cudaHostAlloc(&h->h_done, 64, cudaHostAllocMapped));
     memset(h->h_done, 0, 64);
     TRY_OR_FAIL(cudaHostGetDevicePointer((void**)&h->h_done_dev, h->h_done, 0));
-    if (C == 1) {
-        const size_t cell_bytes = 2 * (H + 5) * sizeof(unsigned long long);
+    if (C * (H + 5) <= 32768) {  // (half a megabyte of cells at most: larger fleets keep the stream sync)
+        const size_t cell_bytes = C * 2 * (H + 5) * sizeof(unsigned long long);
         TRY_OR_FAIL(cudaHostAlloc(&h->h_cells, cell_bytes, cudaHostAllocMapped));
         memset(h->h_cells, 0, cell_bytes);  // epoch 0 is never a call's epoch
         TRY_OR_FAIL(cudaHostGetDevicePointer((void**)&h->h_cells_dev, h->h_cells, 0));

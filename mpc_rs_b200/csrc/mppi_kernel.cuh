@@ -79,10 +79,10 @@ struct MppiParams {
     double* rank_partial;    // [C][kPartialHdr + H]
     unsigned int* done_host;       // mapped host word; the final block stores `epoch` after u_out/info (C == 1 only)
     unsigned int epoch, pad1;
-    // Host hand-over without a fence (C == 1, single-level warp merge): every 8-byte result word goes to mapped host
+    // Host hand-over without a fence (single-level warp merge): every 8-byte result word goes to mapped host
     // memory as two self-validating cells (data half | epoch << 32), one 64-bit store each; the host polls the cells
     // (mppi_api.cu finish_host).  nullptr: u_out_host / info_host + fence.sys + done_host words as before.
-    unsigned long long* host_cells;  // [2 * (H + 5)]: u_out[0..H), then the five words of mpcb_mppi_info
+    unsigned long long* host_cells;  // [C][2 * (H + 5)]: u_out[0..H), then the five words of mpcb_mppi_info
     // FINAL_PEER_EXCHANGE: device tables [G] of every rank's mailbox / flag base (own entry included)
     //   mailbox: [2 parity][G source ranks][C][kPartialHdr + H] doubles;  flags: [2][G][C] u32
     double* const* peer_mbox;
@@ -977,7 +977,7 @@ __device__ __forceinline__ void mppi_block_tail(const MppiParams& p, int c, int 
         fo.info = p.info + c;
         fo.info_host = p.info_host ? p.info_host + c : nullptr;
         fo.out_row = p.rank_partial ? p.rank_partial + (long long)c * PL : nullptr;
-        fo.host_cells = p.host_cells;  // (C == 1)
+        fo.host_cells = p.host_cells ? p.host_cells + (long long)c * 2 * (H + 5) : nullptr;
         fo.epoch = p.epoch;
         if (wid < p_hi - p_lo || (wid == 0 && p.done_host)) {  // warps with a pair (warp 0 also signs off for the block)
             const unsigned int want = p.seq * (unsigned int)p.chunks;

@@ -673,6 +673,24 @@ def test_host_cells_equal_completion_words(gpu_required, monkeypatch):
     assert len(runs["1"]) == len(runs["0"])
     for (ua, ia), (ub, ib) in zip(runs["1"], runs["0"]):
         assert np.array_equal(ua, ub) and ia == ib
+    # several controllers per call (cells instead of a stream sync), one of them failing: rows and per-controller info equal
+    Cn = 6
+    x = np.tile(X0, (Cn, 1))
+    x[2, 1] = np.nan
+    many = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MPCB_MPPI_HOST_CELLS", mode)
+        with Mppi(12, 4096, model=model, lam=lam, std_dev=sig, limit=lim, precision="f32", dt=0.05, seed=3, controllers=Cn) as m:
+            u = np.zeros((Cn, 12))
+            for _ in range(4):
+                u = m.compute(x, u)
+            many[mode] = (u.copy(), [dict(i) for i in m.last_call_info()])
+    assert np.array_equal(many["1"][0], many["0"][0])
+    for ia, ib in zip(many["1"][1], many["0"][1]):  # (a failed controller's sum / max may be NaN: compare NaN-aware)
+        assert ia.keys() == ib.keys()
+        assert all(np.array_equal(ia[k], ib[k], equal_nan=True) for k in ia), (ia, ib)
+    assert many["1"][1][2]["status"] != 0 and not many["1"][0][2].any()  # the failed controller's row is zero
+    assert all(i["status"] == 0 for k, i in enumerate(many["1"][1]) if k != 2) and np.all(np.isfinite(many["1"][0]))
 
 
 def test_back_to_back_device_steps_equal_synchronised_steps(gpu_required):
