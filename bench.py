@@ -591,7 +591,9 @@ def run_gpu(args):
                 f"peak = {peaks['fp32_source']}; neither 'hbm' nor 'tensor' bounds this kernel: it is bound by the SM's instruction "
                 "dispatch (66 issued instructions per rollout-step; this instruction mix caps at frac 0.36, and at 0.22 on this shape "
                 "with its fixed launch + merge tail, DESIGN.md 4.1b) and moves 71 KB of DRAM per launch (traffic: bytes, "
-                "this round's ncu capture); kernel_ms = back-to-back launches enqueued from compiled code, no L2 flush"
+                "this round's ncu capture); kernel_ms = launch-to-launch time of back-to-back launches enqueued from compiled code, no L2 flush; the launches carry "
+                "programmatic stream serialization, so the next grid is scheduled while the previous one drains (MPCB_PDL=0: plain launches, "
+                "+2.5 us); kernel_ms_with_l2_flush is the same step behind a 256 MiB fill, where nothing overlaps"
                 + ("; at N > 1 it includes the in-kernel cross-GPU exchange" if world > 1 else ""),
     }
     if ukf_out and "value" in ukf_out:
